@@ -1,0 +1,173 @@
+/*
+ * sdxl_b200.h — C ABI of libsdxl_b200.so: hand-written sm_100a kernels for the SDXL UNet training step.
+ *
+ * Drop-in boundary.  The reference has no native code and no FFI: its hot path is
+ * `self.model.unet(...)` + `loss.backward()` (src/training/trainers/methods/ddpm_trainer.py:320-325,:271;
+ * flow_matching_trainer.py:400-405,:252), which dispatch through diffusers -> torch -> cuDNN/cuBLAS/SDPA.
+ * Each entry below replaces the library kernel(s) that path reaches for one operator; the "replaces" note
+ * on every group names the reference call site / diffusers module it stands in for.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; all pointers are DEVICE pointers unless named host_*.
+ *   - every launch entry returns 0 on success, a negative code on failure; b2_last_error() (thread-local)
+ *     describes the last failure.  No allocation inside, no ownership transfer, no hidden syncs; all work
+ *     is enqueued on `stream` (a cudaStream_t passed as void*), so calls are CUDA-graph capturable.
+ *   - activations are token-major / NHWC: [B, H*W, C] bf16.  "ld*" / strides are in ELEMENTS.
+ *   - bf16 = __nv_bfloat16 (uint16_t storage).
+ */
+#ifndef SDXL_B200_H
+#define SDXL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_ARG (-1)
+#define B2_ERR_CUDA (-2)
+#define B2_ERR_TMAP (-3)
+
+int b2_version(void);
+const char* b2_last_error(void);
+/* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
+long long b2_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM  (tcgen05.mma, TMEM accumulators, TMA-staged operands, 128xBN tiles)
+ *   D[z][m,n] = alpha * sum_k A[z][m,k] * B[z][n,k]  (+ bias) (+ residual) (+ D_old if accumulate)
+ * replaces: every torch.nn.Linear / 1x1 conv / (with b2_im2col3x3) 3x3 conv of the diffusers UNet, its
+ *   autograd dgrad/wgrad GEMMs, and the QK^T / PV batched matmuls of attention (cuBLASLt / cuDNN today).
+ *   a_mn / b_mn = 0: operand is K-major (k contiguous, ld = row stride);
+ *   a_mn / b_mn = 1: operand is MN-major (m or n contiguous, ld = stride between consecutive k).
+ *   Linear fwd: A=x[M,K] (K-major), B=W[N,K] (K-major).  dgrad: A=dY (K-major), B=W as [K_in rows... ] MN-major.
+ *   wgrad: A=dY^T (MN-major), B=x^T (MN-major).
+ *   batch index z = z_hi * nb_lo + z_lo with independent strides (attention: lo = head, hi = sample).
+ *   bias: bf16, indexed bias[(m / bias_rows_per_group) * bias_group_stride + n]  (plain bias: group_stride 0;
+ *         per-sample time-embedding row: rows_per_group = H*W, group_stride = N).
+ *   TMA constraints (checked): A/B base 16-byte aligned, lda/ldb/batch strides multiples of 8 elements.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b2_gemm_args {
+  const void* A;
+  const void* B;
+  void* D;
+  const void* bias;      /* bf16 or NULL */
+  const void* residual;  /* bf16, same indexing as D with ldr / r_bs_*; or NULL */
+  int32_t M, N, K;
+  int32_t nb_lo, nb_hi;  /* batch counts (>=1) */
+  int32_t a_mn, b_mn;
+  int64_t lda, ldb, ldd, ldr;
+  int64_t a_bs_lo, a_bs_hi, b_bs_lo, b_bs_hi, d_bs_lo, d_bs_hi, r_bs_lo, r_bs_hi;
+  float alpha;
+  int32_t accumulate;    /* 1: D += result (gradient accumulation into bf16/fp32 D) */
+  int32_t out_fp32;      /* 1: D is float, else bf16 */
+  int32_t bias_rows_per_group;
+  int64_t bias_group_stride;
+  int32_t tile_n;        /* 0 = auto, else 64 / 128 / 256 */
+} b2_gemm_args;
+
+int b2_gemm(const b2_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3x3 convolution support (implicit-GEMM operand staging; K ordering = (kh, kw, cin))
+ * replaces: torch Conv2d 3x3 (pad 1, stride 1|2) and Upsample2D's interpolate+conv in ResnetBlock2D /
+ *   Downsample2D / Upsample2D / conv_in / conv_out, and their cuDNN dgrad paths.
+ *   x: [B,H,W,C] bf16 -> col: [B*Ho*Wo, ldc] (ldc >= 9*C, multiple of 8; pad columns written as zero)
+ *   stride: 1 or 2.  upsample: 1 => the conv sees nearest-2x of x (Ho=2H, Wo=2W) without materialising it.
+ *   col2im is the exact adjoint (gather form): dx[B,H,W,C] (+)= sum over taps of dcol.
+ * ------------------------------------------------------------------------------------------------ */
+int b2_im2col3x3(const void* x, void* col, int B, int H, int W, int C, int stride, int upsample,
+                 int64_t ldc, void* stream);
+int b2_col2im3x3(const void* dcol, void* dx, int B, int H, int W, int C, int stride, int upsample,
+                 int64_t ldc, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU), NHWC.  replaces torch.nn.GroupNorm + F.silu in ResnetBlock2D / Transformer2DModel.norm /
+ *   conv_norm_out and their backward.
+ *   stats: ws = double[B*G*2] scratch (zeroed by the call); mean,rstd = float[B*G].
+ *   bwd:   dx = d/dx of silu?(gn(x)); dgamma/dbeta accumulated as fp32 into dgb[2*C] (caller zeroes,
+ *          then folds into the bf16 grads with b2_accum_f32_to_bf16).
+ * ------------------------------------------------------------------------------------------------ */
+int b2_gn_stats(const void* x, int B, int HW, int C, int G, float eps, void* ws, float* mean, float* rstd,
+                void* stream);
+int b2_gn_apply(const void* x, void* y, const float* mean, const float* rstd, const void* gamma,
+                const void* beta, int B, int HW, int C, int G, int silu, void* stream);
+int b2_gn_bwd(const void* x, const void* dy, void* dx, const float* mean, const float* rstd,
+              const void* gamma, const void* beta, int B, int HW, int C, int G, int silu,
+              void* ws /* double[B*G*2] */, float* dgb /* float[2*C], accumulated */, int accumulate_dx,
+              void* stream);
+
+/* LayerNorm over the last dim. replaces torch.nn.LayerNorm(C, eps=1e-5) x210 and backward. */
+int b2_ln_fwd(const void* x, void* y, const void* gamma, const void* beta, float* mean, float* rstd,
+              int M, int C, float eps, void* stream);
+int b2_ln_bwd(const void* x, const void* dy, void* dx, const void* gamma, const float* mean,
+              const float* rstd, float* dgb /* float[2*C], accumulated */, int M, int C, int accumulate_dx,
+              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention softmax over materialised logits (round-1 path; the fused flash kernel supersedes it).
+ * replaces the softmax inside F.scaled_dot_product_attention (attention_processor.AttnProcessor2_0).
+ *   S: float [rows, lds] (already scaled); P: bf16 [rows, ldp]; columns >= n_valid of P are written 0.
+ *   bwd: dS = P * (dP - rowsum(dP*P)) * scale ; dP float [rows, lds], dS bf16 [rows, ldp].
+ * ------------------------------------------------------------------------------------------------ */
+int b2_softmax_fwd(const float* S, void* P, int64_t rows, int n_valid, int64_t lds, int64_t ldp, void* stream);
+int b2_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int n_valid, int64_t lds,
+                   int64_t ldp, float scale, void* stream);
+
+/* GEGLU: z[m, j] = u[m, j] * gelu_erf(u[m, F + j]), u: [M, 2F]. replaces diffusers GEGLU.forward + backward. */
+int b2_geglu_fwd(const void* u, void* z, int64_t M, int F, void* stream);
+int b2_geglu_bwd(const void* u, const void* dz, void* du, int64_t M, int F, void* stream);
+
+/* Elementwise / plumbing */
+int b2_silu_fwd(const void* x, void* y, int64_t n, void* stream);
+int b2_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, int accumulate, void* stream);
+int b2_add(const void* a, const void* b, void* out, int64_t n, void* stream);              /* out = a + b */
+int b2_copy2d(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd,
+              int accumulate, void* stream);                                                  /* bf16 */
+int b2_colsum(const void* dy, void* db, int64_t M, int N, int64_t ld, int accumulate, float* ws /* float[N] */,
+              void* stream);                                                                  /* db[n] (+)= sum_m dy[m,n] */
+int b2_accum_f32_to_bf16(const float* src, void* dst, int64_t n, int accumulate, void* stream);
+int b2_nchw_to_nhwc(const void* x, int x_fp32, void* y, int B, int C, int HW, int Cpad, void* stream);
+int b2_nhwc_to_nchw(const void* x, void* y, int y_fp32, int B, int C, int HW, int Cpad, void* stream);
+
+/* Timestep sinusoid (diffusers get_timestep_embedding, flip_sin_to_cos=True, freq_shift=0):
+ *   out[i, :] = [cos(t_i f_k), sin(t_i f_k)], f_k = exp(-ln(1e4) k / half); t float[n]; out bf16 [n, ldo]. */
+int b2_timestep_embedding(const float* t, void* out, int n, int dim, int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Noise / noising / loss   (reference: ddpm_trainer.py:303-345,380-384; flow_matching_trainer.py:298-335;
+ *   novelai_v3.py:111-127).  Philox4x32-10 counter RNG, Box-Muller; `seed`,`offset` read from device memory
+ *   (uint64[2]) so that a captured CUDA graph draws fresh noise per replay.
+ *   b2_randn:  out fp32[n] ~ N(0,1), optionally rounded through bf16 (the reference draws in model dtype).
+ *   b2_make_noisy: mode 0 (ddpm): noisy = clamp?(x + sigma[t_b] * eps) ; target = eps | (eps - x)/sigma
+ *                  mode 1 (flow): noisy = (1-t_b) eps + t_b x          ; target = x - eps
+ *       x fp32 NCHW [B, CHW]; writes noisy as bf16 NHWC-padded [B,HW,Cpad] and target fp32 NCHW.
+ *   b2_mse_loss: pred bf16 NHWC-padded vs target fp32 NCHW; weight[b] optional;
+ *       loss_sum += sum w_b (pred-target)^2 (double); dpred (bf16 NHWC-padded) = 2 w_b (pred-target) * gscale.
+ *   b2_finalize_loss: loss = sum/count * scale; non-finite or > 1000 -> 1000, ok=0 and dpred zeroed (the
+ *       reference's clamp / fallback pass no gradient); else loss, ok=1.
+ * ------------------------------------------------------------------------------------------------ */
+int b2_randn(float* out, int64_t n, const uint64_t* seed_offset, uint64_t stream_id, int round_bf16, void* stream);
+int b2_philox_advance(uint64_t* seed_offset, uint64_t inc, void* stream);   /* seed_offset[1] += inc (graph-safe) */
+int b2_make_noisy(const float* x, const float* eps, const float* sigma_or_t, int mode, int v_prediction,
+                  int clamp_ztsnr, void* noisy, float* target, int B, int C, int HW, int Cpad, void* stream);
+int b2_mse_loss(const void* pred, const float* target, const float* weight, double* loss_sum, void* dpred,
+                float gscale, int B, int C, int HW, int Cpad, void* stream);
+int b2_finalize_loss(const double* loss_sum, double count, float scale, float* loss_out, int32_t* ok,
+                     void* dpred /* zeroed when !ok; may be NULL */, int64_t n_dpred, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer side: global grad-norm and fused AdamW over the flat bf16 buffers.
+ *   b2_sumsq: out(double) += sum g^2.  b2_adamw: decoupled weight decay, bias-corrected, fp32 m/v,
+ *   clip coefficient computed on device from *gnorm_sq (max_norm <= 0: no clipping).
+ * ------------------------------------------------------------------------------------------------ */
+int b2_sumsq(const void* g, int64_t n, double* out, void* stream);
+int b2_adamw(void* p, float* master /* fp32 master weights or NULL */, const void* g, float* m, float* v, int64_t n,
+             float lr, float beta1, float beta2, float eps, float weight_decay, int step, const double* gnorm_sq,
+             float max_norm, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDXL_B200_H */

@@ -1,0 +1,93 @@
+"""ctypes binding of libsdxl_b200.so (include/sdxl_b200.h).  No CPU fallback: a missing library raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsdxl_b200.so")
+
+c_p = C.c_void_p
+i32, i64, f32, f64, u64 = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_uint64
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", c_p), ("B", c_p), ("D", c_p), ("bias", c_p), ("residual", c_p),
+        ("M", i32), ("N", i32), ("K", i32),
+        ("nb_lo", i32), ("nb_hi", i32),
+        ("a_mn", i32), ("b_mn", i32),
+        ("lda", i64), ("ldb", i64), ("ldd", i64), ("ldr", i64),
+        ("a_bs_lo", i64), ("a_bs_hi", i64), ("b_bs_lo", i64), ("b_bs_hi", i64),
+        ("d_bs_lo", i64), ("d_bs_hi", i64), ("r_bs_lo", i64), ("r_bs_hi", i64),
+        ("alpha", f32), ("accumulate", i32), ("out_fp32", i32),
+        ("bias_rows_per_group", i32), ("bias_group_stride", i64),
+        ("tile_n", i32),
+    ]
+
+
+# name -> argtypes (return type is int unless listed in _RESTYPES); mirrors include/sdxl_b200.h one to one.
+SIGNATURES = {
+    "b2_version": [],
+    "b2_last_error": [],
+    "b2_launch_count": [],
+    "b2_gemm": [C.POINTER(GemmArgs), c_p],
+    "b2_im2col3x3": [c_p, c_p, i32, i32, i32, i32, i32, i32, i64, c_p],
+    "b2_col2im3x3": [c_p, c_p, i32, i32, i32, i32, i32, i32, i64, i32, c_p],
+    "b2_gn_stats": [c_p, i32, i32, i32, i32, f32, c_p, c_p, c_p, c_p],
+    "b2_gn_apply": [c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, c_p],
+    "b2_gn_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, c_p, c_p, i32, c_p],
+    "b2_ln_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, f32, c_p],
+    "b2_ln_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, i32, c_p],
+    "b2_softmax_fwd": [c_p, c_p, i64, i32, i64, i64, c_p],
+    "b2_softmax_bwd": [c_p, c_p, c_p, i64, i32, i64, i64, f32, c_p],
+    "b2_geglu_fwd": [c_p, c_p, i64, i32, c_p],
+    "b2_geglu_bwd": [c_p, c_p, c_p, i64, i32, c_p],
+    "b2_silu_fwd": [c_p, c_p, i64, c_p],
+    "b2_silu_bwd": [c_p, c_p, c_p, i64, i32, c_p],
+    "b2_add": [c_p, c_p, c_p, i64, c_p],
+    "b2_copy2d": [c_p, c_p, i64, i64, i64, i64, i32, c_p],
+    "b2_colsum": [c_p, c_p, i64, i32, i64, i32, c_p, c_p],
+    "b2_accum_f32_to_bf16": [c_p, c_p, i64, i32, c_p],
+    "b2_nchw_to_nhwc": [c_p, i32, c_p, i32, i32, i32, i32, c_p],
+    "b2_nhwc_to_nchw": [c_p, c_p, i32, i32, i32, i32, i32, c_p],
+    "b2_timestep_embedding": [c_p, c_p, i32, i32, i64, c_p],
+    "b2_randn": [c_p, i64, c_p, u64, i32, c_p],
+    "b2_philox_advance": [c_p, u64, c_p],
+    "b2_make_noisy": [c_p, c_p, c_p, i32, i32, i32, c_p, c_p, i32, i32, i32, i32, c_p],
+    "b2_mse_loss": [c_p, c_p, c_p, c_p, c_p, f32, i32, i32, i32, i32, c_p],
+    "b2_finalize_loss": [c_p, f64, f32, c_p, c_p, c_p, i64, c_p],
+    "b2_sumsq": [c_p, i64, c_p, c_p],
+    "b2_adamw": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, c_p, f32, f32, c_p],
+}
+_RESTYPES = {"b2_last_error": C.c_char_p, "b2_launch_count": C.c_longlong}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for the sm_100a kernels)")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().b2_last_error()
+        raise RuntimeError(f"libsdxl_b200 {what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().b2_launch_count())

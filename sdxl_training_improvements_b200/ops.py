@@ -1,0 +1,284 @@
+"""Thin Python wrappers: torch tensors (device memory + stream only) -> C-ABI calls of libsdxl_b200.so.
+
+Every function enqueues hand-written sm_100a kernels on torch's current CUDA stream; nothing here computes
+with torch ops.  Shapes follow the token-major convention [B*H*W, C] bf16.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+bf16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("sdxl_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+# --------------------------------------------------------------------------------------- GEMM
+def gemm_raw(A, B, D, M, N, K, *, a_mn=False, b_mn=False, lda, ldb, ldd, bias=None, residual=None, ldr=0,
+             nb_lo=1, nb_hi=1, a_bs=(0, 0), b_bs=(0, 0), d_bs=(0, 0), r_bs=(0, 0), alpha=1.0, accumulate=False,
+             out_fp32=False, bias_rows_per_group=0, bias_group_stride=0, tile_n=0):
+    _need_cuda(A, B, D, bias, residual)
+    lib = _lib.load()
+    g = _lib.GemmArgs()
+    g.A, g.B, g.D, g.bias, g.residual = _p(A), _p(B), _p(D), _p(bias), _p(residual)
+    g.M, g.N, g.K = int(M), int(N), int(K)
+    g.nb_lo, g.nb_hi = int(nb_lo), int(nb_hi)
+    g.a_mn, g.b_mn = int(a_mn), int(b_mn)
+    g.lda, g.ldb, g.ldd, g.ldr = int(lda), int(ldb), int(ldd), int(ldr)
+    g.a_bs_lo, g.a_bs_hi = int(a_bs[0]), int(a_bs[1])
+    g.b_bs_lo, g.b_bs_hi = int(b_bs[0]), int(b_bs[1])
+    g.d_bs_lo, g.d_bs_hi = int(d_bs[0]), int(d_bs[1])
+    g.r_bs_lo, g.r_bs_hi = int(r_bs[0]), int(r_bs[1])
+    g.alpha = float(alpha)
+    g.accumulate, g.out_fp32 = int(accumulate), int(out_fp32)
+    g.bias_rows_per_group, g.bias_group_stride = int(bias_rows_per_group), int(bias_group_stride)
+    g.tile_n = int(tile_n)
+    _lib.check(lib.b2_gemm(C.byref(g), _stream()), "b2_gemm")
+    return D
+
+
+def linear_fwd(x, W, bias=None, residual=None, out=None, *, bias_rows_per_group=0, bias_group_stride=0, ldw=None):
+    """out[M,N] = x[M,K] @ W[N,K]^T (+bias) (+residual).  x, W row-major (W may have row stride ldw)."""
+    M, K = x.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=bf16)
+    return gemm_raw(x, W, out, M, N, K, lda=x.stride(0), ldb=(ldw or W.stride(0)), ldd=out.stride(0), bias=bias,
+                    residual=residual, ldr=(residual.stride(0) if residual is not None else 0),
+                    bias_rows_per_group=bias_rows_per_group, bias_group_stride=bias_group_stride)
+
+
+def linear_dgrad(dy, W, dx=None, accumulate=False, *, K=None, ldw=None):
+    """dx[M,K] (+)= dy[M,N] @ W[N,K]."""
+    M, N = dy.shape
+    K = K or W.shape[1]
+    if dx is None:
+        dx = torch.empty((M, K), device=dy.device, dtype=bf16)
+        accumulate = False
+    return gemm_raw(dy, W, dx, M, K, N, a_mn=False, b_mn=True, lda=dy.stride(0), ldb=(ldw or W.stride(0)),
+                    ldd=dx.stride(0), accumulate=accumulate)
+
+
+def linear_wgrad(dy, x, dW, accumulate=True, *, ldw=None, K=None):
+    """dW[N,K] (+)= dy[M,N]^T @ x[M,K]."""
+    M, N = dy.shape
+    K = K or x.shape[1]
+    return gemm_raw(dy, x, dW, N, K, M, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0),
+                    ldd=(ldw or dW.stride(0)), accumulate=accumulate)
+
+
+# --------------------------------------------------------------------------------------- conv staging
+def conv_out_hw(H, W, stride=1, upsample=False):
+    Hin, Win = (2 * H, 2 * W) if upsample else (H, W)
+    return (Hin + 2 - 3) // stride + 1, (Win + 2 - 3) // stride + 1
+
+
+def im2col3x3(x, B, H, W, Cc, stride=1, upsample=False, out=None):
+    Ho, Wo = conv_out_hw(H, W, stride, upsample)
+    ldc = 9 * Cc
+    if out is None:
+        out = torch.empty((B * Ho * Wo, ldc), device=x.device, dtype=bf16)
+    _lib.check(_lib.load().b2_im2col3x3(_p(x), _p(out), B, H, W, Cc, stride, int(upsample), ldc, _stream()), "im2col")
+    return out
+
+
+def col2im3x3(dcol, dx, B, H, W, Cc, stride=1, upsample=False, accumulate=False):
+    _lib.check(_lib.load().b2_col2im3x3(_p(dcol), _p(dx), B, H, W, Cc, stride, int(upsample), dcol.stride(0),
+                                       int(accumulate), _stream()), "col2im")
+    return dx
+
+
+# --------------------------------------------------------------------------------------- norms
+def gn_stats(x, B, HW, Cc, G, eps):
+    ws = torch.empty(B * G * 2, device=x.device, dtype=torch.float64)
+    mean = torch.empty(B * G, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(B * G, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().b2_gn_stats(_p(x), B, HW, Cc, G, eps, _p(ws), _p(mean), _p(rstd), _stream()), "gn_stats")
+    return mean, rstd
+
+
+def gn_apply(x, mean, rstd, gamma, beta, B, HW, Cc, G, silu, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.load().b2_gn_apply(_p(x), _p(out), _p(mean), _p(rstd), _p(gamma), _p(beta), B, HW, Cc, G,
+                                      int(silu), _stream()), "gn_apply")
+    return out
+
+
+def gn_bwd(x, dy, mean, rstd, gamma, beta, B, HW, Cc, G, silu, dgb, dx=None, accumulate=False):
+    if dx is None:
+        dx = torch.empty_like(x)
+        accumulate = False
+    ws = torch.empty(B * G * 2, device=x.device, dtype=torch.float64)
+    _lib.check(_lib.load().b2_gn_bwd(_p(x), _p(dy), _p(dx), _p(mean), _p(rstd), _p(gamma), _p(beta), B, HW, Cc, G,
+                                    int(silu), _p(ws), _p(dgb), int(accumulate), _stream()), "gn_bwd")
+    return dx
+
+
+def ln_fwd(x, gamma, beta, eps=1e-5):
+    M, Cc = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().b2_ln_fwd(_p(x), _p(y), _p(gamma), _p(beta), _p(mean), _p(rstd), M, Cc, eps, _stream()),
+               "ln_fwd")
+    return y, mean, rstd
+
+
+def ln_bwd(x, dy, gamma, mean, rstd, dgb, dx=None, accumulate=False):
+    M, Cc = x.shape
+    if dx is None:
+        dx = torch.empty_like(x)
+        accumulate = False
+    _lib.check(_lib.load().b2_ln_bwd(_p(x), _p(dy), _p(dx), _p(gamma), _p(mean), _p(rstd), _p(dgb), M, Cc,
+                                    int(accumulate), _stream()), "ln_bwd")
+    return dx
+
+
+# --------------------------------------------------------------------------------------- attention pieces
+def softmax_fwd(S, P, rows, n_valid):
+    _lib.check(_lib.load().b2_softmax_fwd(_p(S), _p(P), rows, n_valid, S.stride(-2), P.stride(-2), _stream()), "softmax")
+    return P
+
+
+def softmax_bwd(P, dP, dS, rows, n_valid, scale):
+    _lib.check(_lib.load().b2_softmax_bwd(_p(P), _p(dP), _p(dS), rows, n_valid, dP.stride(-2), P.stride(-2),
+                                         float(scale), _stream()), "softmax_bwd")
+    return dS
+
+
+# --------------------------------------------------------------------------------------- elementwise
+def geglu_fwd(u, F):
+    M = u.shape[0]
+    z = torch.empty((M, F), device=u.device, dtype=bf16)
+    _lib.check(_lib.load().b2_geglu_fwd(_p(u), _p(z), M, F, _stream()), "geglu_fwd")
+    return z
+
+
+def geglu_bwd(u, dz, F):
+    M = u.shape[0]
+    du = torch.empty_like(u)
+    _lib.check(_lib.load().b2_geglu_bwd(_p(u), _p(dz), _p(du), M, F, _stream()), "geglu_bwd")
+    return du
+
+
+def silu_fwd(x):
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().b2_silu_fwd(_p(x), _p(y), x.numel(), _stream()), "silu_fwd")
+    return y
+
+
+def silu_bwd(x, dy, dx=None, accumulate=False):
+    if dx is None:
+        dx = torch.empty_like(x)
+        accumulate = False
+    _lib.check(_lib.load().b2_silu_bwd(_p(x), _p(dy), _p(dx), x.numel(), int(accumulate), _stream()), "silu_bwd")
+    return dx
+
+
+def add(a, b, out=None):
+    if out is None:
+        out = torch.empty_like(a)
+    _lib.check(_lib.load().b2_add(_p(a), _p(b), _p(out), a.numel(), _stream()), "add")
+    return out
+
+
+def copy2d(src, dst, rows, cols, lds, ldd, accumulate=False):
+    _lib.check(_lib.load().b2_copy2d(_p(src), _p(dst), rows, cols, lds, ldd, int(accumulate), _stream()), "copy2d")
+    return dst
+
+
+def colsum(dy, db, accumulate=True):
+    M, N = dy.shape
+    ws = torch.empty(N, device=dy.device, dtype=torch.float32)
+    _lib.check(_lib.load().b2_colsum(_p(dy), _p(db), M, N, dy.stride(0), int(accumulate), _p(ws), _stream()), "colsum")
+    return db
+
+
+def accum_f32_to_bf16(src, dst, accumulate=True):
+    _lib.check(_lib.load().b2_accum_f32_to_bf16(_p(src), _p(dst), src.numel(), int(accumulate), _stream()), "accum")
+    return dst
+
+
+def nchw_to_nhwc(x, Cpad):
+    B, Cc, H, W = x.shape
+    x = x.contiguous()
+    if x.dtype not in (torch.float32, bf16):
+        x = x.float()
+    y = torch.empty((B * H * W, Cpad), device=x.device, dtype=bf16)
+    _lib.check(_lib.load().b2_nchw_to_nhwc(_p(x), int(x.dtype == torch.float32), _p(y), B, Cc, H * W, Cpad, _stream()),
+               "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x, B, Cc, H, W, Cpad, dtype=bf16):
+    y = torch.empty((B, Cc, H, W), device=x.device, dtype=dtype)
+    _lib.check(_lib.load().b2_nhwc_to_nchw(_p(x), _p(y), int(dtype == torch.float32), B, Cc, H * W, Cpad, _stream()),
+               "nhwc_to_nchw")
+    return y
+
+
+def timestep_embedding(t_f32, dim, out=None, ldo=None):
+    n = t_f32.numel()
+    if out is None:
+        out = torch.empty((n, dim), device=t_f32.device, dtype=bf16)
+        ldo = dim
+    _lib.check(_lib.load().b2_timestep_embedding(_p(t_f32), _p(out), n, dim, ldo, _stream()), "timestep_embedding")
+    return out
+
+
+# --------------------------------------------------------------------------------------- loss side
+def randn(n, seed_offset, stream_id, round_bf16=True, out=None):
+    if out is None:
+        out = torch.empty(n, device=seed_offset.device, dtype=torch.float32)
+    _lib.check(_lib.load().b2_randn(_p(out), n, _p(seed_offset), int(stream_id), int(round_bf16), _stream()), "randn")
+    return out
+
+
+def philox_advance(seed_offset, inc=1):
+    _lib.check(_lib.load().b2_philox_advance(_p(seed_offset), int(inc), _stream()), "philox_advance")
+
+
+def make_noisy(x, eps, sigma_or_t, mode, v_prediction, clamp_ztsnr, B, Cc, HW, Cpad):
+    noisy = torch.empty((B * HW, Cpad), device=x.device, dtype=bf16)
+    target = torch.empty((B, Cc, HW), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().b2_make_noisy(_p(x), _p(eps), _p(sigma_or_t), mode, int(v_prediction), int(clamp_ztsnr),
+                                        _p(noisy), _p(target), B, Cc, HW, Cpad, _stream()), "make_noisy")
+    return noisy, target
+
+
+def mse_loss(pred, target, weight, loss_sum, dpred, gscale, B, Cc, HW, Cpad):
+    _lib.check(_lib.load().b2_mse_loss(_p(pred), _p(target), _p(weight), _p(loss_sum), _p(dpred), float(gscale), B, Cc,
+                                      HW, Cpad, _stream()), "mse_loss")
+
+
+def finalize_loss(loss_sum, count, scale, loss_out, ok, dpred=None):
+    _lib.check(_lib.load().b2_finalize_loss(_p(loss_sum), float(count), float(scale), _p(loss_out), _p(ok), _p(dpred),
+                                           0 if dpred is None else dpred.numel(), _stream()), "finalize_loss")
+
+
+def sumsq(g, out):
+    _lib.check(_lib.load().b2_sumsq(_p(g), g.numel(), _p(out), _stream()), "sumsq")
+
+
+def adamw(p, master, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, step=1, gnorm_sq=None,
+          max_norm=0.0, grad_scale=1.0):
+    _lib.check(_lib.load().b2_adamw(_p(p), _p(master), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps,
+                                   weight_decay, int(step), _p(gnorm_sq), float(max_norm), float(grad_scale),
+                                   _stream()), "adamw")
