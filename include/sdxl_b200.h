@@ -125,6 +125,8 @@ int b2_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, int accumula
 int b2_add(const void* a, const void* b, void* out, int64_t n, void* stream);              /* out = a + b */
 int b2_copy2d(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd,
               int accumulate, void* stream);                                                  /* bf16 */
+int b2_copy2d_any(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd,
+                  int accumulate, void* stream);                   /* bf16, no alignment requirements (scalar) */
 int b2_colsum(const void* dy, void* db, int64_t M, int N, int64_t ld, int accumulate, float* ws /* float[N] */,
               void* stream);                                                                  /* db[n] (+)= sum_m dy[m,n] */
 int b2_accum_f32_to_bf16(const float* src, void* dst, int64_t n, int accumulate, void* stream);
@@ -163,6 +165,11 @@ int b2_finalize_loss(const double* loss_sum, double count, float scale, float* l
  *   clip coefficient computed on device from *gnorm_sq (max_norm <= 0: no clipping).
  * ------------------------------------------------------------------------------------------------ */
 int b2_sumsq(const void* g, int64_t n, double* out, void* stream);
+/* out[0] += sum|x|, out[1] += sum x^2 over elements with (i % period) < valid (period 0: all). Metrics of the
+ * reference's step dicts (ddpm_trainer.py:386-396, flow_matching_trainer.py:338-347) without host syncs. */
+int b2_abs_sq_sums(const void* x, int is_fp32, int64_t n, int period, int valid, double* out, void* stream);
+/* x *= (*dev_scale if given) * host_scale  — applies autograd's upstream scalar (loss / accum) to dL/dpred. */
+int b2_scale_bf16(void* x, int64_t n, const float* dev_scale, float host_scale, void* stream);
 int b2_adamw(void* p, float* master /* fp32 master weights or NULL */, const void* g, float* m, float* v, int64_t n,
              float lr, float beta1, float beta2, float eps, float weight_decay, int step, const double* gnorm_sq,
              float max_norm, float grad_scale, void* stream);

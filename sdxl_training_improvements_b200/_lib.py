@@ -47,6 +47,7 @@ SIGNATURES = {
     "b2_silu_bwd": [c_p, c_p, c_p, i64, i32, c_p],
     "b2_add": [c_p, c_p, c_p, i64, c_p],
     "b2_copy2d": [c_p, c_p, i64, i64, i64, i64, i32, c_p],
+    "b2_copy2d_any": [c_p, c_p, i64, i64, i64, i64, i32, c_p],
     "b2_colsum": [c_p, c_p, i64, i32, i64, i32, c_p, c_p],
     "b2_accum_f32_to_bf16": [c_p, c_p, i64, i32, c_p],
     "b2_nchw_to_nhwc": [c_p, i32, c_p, i32, i32, i32, i32, c_p],
@@ -57,6 +58,8 @@ SIGNATURES = {
     "b2_make_noisy": [c_p, c_p, c_p, i32, i32, i32, c_p, c_p, i32, i32, i32, i32, c_p],
     "b2_mse_loss": [c_p, c_p, c_p, c_p, c_p, f32, i32, i32, i32, i32, c_p],
     "b2_finalize_loss": [c_p, f64, f32, c_p, c_p, c_p, i64, c_p],
+    "b2_abs_sq_sums": [c_p, i32, i64, i32, i32, c_p, c_p],
+    "b2_scale_bf16": [c_p, i64, c_p, f32, c_p],
     "b2_sumsq": [c_p, i64, c_p, c_p],
     "b2_adamw": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, c_p, f32, f32, c_p],
 }

@@ -136,6 +136,18 @@ __global__ void copy2d_kernel(const bf16* __restrict__ src, bf16* __restrict__ d
   }
 }
 
+// generic (unaligned / narrow) strided copy, one element per thread
+__global__ void copy2d_any_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long long rows, long long cols,
+                                  long long lds, long long ldd, int accumulate) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    float v = __bfloat162float(src[r * lds + c]);
+    if (accumulate) v += __bfloat162float(dst[r * ldd + c]);
+    dst[r * ldd + c] = __float2bfloat16(v);
+  }
+}
+
 // ---------------------------------------------------------------- column sum (bias gradients)
 __global__ void colsum_kernel(const bf16* __restrict__ dy, float* ws, long long M, int N, long long ld,
                               long long rows_per_cta) {
@@ -272,6 +284,13 @@ extern "C" int b2_copy2d(const void* src, void* dst, int64_t rows, int64_t cols,
   copy2d_kernel<<<ew_blocks(rows * (cols / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, rows,
                                                                                      cols, lds, ldd, accumulate);
   return check_launch("copy2d");
+}
+extern "C" int b2_copy2d_any(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd,
+                             int accumulate, void* stream) {
+  B2_REQUIRE(src && dst && rows > 0 && cols > 0, "b2_copy2d_any: bad args");
+  copy2d_any_kernel<<<ew_blocks(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, rows, cols,
+                                                                                   lds, ldd, accumulate);
+  return check_launch("copy2d_any");
 }
 extern "C" int b2_accum_f32_to_bf16(const float* src, void* dst, int64_t n, int accumulate, void* stream) {
   B2_REQUIRE(src && dst && n > 0, "b2_accum_f32_to_bf16: bad args");

@@ -183,6 +183,37 @@ __global__ void adamw_kernel(bf16* __restrict__ p, float* __restrict__ master, c
   }
 }
 
+// out[0] += sum |x|, out[1] += sum x^2   (metrics: noise_scale / pred_scale / *_norm of the reference's dicts)
+template <typename T>
+__global__ void abs_sq_sums_kernel(const T* __restrict__ x, long long n, int period, int valid, double* out) {
+  float sa = 0.f, sq = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (period > 0 && (int)(i % period) >= valid) continue;  // skip channel padding
+    const float f = (float)x[i];
+    sa += fabsf(f);
+    sq += f * f;
+  }
+  sa = warp_sum(sa);
+  sq = warp_sum(sq);
+  __shared__ float sm[2][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sm[0][warp] = sa; sm[1][warp] = sq; }
+  __syncthreads();
+  if (warp == 0) {
+    float a = lane < (blockDim.x >> 5) ? sm[0][lane] : 0.f;
+    float q = lane < (blockDim.x >> 5) ? sm[1][lane] : 0.f;
+    a = warp_sum(a);
+    q = warp_sum(q);
+    if (lane == 0) { atomicAdd(&out[0], (double)a); atomicAdd(&out[1], (double)q); }
+  }
+}
+
+__global__ void scale_bf16_kernel(bf16* x, long long n, const float* scale, float host_scale) {
+  const float s = (scale ? *scale : 1.f) * host_scale;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = __float2bfloat16(__bfloat162float(x[i]) * s);
+}
+
 static inline int red_blocks(long long items) {
   long long b = (items + 255) / 256;
   const long long cap = 8LL * num_sms();
@@ -227,6 +258,19 @@ extern "C" int b2_finalize_loss(const double* loss_sum, double count, float scal
   if (rc || !dpred) return rc;
   mask_grad_kernel<<<red_blocks(n_dpred), 256, 0, (cudaStream_t)stream>>>((bf16*)dpred, n_dpred, ok);
   return check_launch("mask_grad");
+}
+extern "C" int b2_abs_sq_sums(const void* x, int is_fp32, int64_t n, int period, int valid, double* out, void* stream) {
+  B2_REQUIRE(x && out && n > 0, "b2_abs_sq_sums: bad args");
+  if (is_fp32)
+    abs_sq_sums_kernel<float><<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>((const float*)x, n, period, valid, out);
+  else
+    abs_sq_sums_kernel<bf16><<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, n, period, valid, out);
+  return check_launch("abs_sq_sums");
+}
+extern "C" int b2_scale_bf16(void* x, int64_t n, const float* dev_scale, float host_scale, void* stream) {
+  B2_REQUIRE(x && n > 0, "b2_scale_bf16: bad args");
+  scale_bf16_kernel<<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>((bf16*)x, n, dev_scale, host_scale);
+  return check_launch("scale_bf16");
 }
 extern "C" int b2_sumsq(const void* g, int64_t n, double* out, void* stream) {
   B2_REQUIRE(g && out && n > 0 && !((uintptr_t)g & 15), "b2_sumsq: bad args");

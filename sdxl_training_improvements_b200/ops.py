@@ -204,6 +204,11 @@ def copy2d(src, dst, rows, cols, lds, ldd, accumulate=False):
     return dst
 
 
+def copy2d_any(src, dst, rows, cols, lds, ldd, accumulate=False):
+    _lib.check(_lib.load().b2_copy2d_any(_p(src), _p(dst), rows, cols, lds, ldd, int(accumulate), _stream()), "copy2d_any")
+    return dst
+
+
 def colsum(dy, db, accumulate=True):
     M, N = dy.shape
     ws = torch.empty(N, device=dy.device, dtype=torch.float32)
@@ -271,6 +276,15 @@ def mse_loss(pred, target, weight, loss_sum, dpred, gscale, B, Cc, HW, Cpad):
 def finalize_loss(loss_sum, count, scale, loss_out, ok, dpred=None):
     _lib.check(_lib.load().b2_finalize_loss(_p(loss_sum), float(count), float(scale), _p(loss_out), _p(ok), _p(dpred),
                                            0 if dpred is None else dpred.numel(), _stream()), "finalize_loss")
+
+
+def abs_sq_sums(x, out, period=0, valid=0):
+    _lib.check(_lib.load().b2_abs_sq_sums(_p(x), int(x.dtype == torch.float32), x.numel(), period, valid, _p(out),
+                                         _stream()), "abs_sq_sums")
+
+
+def scale_bf16(x, dev_scale=None, host_scale=1.0):
+    _lib.check(_lib.load().b2_scale_bf16(_p(x), x.numel(), _p(dev_scale), float(host_scale), _stream()), "scale_bf16")
 
 
 def sumsq(g, out):

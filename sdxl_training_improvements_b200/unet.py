@@ -1,0 +1,621 @@
+"""B200-native SDXL UNet: forward + hand-written backward over the C-ABI kernels.
+
+Stands in for `self.model.unet` of the reference (a diffusers `UNet2DConditionModel`; call sites
+src/training/trainers/methods/ddpm_trainer.py:320-325, flow_matching_trainer.py:400-405,
+src/training/trainers/sdxl_trainer.py:65-70).  The module graph is SURVEY.md Appendix A; nothing here calls a
+torch compute op on the hot path — torch supplies device memory, the stream and (for the drop-in surface) one
+autograd.Function around the whole network.
+
+Execution model: activations are token-major [B*H*W, C] bf16.  `forward()` runs the kernels and records one
+backward closure per operator on a tape; `backward()` replays the tape in reverse.  Gradients w.r.t. activations
+are accumulated in place by the kernels' `accumulate` epilogues (no separate add passes for fan-out), parameter
+gradients accumulate (`+=`) into the flat bf16 gradient buffer of `ParamStore`, which is what gradient
+accumulation and the single NCCL all-reduce operate on.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import ops
+from .params import SDXL_BASE, ParamStore
+
+bf16 = torch.bfloat16
+HEAD_DIM = 64
+
+
+class Act:
+    """An activation and its (lazily allocated) gradient."""
+    __slots__ = ("d", "g")
+
+    def __init__(self, d: torch.Tensor):
+        self.d = d
+        self.g: Optional[torch.Tensor] = None
+
+
+def _gslot(t: Act):
+    """(gradient buffer, accumulate?) for writing a contribution into t.g."""
+    if t.g is None:
+        t.g = torch.empty_like(t.d)
+        return t.g, False
+    return t.g, True
+
+
+def _ceil8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class UNetEngine:
+    """Kernel-level forward/backward of the UNet for one (B, H, W) problem."""
+
+    def __init__(self, store: ParamStore):
+        self.store = store
+        self.cfg = store.cfg
+        self.tape: List[Callable[[], None]] = []
+        self._ws: Dict[str, torch.Tensor] = {}
+        st = store
+        for pfx in self._attn_prefixes():
+            assert st.adjacent(f"{pfx}.attn1.to_q.weight", f"{pfx}.attn1.to_k.weight", f"{pfx}.attn1.to_v.weight")
+            assert st.adjacent(f"{pfx}.attn2.to_k.weight", f"{pfx}.attn2.to_v.weight")
+
+    def _attn_prefixes(self):
+        return sorted({n.rsplit(".attn1.", 1)[0] for n, _ in self.store.specs if ".attn1.to_q." in n})
+
+    # ------------------------------------------------------------------ workspaces
+    def ws(self, key: str, numel: int, dtype) -> torch.Tensor:
+        """Grow-only scratch buffers reused by every layer (stream-ordered reuse is safe on one stream)."""
+        cur = self._ws.get(key)
+        if cur is None or cur.numel() < numel or cur.dtype != dtype:
+            dev = self.store.flat.device
+            cur = torch.empty(numel, device=dev, dtype=dtype)
+            self._ws[key] = cur
+        return cur[:numel]
+
+    def reserve_workspaces(self, B, H, W):
+        """Pre-size the scratch buffers for a problem (required before CUDA-graph capture)."""
+        boc = self.cfg["block_out_channels"]
+        heads = self.cfg["num_heads"]
+        depth = self.cfg["transformer_layers_per_block"]
+        M0 = B * H * W
+        maxcol = 0
+        maxS = 0
+        for lvl, c in enumerate(boc):
+            m = M0 >> (2 * lvl)
+            cin_max = c + (boc[min(lvl + 1, len(boc) - 1)] if lvl < len(boc) - 1 else c)
+            cin_max = max(cin_max, 2 * c, c + (boc[lvl - 1] if lvl > 0 else c))
+            maxcol = max(maxcol, m * 9 * cin_max)
+            if lvl > 0:
+                maxcol = max(maxcol, m * 9 * boc[lvl])  # upsample conv output grid
+            if depth[lvl] > 0:
+                n = (H >> lvl) * (W >> lvl)
+                maxS = max(maxS, B * heads[lvl] * n * _ceil8(n))
+        maxcol = max(maxcol, (M0 // 4) * 9 * boc[1] * 4)  # Upsample2D(640) writes a 128^2 grid of 9*640
+        self.ws("col", maxcol, bf16)
+        self.ws("dcol", maxcol, bf16)
+        if maxS:
+            self.ws("S", maxS, torch.float32)
+            self.ws("dS", maxS, bf16)
+
+    # ------------------------------------------------------------------ primitive layers
+    def _pgrad_norm(self, dgb: torch.Tensor, wname: str, bname: str, Cc: int):
+        ops.accum_f32_to_bf16(dgb[:Cc], self.store.gv(wname), True)
+        ops.accum_f32_to_bf16(dgb[Cc:], self.store.gv(bname), True)
+
+    def linear(self, x: Act, wname: str, N: int, K: int, bname: Optional[str] = None, residual: Optional[Act] = None,
+               need_dx: bool = True, res_ld0: Optional[torch.Tensor] = None) -> Act:
+        st = self.store
+        Wt = st.w(wname, N, K)
+        bias = st.v(bname) if bname else None
+        if res_ld0 is not None:  # broadcast row added through the residual port (ldr = 0)
+            y = torch.empty((x.d.shape[0], N), device=x.d.device, dtype=bf16)
+            ops.gemm_raw(x.d, Wt, y, x.d.shape[0], N, K, lda=x.d.stride(0), ldb=K, ldd=N, bias=bias,
+                         residual=res_ld0, ldr=0)
+        else:
+            y = ops.linear_fwd(x.d, Wt, bias=bias, residual=residual.d if residual is not None else None)
+        out = Act(y)
+
+        def bwd():
+            dy = out.g
+            ops.linear_wgrad(dy, x.d, st.g(wname, N, K), accumulate=True)
+            if bname:
+                ops.colsum(dy, st.gv(bname), accumulate=True)
+            if need_dx:
+                buf, acc = _gslot(x)
+                ops.linear_dgrad(dy, Wt, buf, acc)
+            if residual is not None:
+                self._add_grad(residual, dy)
+
+        self.tape.append(bwd)
+        return out
+
+    def _add_grad(self, t: Act, dy: torch.Tensor):
+        if t.g is None:
+            t.g = dy  # alias: dy's readers are all enqueued before any later in-place accumulation
+        else:
+            ops.add(t.g, dy, t.g)
+
+    def groupnorm(self, x: Act, B, HW, Cc, wname, bname, eps, silu) -> Act:
+        st = self.store
+        G = self.cfg["norm_num_groups"]
+        gamma, beta = st.v(wname), st.v(bname)
+        mean, rstd = ops.gn_stats(x.d, B, HW, Cc, G, eps)
+        out = Act(ops.gn_apply(x.d, mean, rstd, gamma, beta, B, HW, Cc, G, silu))
+
+        def bwd():
+            dgb = torch.zeros(2 * Cc, device=x.d.device, dtype=torch.float32)
+            buf, acc = _gslot(x)
+            ops.gn_bwd(x.d, out.g, mean, rstd, gamma, beta, B, HW, Cc, G, silu, dgb, buf, acc)
+            self._pgrad_norm(dgb, wname, bname, Cc)
+
+        self.tape.append(bwd)
+        return out
+
+    def layernorm(self, x: Act, Cc, wname, bname) -> Act:
+        st = self.store
+        gamma, beta = st.v(wname), st.v(bname)
+        y, mean, rstd = ops.ln_fwd(x.d, gamma, beta, 1e-5)
+        out = Act(y)
+
+        def bwd():
+            dgb = torch.zeros(2 * Cc, device=x.d.device, dtype=torch.float32)
+            buf, acc = _gslot(x)
+            ops.ln_bwd(x.d, out.g, gamma, mean, rstd, dgb, buf, acc)
+            self._pgrad_norm(dgb, wname, bname, Cc)
+
+        self.tape.append(bwd)
+        return out
+
+    def conv3x3(self, x: Act, B, H, W, Cin, Cout, wname, bname, stride=1, up=False, rowbias: Optional[Act] = None,
+                residual: Optional[Act] = None, need_dx=True, Wk=None, gWk=None, bias_t=None, Npad=None) -> Act:
+        """3x3 conv as im2col (TMA-friendly K-major operand) + tcgen05 GEMM.  `rowbias` [B, Cout] already contains the
+        conv bias (time-embedding projection path of ResnetBlock2D.conv1)."""
+        st = self.store
+        Ho, Wo = ops.conv_out_hw(H, W, stride, up)
+        M = B * Ho * Wo
+        K = 9 * Cin
+        N = Npad or Cout
+        Wk = st.w(wname, Cout, K) if Wk is None else Wk
+        gWk = st.g(wname, Cout, K) if gWk is None else gWk
+        col = ops.im2col3x3(x.d, B, H, W, Cin, stride, up, out=self.ws("col", M * K, bf16).view(M, K))
+        y = torch.empty((M, N), device=x.d.device, dtype=bf16)
+        res = residual.d if residual is not None else None
+        if rowbias is not None:
+            ops.gemm_raw(col, Wk, y, M, N, K, lda=K, ldb=K, ldd=N, bias=rowbias.d, residual=res, ldr=N,
+                         bias_rows_per_group=Ho * Wo, bias_group_stride=N)
+        else:
+            bias = bias_t if bias_t is not None else st.v(bname)
+            ops.gemm_raw(col, Wk, y, M, N, K, lda=K, ldb=K, ldd=N, bias=bias, residual=res, ldr=N)
+        out = Act(y)
+
+        def bwd():
+            dy = out.g
+            colb = ops.im2col3x3(x.d, B, H, W, Cin, stride, up, out=self.ws("col", M * K, bf16).view(M, K))
+            ops.gemm_raw(dy, colb, gWk, N, K, M, a_mn=True, b_mn=True, lda=N, ldb=K, ldd=K, accumulate=True)
+            if rowbias is not None:
+                if rowbias.g is None:
+                    rowbias.g = torch.empty_like(rowbias.d)
+                    acc = False
+                else:
+                    acc = True
+                hw = Ho * Wo
+                for b in range(B):
+                    ops.colsum(dy[b * hw:(b + 1) * hw], rowbias.g[b], accumulate=acc)
+            elif bias_t is None:
+                ops.colsum(dy, st.gv(bname), accumulate=True)
+            if need_dx:
+                dcol = self.ws("dcol", M * K, bf16).view(M, K)
+                ops.gemm_raw(dy, Wk, dcol, M, K, N, b_mn=True, lda=N, ldb=K, ldd=K)
+                buf, acc = _gslot(x)
+                ops.col2im3x3(dcol, buf, B, H, W, Cin, stride, up, accumulate=acc)
+            if residual is not None:
+                self._add_grad(residual, dy)
+
+        self.tape.append(bwd)
+        return out
+
+    def concat(self, a: Act, b: Act, M, Ca, Cb) -> Act:
+        y = torch.empty((M, Ca + Cb), device=a.d.device, dtype=bf16)
+        ops.copy2d(a.d, y, M, Ca, Ca, Ca + Cb)
+        ops.copy2d(b.d, y[:, Ca:], M, Cb, Cb, Ca + Cb)
+        out = Act(y)
+
+        def bwd():
+            ga, acca = _gslot(a)
+            ops.copy2d(out.g, ga, M, Ca, Ca + Cb, Ca, accumulate=acca)
+            gb, accb = _gslot(b)
+            ops.copy2d(out.g[:, Ca:], gb, M, Cb, Ca + Cb, Cb, accumulate=accb)
+
+        self.tape.append(bwd)
+        return out
+
+    def silu(self, x: Act) -> Act:
+        out = Act(ops.silu_fwd(x.d))
+
+        def bwd():
+            buf, acc = _gslot(x)
+            ops.silu_bwd(x.d, out.g, buf, acc)
+
+        self.tape.append(bwd)
+        return out
+
+    # ------------------------------------------------------------------ composite blocks
+    def resnet(self, x: Act, emb_silu: Act, B, H, W, Cin, Cout, pfx) -> Act:
+        st = self.store
+        temb = self.cfg["block_out_channels"][0] * 4
+        eps = self.cfg["norm_eps"]
+        a1 = self.groupnorm(x, B, H * W, Cin, f"{pfx}.norm1.weight", f"{pfx}.norm1.bias", eps, True)
+        # time_emb_proj(SiLU(emb)) + conv1.bias  ->  one [B, Cout] row per sample, added in conv1's epilogue
+        tproj = self.linear(emb_silu, f"{pfx}.time_emb_proj.weight", Cout, temb, f"{pfx}.time_emb_proj.bias",
+                            res_ld0=st.v(f"{pfx}.conv1.bias"))
+        h1 = self.conv3x3(a1, B, H, W, Cin, Cout, f"{pfx}.conv1.weight", f"{pfx}.conv1.bias", rowbias=tproj)
+
+        def conv1_bias_grad():  # d conv1.bias = sum over samples of d tproj
+            ops.colsum(tproj.g, st.gv(f"{pfx}.conv1.bias"), accumulate=True)
+
+        # runs after conv1's backward (which fills tproj.g) and before the time_emb_proj linear's backward
+        self.tape.insert(len(self.tape) - 1, conv1_bias_grad)
+        a2 = self.groupnorm(h1, B, H * W, Cout, f"{pfx}.norm2.weight", f"{pfx}.norm2.bias", eps, True)
+        if Cin != Cout:
+            sc = self.linear(x, f"{pfx}.conv_shortcut.weight", Cout, Cin, f"{pfx}.conv_shortcut.bias")
+        else:
+            sc = x
+        return self.conv3x3(a2, B, H, W, Cout, Cout, f"{pfx}.conv2.weight", f"{pfx}.conv2.bias", residual=sc)
+
+    def attention(self, xn: Act, res: Act, B, n, Cc, pfx, ctx: Optional[torch.Tensor], n_ctx: int) -> Act:
+        """softmax(Q K^T / 8) V with materialised logits (round-1 path), then to_out + residual."""
+        st = self.store
+        heads = Cc // HEAD_DIM
+        d = HEAD_DIM
+        scale = 1.0 / math.sqrt(d)
+        M = B * n
+        dev = xn.d.device
+        is_self = ctx is None
+        if is_self:
+            nk = n
+            Wqkv = st.w(f"{pfx}.to_q.weight", 3 * Cc, Cc)
+            qkv = ops.linear_fwd(xn.d, Wqkv)  # [M, 3C]
+            q_t, q_ld, q_bs = qkv, 3 * Cc, (d, n * 3 * Cc)
+            k_t, v_t, kv_ld, kv_bs = qkv[:, Cc:], qkv[:, 2 * Cc:], 3 * Cc, (d, n * 3 * Cc)
+        else:
+            nk = n_ctx
+            cdim = self.cfg["cross_attention_dim"]
+            Wq = st.w(f"{pfx}.to_q.weight", Cc, Cc)
+            Wkv = st.w(f"{pfx}.to_k.weight", 2 * Cc, cdim)
+            q = ops.linear_fwd(xn.d, Wq)
+            kv = ops.linear_fwd(ctx, Wkv)  # [B*77, 2C]
+            q_t, q_ld, q_bs = q, Cc, (d, n * Cc)
+            k_t, v_t, kv_ld, kv_bs = kv, kv[:, Cc:], 2 * Cc, (d, nk * 2 * Cc)
+        ldk = _ceil8(nk)
+        s_bs = (n * ldk, heads * n * ldk)
+        rows = B * heads * n
+        S = self.ws("S", rows * ldk, torch.float32).view(rows, ldk)
+        ops.gemm_raw(q_t, k_t, S, n, nk, d, lda=q_ld, ldb=kv_ld, ldd=ldk, nb_lo=heads, nb_hi=B, a_bs=q_bs, b_bs=kv_bs,
+                     d_bs=s_bs, alpha=scale, out_fp32=True)
+        P = torch.empty((rows, ldk), device=dev, dtype=bf16)
+        ops.softmax_fwd(S, P, rows, nk)
+        O = torch.empty((M, Cc), device=dev, dtype=bf16)
+        ops.gemm_raw(P, v_t, O, n, d, nk, b_mn=True, lda=ldk, ldb=kv_ld, ldd=Cc, nb_lo=heads, nb_hi=B, a_bs=s_bs,
+                     b_bs=kv_bs, d_bs=(d, n * Cc))
+        Oa = Act(O)
+        out = self.linear(Oa, f"{pfx}.to_out.0.weight", Cc, Cc, f"{pfx}.to_out.0.bias", residual=res)
+
+        def bwd():
+            dO = Oa.g
+            o_bs = (d, n * Cc)
+            if is_self:
+                dqkv = torch.empty_like(qkv)
+                dq_t, dq_ld, dq_bs = dqkv, 3 * Cc, q_bs
+                dk_t, dv_t, dkv_ld = dqkv[:, Cc:], dqkv[:, 2 * Cc:], 3 * Cc
+            else:
+                dq = torch.empty_like(q)
+                dkv = torch.empty_like(kv)
+                dq_t, dq_ld, dq_bs = dq, Cc, q_bs
+                dk_t, dv_t, dkv_ld = dkv, dkv[:, Cc:], 2 * Cc
+            # dV = P^T dO
+            ops.gemm_raw(P, dO, dv_t, nk, d, n, a_mn=True, b_mn=True, lda=ldk, ldb=Cc, ldd=dkv_ld, nb_lo=heads, nb_hi=B,
+                         a_bs=s_bs, b_bs=o_bs, d_bs=kv_bs)
+            # dP = dO V^T   (fp32)
+            dP = self.ws("S", rows * ldk, torch.float32).view(rows, ldk)
+            ops.gemm_raw(dO, v_t, dP, n, nk, d, lda=Cc, ldb=kv_ld, ldd=ldk, nb_lo=heads, nb_hi=B, a_bs=o_bs, b_bs=kv_bs,
+                         d_bs=s_bs, out_fp32=True)
+            dS = self.ws("dS", rows * ldk, bf16).view(rows, ldk)
+            ops.softmax_bwd(P, dP, dS, rows, nk, scale)
+            # dQ = dS K ; dK = dS^T Q
+            ops.gemm_raw(dS, k_t, dq_t, n, d, nk, b_mn=True, lda=ldk, ldb=kv_ld, ldd=dq_ld, nb_lo=heads, nb_hi=B,
+                         a_bs=s_bs, b_bs=kv_bs, d_bs=dq_bs)
+            ops.gemm_raw(dS, q_t, dk_t, nk, d, n, a_mn=True, b_mn=True, lda=ldk, ldb=q_ld, ldd=dkv_ld, nb_lo=heads,
+                         nb_hi=B, a_bs=s_bs, b_bs=q_bs, d_bs=kv_bs)
+            buf, acc = _gslot(xn)
+            if is_self:
+                ops.linear_wgrad(dqkv, xn.d, st.g(f"{pfx}.to_q.weight", 3 * Cc, Cc), accumulate=True)
+                ops.linear_dgrad(dqkv, Wqkv, buf, acc)
+            else:
+                ops.linear_wgrad(dq, xn.d, st.g(f"{pfx}.to_q.weight", Cc, Cc), accumulate=True)
+                ops.linear_dgrad(dq, Wq, buf, acc)
+                ops.linear_wgrad(dkv, ctx, st.g(f"{pfx}.to_k.weight", 2 * Cc, cdim), accumulate=True)
+
+        # attention-core backward must run after to_out's backward (already on the tape) -> append
+        self.tape.append(bwd)
+        # ...but the tape is replayed in reverse, so the closure appended last runs first: swap the two
+        self.tape[-1], self.tape[-2] = self.tape[-2], self.tape[-1]
+        return out
+
+    def transformer_block(self, h: Act, B, n, Cc, pfx, ctx, n_ctx) -> Act:
+        n1 = self.layernorm(h, Cc, f"{pfx}.norm1.weight", f"{pfx}.norm1.bias")
+        h1 = self.attention(n1, h, B, n, Cc, f"{pfx}.attn1", None, 0)
+        n2 = self.layernorm(h1, Cc, f"{pfx}.norm2.weight", f"{pfx}.norm2.bias")
+        h2 = self.attention(n2, h1, B, n, Cc, f"{pfx}.attn2", ctx, n_ctx)
+        n3 = self.layernorm(h2, Cc, f"{pfx}.norm3.weight", f"{pfx}.norm3.bias")
+        u = self.linear(n3, f"{pfx}.ff.net.0.proj.weight", 8 * Cc, Cc, f"{pfx}.ff.net.0.proj.bias")
+        z = Act(ops.geglu_fwd(u.d, 4 * Cc))
+
+        def geglu_bwd():
+            u.g = ops.geglu_bwd(u.d, z.g, 4 * Cc)
+
+        self.tape.append(geglu_bwd)
+        return self.linear(z, f"{pfx}.ff.net.2.weight", Cc, 4 * Cc, f"{pfx}.ff.net.2.bias", residual=h2)
+
+    def transformer(self, x: Act, B, H, W, Cc, depth, pfx, ctx, n_ctx) -> Act:
+        a = self.groupnorm(x, B, H * W, Cc, f"{pfx}.norm.weight", f"{pfx}.norm.bias", 1e-6, False)
+        h = self.linear(a, f"{pfx}.proj_in.weight", Cc, Cc, f"{pfx}.proj_in.bias")
+        for k in range(depth):
+            h = self.transformer_block(h, B, H * W, Cc, f"{pfx}.transformer_blocks.{k}", ctx, n_ctx)
+        return self.linear(h, f"{pfx}.proj_out.weight", Cc, Cc, f"{pfx}.proj_out.bias", residual=x)
+
+    def embeddings(self, t_f32: torch.Tensor, pooled: torch.Tensor, time_ids_f32: torch.Tensor, B) -> Act:
+        """time_embedding(sinus(t)) + add_embedding([pooled, sinus(time_ids)]) -> SiLU (shared by all resnets)."""
+        cfg = self.cfg
+        boc0 = cfg["block_out_channels"][0]
+        temb = boc0 * 4
+        adim = cfg["addition_time_embed_dim"]
+        pin = cfg["projection_class_embeddings_input_dim"]
+        pooled_dim = pin - 6 * adim
+        dev = t_f32.device
+        ts = Act(ops.timestep_embedding(t_f32, boc0))
+        e1 = self.linear(ts, "time_embedding.linear_1.weight", temb, boc0, "time_embedding.linear_1.bias", need_dx=False)
+        e1s = self.silu(e1)
+        et = self.linear(e1s, "time_embedding.linear_2.weight", temb, temb, "time_embedding.linear_2.bias")
+        tid = ops.timestep_embedding(time_ids_f32.reshape(-1), adim)  # [B*6, adim] == [B, 6*adim]
+        add_in = torch.empty((B, pin), device=dev, dtype=bf16)
+        ops.copy2d(pooled, add_in, B, pooled_dim, pooled_dim, pin)
+        ops.copy2d(tid, add_in[:, pooled_dim:], B, 6 * adim, 6 * adim, pin)
+        a1 = self.linear(Act(add_in), "add_embedding.linear_1.weight", temb, pin, "add_embedding.linear_1.bias",
+                         need_dx=False)
+        a1s = self.silu(a1)
+        emb = self.linear(a1s, "add_embedding.linear_2.weight", temb, temb, "add_embedding.linear_2.bias", residual=et)
+        return self.silu(emb)
+
+    # ------------------------------------------------------------------ whole network
+    def forward(self, x_nhwc8: torch.Tensor, t_f32: torch.Tensor, ctx: torch.Tensor, pooled: torch.Tensor,
+                time_ids_f32: torch.Tensor, B: int, H: int, W: int) -> Act:
+        """x_nhwc8: [B*H*W, 8] bf16 (4 latent channels + 4 zero pad).  Returns pred as Act([B*H*W, 8])."""
+        cfg = self.cfg
+        st = self.store
+        self.tape = []
+        boc = cfg["block_out_channels"]
+        depth = cfg["transformer_layers_per_block"]
+        L = cfg["layers_per_block"]
+        n_ctx = ctx.shape[0] // B
+        cin = cfg["in_channels"]
+        assert cin <= 8 and cfg["out_channels"] <= 8
+        dev = x_nhwc8.device
+
+        emb_silu = self.embeddings(t_f32, pooled, time_ids_f32, B)
+
+        # conv_in: weight repacked to Cin padded to 8 (K = 72)
+        w_in = st.v("conv_in.weight").view(boc[0] * 9, cin)
+        wk_in = torch.zeros((boc[0], 72), device=dev, dtype=bf16)
+        ops.copy2d_any(w_in, wk_in.view(boc[0] * 9, 8), boc[0] * 9, cin, cin, 8)
+        gwk_in = torch.zeros((boc[0], 72), device=dev, dtype=bf16)
+        h = self.conv3x3(Act(x_nhwc8), B, H, W, 8, boc[0], "conv_in.weight", "conv_in.bias", need_dx=False,
+                         Wk=wk_in, gWk=gwk_in)
+
+        def conv_in_wgrad():
+            ops.copy2d_any(gwk_in.view(boc[0] * 9, 8), st.gv("conv_in.weight").view(boc[0] * 9, cin), boc[0] * 9, cin, 8,
+                           cin, accumulate=True)
+
+        self.tape.insert(len(self.tape) - 1, conv_in_wgrad)  # runs after conv_in's backward
+
+        skips = [(h, boc[0])]
+        ch, cH, cW = boc[0], H, W
+        for i, cout in enumerate(boc):
+            last = i == len(boc) - 1
+            for j in range(L):
+                h = self.resnet(h, emb_silu, B, cH, cW, ch, cout, f"down_blocks.{i}.resnets.{j}")
+                ch = cout
+                if depth[i] > 0:
+                    h = self.transformer(h, B, cH, cW, ch, depth[i], f"down_blocks.{i}.attentions.{j}", ctx, n_ctx)
+                skips.append((h, ch))
+            if not last:
+                h = self.conv3x3(h, B, cH, cW, ch, ch, f"down_blocks.{i}.downsamplers.0.conv.weight",
+                                 f"down_blocks.{i}.downsamplers.0.conv.bias", stride=2)
+                cH, cW = ops.conv_out_hw(cH, cW, 2, False)
+                skips.append((h, ch))
+
+        h = self.resnet(h, emb_silu, B, cH, cW, ch, ch, "mid_block.resnets.0")
+        h = self.transformer(h, B, cH, cW, ch, depth[-1], "mid_block.attentions.0", ctx, n_ctx)
+        h = self.resnet(h, emb_silu, B, cH, cW, ch, ch, "mid_block.resnets.1")
+
+        rev, rdepth = list(reversed(boc)), list(reversed(depth))
+        for i, cout in enumerate(rev):
+            last = i == len(rev) - 1
+            for j in range(L + 1):
+                s, sc = skips.pop()
+                h = self.concat(h, s, B * cH * cW, ch, sc)
+                h = self.resnet(h, emb_silu, B, cH, cW, ch + sc, cout, f"up_blocks.{i}.resnets.{j}")
+                ch = cout
+                if rdepth[i] > 0:
+                    h = self.transformer(h, B, cH, cW, ch, rdepth[i], f"up_blocks.{i}.attentions.{j}", ctx, n_ctx)
+            if not last:
+                h = self.conv3x3(h, B, cH, cW, ch, ch, f"up_blocks.{i}.upsamplers.0.conv.weight",
+                                 f"up_blocks.{i}.upsamplers.0.conv.bias", up=True)
+                cH, cW = cH * 2, cW * 2
+
+        a = self.groupnorm(h, B, cH * cW, ch, "conv_norm_out.weight", "conv_norm_out.bias", cfg["norm_eps"], True)
+        # conv_out: Cout padded to 8 rows (zero rows / zero bias) so the GEMM's N and the dgrad's K satisfy TMA
+        co = cfg["out_channels"]
+        K = 9 * ch
+        wk_out = torch.zeros((8, K), device=dev, dtype=bf16)
+        ops.copy2d(st.w("conv_out.weight", co, K), wk_out, co, K, K, K)
+        gwk_out = torch.zeros((8, K), device=dev, dtype=bf16)
+        b_out = torch.zeros(8, device=dev, dtype=bf16)
+        ops.copy2d_any(st.v("conv_out.bias").view(1, co), b_out.view(1, 8), 1, co, co, 8)
+        pred = self.conv3x3(a, B, cH, cW, ch, co, "conv_out.weight", "conv_out.bias", Wk=wk_out, gWk=gwk_out,
+                            bias_t=b_out, Npad=8)
+
+        def conv_out_pgrad():
+            ops.copy2d(gwk_out, st.g("conv_out.weight", co, K), co, K, K, K, accumulate=True)
+            gb = torch.zeros(8, device=dev, dtype=bf16)
+            ops.colsum(pred.g, gb, accumulate=False)
+            ops.copy2d_any(gb.view(1, 8), st.gv("conv_out.bias").view(1, co), 1, co, 8, co, accumulate=True)
+
+        self.tape.insert(len(self.tape) - 1, conv_out_pgrad)
+        self._out = pred
+        return pred
+
+    def detach_tape(self):
+        """Hand the recorded tape to the caller (one tape per forward call)."""
+        t = (self.tape, self._out)
+        self.tape, self._out = [], None
+        return t
+
+    def backward(self, dpred_nhwc8: torch.Tensor, saved=None):
+        """Replay a tape: fills ParamStore.grad (+=).  dpred: [B*H*W, 8] bf16 (pad channels must be zero)."""
+        tape, out = saved if saved is not None else self.detach_tape()
+        out.g = dpred_nhwc8
+        for fn in reversed(tape):
+            fn()
+        tape.clear()
+
+
+class _UNetFunction(torch.autograd.Function):
+    """Bridges the hand-written backward into torch autograd so `loss.backward()` of the reference loops works
+    unchanged (ddpm_trainer.py:268-271, flow_matching_trainer.py:249-252).  The flat-parameter tensor is an input so
+    that autograd considers the output differentiable; parameter gradients are written by the kernels directly
+    into `p.grad` (accumulating), the returned gradient for it is None."""
+
+    @staticmethod
+    def forward(ctx, unet, sample, t_f32, ehs, pooled, time_ids, anchor):
+        B, Cc, H, W = sample.shape
+        eng = unet.engine
+        x8 = ops.nchw_to_nhwc(sample, 8)
+        pred = eng.forward(x8, t_f32, ehs, pooled, time_ids, B, H, W)
+        ctx.saved_tape = eng.detach_tape()
+        ctx.unet = unet
+        ctx.shape = (B, Cc, H, W)
+        ctx.out_dtype = sample.dtype if sample.dtype in (bf16, torch.float32) else bf16
+        return ops.nhwc_to_nchw(pred.d, B, Cc, H, W, 8, dtype=ctx.out_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        B, Cc, H, W = ctx.shape
+        g8 = ops.nchw_to_nhwc(grad_out.contiguous(), 8)
+        ctx.unet.engine.backward(g8, ctx.saved_tape)
+        ctx.saved_tape = None
+        return (None,) * 7
+
+
+class B200UNet:
+    """Duck-typed replacement for `StableDiffusionXL.unet` (src/models/sdxl.py:38-66).
+
+    Surface honoured: `unet(sample, timestep, encoder_hidden_states, added_cond_kwargs=...)
+    -> object with .sample`, `parameters()`, `named_parameters()`, `state_dict()/load_state_dict()`, `to()`,
+    `train()/eval()`, `zero_grad()`, `save_pretrained()`, no-op `enable_gradient_checkpointing()` and
+    `enable_xformers_memory_efficient_attention()` (flow_matching_trainer.py:60-72).
+    """
+
+    def __init__(self, cfg: Optional[dict] = None, device="cuda"):
+        self.config = dict(SDXL_BASE if cfg is None else cfg)
+        self.store = ParamStore(self.config, device=device)
+        self.engine = UNetEngine(self.store)
+        self.training = True
+        self.dtype = bf16
+        self._anchor = torch.zeros(1, device=device, requires_grad=True)
+
+    # --- nn.Module-like surface ---
+    @property
+    def device(self):
+        return self.store.flat.device
+
+    def parameters(self):
+        return iter(self.store.params.values())
+
+    def named_parameters(self):
+        return iter(self.store.params.items())
+
+    def state_dict(self):
+        return self.store.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        return self.store.load_state_dict(sd, strict)
+
+    def to(self, *args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, (str, torch.device)) and torch.device(a).type == "cuda":
+                if self.store.flat.device != torch.device(a):
+                    self.store.to(a)
+                    self.engine = UNetEngine(self.store)
+                    self._anchor = torch.zeros(1, device=a, requires_grad=True)
+            elif isinstance(a, torch.dtype) and a not in (bf16,):
+                raise RuntimeError("B200UNet computes in bf16 only (the reference casts the UNet to bf16, "
+                                   "sdxl_trainer.py:52-55)")
+        return self
+
+    def train(self, mode: bool = True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def requires_grad_(self, flag=True):
+        for p in self.parameters():
+            p.requires_grad_(flag)
+        return self
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.store.grad.zero_()
+
+    def enable_gradient_checkpointing(self):  # 180 GB HBM: activations are kept
+        return None
+
+    def enable_xformers_memory_efficient_attention(self, *a, **k):  # attention is our own kernel
+        return None
+
+    def save_pretrained(self, path, safe_serialization=True, **kw):
+        import json
+        import os
+        os.makedirs(path, exist_ok=True)
+        sd = {k: v.contiguous() for k, v in self.state_dict().items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file({k: v.cpu() for k, v in sd.items()}, os.path.join(path, "diffusion_pytorch_model.safetensors"))
+        else:
+            torch.save(sd, os.path.join(path, "diffusion_pytorch_model.bin"))
+        with open(os.path.join(path, "config.json"), "w") as f:
+            json.dump({"_class_name": "UNet2DConditionModel", **{k: (list(v) if isinstance(v, tuple) else v)
+                                                                for k, v in self.config.items()}}, f, indent=1)
+
+    # --- forward ---
+    def __call__(self, sample, timestep, encoder_hidden_states=None, added_cond_kwargs=None, **kw):
+        if added_cond_kwargs is None:
+            raise ValueError("SDXL UNet needs added_cond_kwargs={'text_embeds','time_ids'}")
+        dev = self.device
+        B = sample.shape[0]
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([timestep], device=dev)
+        t = timestep.to(dev).float().reshape(-1)
+        if t.numel() == 1 and B > 1:
+            t = t.expand(B)
+        t = t.contiguous()
+        ehs = encoder_hidden_states.to(dev, bf16).reshape(-1, encoder_hidden_states.shape[-1]).contiguous()
+        pooled = added_cond_kwargs["text_embeds"].to(dev, bf16).reshape(B, -1).contiguous()
+        tid = added_cond_kwargs["time_ids"].to(dev).float().reshape(B, -1).contiguous()
+        sample = sample.to(dev)
+        out = _UNetFunction.apply(self, sample, t, ehs, pooled, tid, self._anchor)
+        return SimpleNamespace(sample=out)
+
+    forward = __call__
