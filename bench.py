@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — SDXL-base 1024^2 bf16 training images/sec on N x B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--method ddpm|flow_matching]
+  N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One "step" = one optimizer step of the reference's default micro-batch (bs=4 per GPU, latent [4,4,128,128], text
+[4,77,2048]): Philox noise + noising + full SDXL UNet forward + full backward + MSE loss (+ one all-reduce of the flat
+gradient buffer when N>1) + grad-norm clip + fused AdamW.  Synthetic data, seeded random-init weights (no checkpoints
+offline).  `value` is timed with the batch resident in HBM; `e2e` goes through the plugin API
+(`B200DDPMTrainer._execute_training_step(batch)`) with pinned-host inputs copied H2D and the loss/metrics read back
+D2H inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "sdxl_base_1024px_bf16_train_images_per_sec"
+IMG_FLOPS_1024 = None  # filled from the analytical model
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=float(d["bf16_tflops"]), sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    hbm=float(d["hbm_gbs"]), src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+def _config_ns(method: str):
+    return SimpleNamespace(
+        model=SimpleNamespace(num_timesteps=1000, sigma_min=0.002, sigma_max=20000.0, use_ztsnr=True,
+                              min_snr_gamma=None, prediction_type="v_prediction"),
+        training=SimpleNamespace(method=method, prediction_type="v_prediction", gradient_accumulation_steps=1,
+                                 clip_grad_norm=1.0, batch_size=4))
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML during the timed region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def stop(self):
+        self._halt.set()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _init_weights_(unet, seed: int):
+    """Seeded synthetic init on device: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) weights, unit norm scales, small biases."""
+    g = torch.Generator(device=unet.device).manual_seed(seed)
+    with torch.no_grad():
+        for name, p in unet.named_parameters():
+            if p.dim() >= 2:
+                bound = 1.0 / (p[0].numel() ** 0.5)
+                p.copy_((torch.rand(p.shape, device=p.device, generator=g) * 2 - 1) * bound)
+            elif name.endswith("weight"):
+                p.fill_(1.0)
+            else:
+                p.copy_((torch.rand(p.shape, device=p.device, generator=g) * 2 - 1) * 0.02)
+
+
+def _synthetic_batch(B, H, W, seed, pin=True):
+    g = torch.Generator().manual_seed(seed)
+    b = {
+        "vae_latents": torch.randn(B, 4, H, W, generator=g),
+        "prompt_embeds": torch.randn(B, 77, 2048, generator=g).to(torch.bfloat16),
+        "pooled_prompt_embeds": torch.randn(B, 1280, generator=g).to(torch.bfloat16),
+        "time_ids": torch.tensor([[8.0 * W, 8.0 * H, 0, 0, 8.0 * W, 8.0 * H]]).repeat(B, 1)[:, None],
+    }
+    if pin:
+        b = {k: v.pin_memory() for k, v in b.items()}
+    b["metadata"] = [{} for _ in range(B)]
+    return b
+
+
+def _time_gemm_roofline(ops, peaks):
+    """Dominant kernel = gemm_tcgen05_kernel<128,3>; timed live on the GEGLU up-projection shape (41.7 % of FLOPs)."""
+    M, N, K = 4096, 10240, 1280
+    nset = 6  # rotate operands: 6 x (26 MB W + 84 MB D) >> 126 MB L2
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    Ws = [torch.randn(N, K, device="cuda").to(torch.bfloat16) * 0.03 for _ in range(nset)]
+    Ds = [torch.empty(M, N, device="cuda", dtype=torch.bfloat16) for _ in range(nset)]
+    for i in range(nset):
+        ops.linear_fwd(x, Ws[i], out=Ds[i])
+    torch.cuda.synchronize()
+    iters = 60
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        ops.linear_fwd(x, Ws[i % nset], out=Ds[i % nset])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * M * N * K
+    ach = flops / (ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    return {"bound": "tensor", "achieved": round(ach, 1), "peak": peaks["burst"], "unit": "TFLOP/s",
+            "frac": round(ach / peaks["burst"], 4), "traffic": traffic,
+            "kernel": "gemm_tcgen05_kernel<128,3> on M=4096,N=10240,K=1280 (GEGLU up-projection), "
+                      f"{flops / 1e9:.1f} GFLOP/launch, {ms * 1e3:.1f} us/launch, peak = {peaks['src']} burst bf16"}
+
+
+def _cpu_baseline(seconds_budget=30.0, threads=None):
+    """The oracle (PyTorch-eager bf16 on the host CPU = the reference's own CPU path) on a bounded sample."""
+    from oracle.unet_sdxl import OracleUNet
+    from sdxl_training_improvements_b200.flops import train_step_flops
+    threads = threads or torch.get_num_threads()
+    t0 = time.time()
+    with torch.device("meta"):
+        m = OracleUNet()
+    m = m.to(torch.bfloat16).to_empty(device="cpu")
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() >= 2:
+                p.uniform_(-0.02, 0.02)
+            else:
+                p.fill_(0.5)
+    build_s = time.time() - t0
+
+    def one(hw):
+        x = torch.randn(1, 4, hw, hw).to(torch.bfloat16)
+        ctx = torch.randn(1, 77, 2048).to(torch.bfloat16)
+        pooled = torch.randn(1, 1280).to(torch.bfloat16)
+        tid = torch.tensor([[8.0 * hw, 8.0 * hw, 0, 0, 8.0 * hw, 8.0 * hw]])
+        t = time.time()
+        out = m(x, torch.tensor([500]), ctx, added_cond_kwargs={"text_embeds": pooled, "time_ids": tid}).sample
+        out.float().square().mean().backward()
+        for p in m.parameters():
+            p.grad = None
+        return time.time() - t
+
+    probe = one(32)  # also warms the allocator / threads
+    probe = min(probe, one(32))
+    full = train_step_flops(None, 128, 128)
+    best = 32
+    for hw in (128, 96, 64, 48):
+        est = probe * train_step_flops(None, hw, hw) / train_step_flops(None, 32, 32)
+        if est <= seconds_budget:
+            best = hw
+            break
+    dt = one(best) if best != 32 else probe
+    frac = train_step_flops(None, best, best) / full
+    return m, {"value": round(frac / dt, 5), "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"oracle (PyTorch eager bf16, CPU) fwd+bwd of the full SDXL UNet, B=1, latent {best}x{best} "
+                         f"({dt:.1f} s), scaled to 1024^2-image equivalents by algorithmic FLOPs ({frac:.3f} img/step); "
+                         f"model build {build_s:.0f} s untimed"}, one
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from sdxl_training_improvements_b200.flops import train_step_flops
+    total_steps = args.steps + args.warmup
+    per_step = max(3.0, 150.0 / max(1, total_steps))
+    m, cb, one = _cpu_baseline(seconds_budget=per_step)
+    import re
+    hw = int(re.search(r"latent (\d+)x", cb["sample"]).group(1))
+    for _ in range(args.warmup):
+        one(hw)
+    t0 = time.time()
+    for _ in range(args.steps):
+        one(hw)
+    dt = (time.time() - t0) / max(1, args.steps)
+    frac = train_step_flops(None, hw, hw) / train_step_flops(None, 128, 128)
+    val = frac / dt
+    cb["value"] = round(val, 5)
+    out = {"impl": "reference", "metric": METRIC, "value": round(val, 5), "unit": "images/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "SDXL-base UNet, ddpm v_prediction, 1024^2, bf16 (configs[1]); CPU sample: B=1 "
+                                  f"latent {hw}x{hw} fwd+bwd per step, FLOP-scaled to 1024^2 images"},
+           "cpu_baseline": cb,
+           "e2e": {"value": round(val, 5), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args):
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the sm_100a kernels have no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = torch.distributed
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from sdxl_training_improvements_b200 import _lib, ops
+    from sdxl_training_improvements_b200.flops import train_step_flops
+    from sdxl_training_improvements_b200.trainer import B200AdamW, create_trainer
+    from sdxl_training_improvements_b200.unet import B200UNet
+
+    peaks = _peaks()
+    B, H, W = 4, 128, 128
+    cfg = _config_ns(args.method)
+    unet = B200UNet(device=f"cuda:{local}")
+    _init_weights_(unet, seed=1234)  # identical on every rank (replicated parameters)
+    opt = B200AdamW(unet, lr=4e-7, weight_decay=1e-2, master_weights=True)
+    trainer = create_trainer(cfg, unet, opt, device=f"cuda:{local}", seed=1000 + rank)
+    batch = _synthetic_batch(B, H, W, seed=77 + rank)
+    h2d = sum(v.numel() * v.element_size() for k, v in batch.items() if torch.is_tensor(v))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up through the public plugin API (also JITs nothing: all kernels are prebuilt) ----
+    for _ in range(max(args.warmup, 3)):
+        trainer._execute_training_step(batch)
+    barrier()
+
+    # ---- (1) device-resident timing: `value` ----
+    from sdxl_training_improvements_b200.trainer import _prep_batch, allreduce_gradients
+    dev_batch = _prep_batch(batch, unet.device)
+    K = args.steps
+    sched = trainer.noise_scheduler if args.method == "ddpm" else None
+    gen = torch.Generator().manual_seed(5 + rank)
+    if args.method == "ddpm":
+        ts = [sched.sample_timesteps(B, generator=gen) for _ in range(K)]
+        t_embed = [t.float().cuda() for t in ts]
+        sig = [sched.timestep_to_sigma(t).float().cuda() for t in ts]
+    else:
+        from sdxl_training_improvements_b200.trainer import sample_logit_normal
+        ts = [sample_logit_normal((B,), generator=gen) for _ in range(K)]
+        t_embed = [t.float().cuda() for t in ts]
+        sig = t_embed
+    core = trainer.core
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        core.step_no_autograd(latents=dev_batch["latents"], ctx=dev_batch["ctx"], pooled=dev_batch["pooled"],
+                              time_ids=dev_batch["time_ids"], t_embed=t_embed[i], sig_or_t=sig[i], weight=None,
+                              loss_scale=1.0)
+        if world > 1:
+            allreduce_gradients(unet)
+        opt.fused_step(max_norm=1.0, grad_scale=1.0 / world)
+        opt.zero_grad()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms_dev = e0.elapsed_time(e1) / K
+
+    # ---- (2) end-to-end through the plugin API with host buffers: `e2e` ----
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last_loss = None
+    for i in range(K):
+        loss, metrics = trainer._execute_training_step(batch)
+        last_loss = metrics["loss"]  # python float: the D2H read of the step's result already happened
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3) / K
+    clocks = sampler.stop()
+
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        step_flops = train_step_flops(None, H, W) * B
+        value = world * B / (ms_dev * 1e-3)
+        e2e_v = world * B / (ms_e2e * 1e-3)
+        roof = _time_gemm_roofline(ops, peaks)
+        roof["step_tflops_per_gpu"] = round(step_flops / (ms_dev * 1e-3) / 1e12, 1)
+        roof["step_frac_of_sustained_peak"] = round(step_flops / (ms_dev * 1e-3) / 1e12 / peaks["sustained"], 4)
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            _, cb, _ = _cpu_baseline(seconds_budget=25.0)
+        out = {"metric": METRIC, "value": round(value, 4), "unit": "images/s", "n_gpus": world, "steps": K,
+               "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev, 2), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": f"SDXL-base UNet, {args.method} v_prediction, bs=4/GPU, 1024^2 (latent 128x128), "
+                                      "bf16, full fwd+bwd+loss+clip+AdamW (configs[1])",
+                          "global_batch": B * world, "parallelism": f"dp{world}",
+                          "l2": "working set >> L2: 5.1 GB of weights + ~40 GB activations streamed every step",
+                          "last_loss": last_loss},
+               "e2e": {"value": round(e2e_v, 4), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": 4 + 6 * 8, "ms_per_step": round(ms_e2e, 2),
+                       "api": "B200DDPMTrainer._execute_training_step(batch) with pinned host tensors"},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--method", default="ddpm", choices=["ddpm", "flow_matching"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

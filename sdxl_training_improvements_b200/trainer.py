@@ -1,0 +1,404 @@
+"""Drop-in training-step plugins for the reference's `src/training` surface, running on the B200 kernels.
+
+Mirrors (same names, argument meaning and error behaviour):
+  * `DDPMTrainer.training_step(batch)`            src/training/trainers/methods/ddpm_trainer.py:280-405
+  * `FlowMatchingTrainer.compute_loss(model, batch, generator=None)`  .../flow_matching_trainer.py:261-356
+  * `NoiseScheduler` (Karras / ZTSNR table, sample_timesteps)         src/training/schedulers/novelai_v3.py:101-184
+  * accumulate / clip / step protocol             .../example_method.py:124-148,191-206 (defect B4 decision)
+  * DDP contract: all-reduce of the UNet gradients only (src/core/distributed.py:142-163, B9)
+
+Host-side logic (which timesteps, which sigma) is the reference's own tiny torch-CPU arithmetic restated; all tensor
+work on latents/activations/gradients runs in libsdxl_b200 kernels: Philox noise, noising, target, UNet fwd/bwd,
+MSE (+min-SNR / tag weights), clamp/fallback, grad-norm, AdamW.
+"""
+from __future__ import annotations
+
+import math
+import time
+from types import SimpleNamespace
+from typing import Any, Dict, Optional
+
+import torch
+
+from . import ops
+from .unet import B200UNet, bf16
+
+LATENT_PAD = 8
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# schedule (host side; reference: novelai_v3.py)
+# ----------------------------------------------------------------------------------------------------------------
+def get_karras_sigmas(n_sigmas: int, sigma_min: float, sigma_max: float, rho: float = 7.0, device=None) -> torch.Tensor:
+    """novelai_v3.py:160-184 — descending fp32 table (index 0 = sigma_max)."""
+    ramp = torch.linspace(0, 1, n_sigmas, device=device)
+    min_inv_rho = sigma_min ** (1 / rho)
+    max_inv_rho = sigma_max ** (1 / rho)
+    return (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho
+
+
+class NoiseScheduler:
+    """The subset of the reference's NoiseScheduler the training step uses (novelai_v3.py:101-151)."""
+
+    def __init__(self, config=None, device="cpu"):
+        m = getattr(config, "model", None)
+        self.num_timesteps = int(getattr(m, "num_timesteps", 1000))
+        self.sigma_min = float(getattr(m, "sigma_min", 0.002))
+        self.sigma_max = float(getattr(m, "sigma_max", 20000.0))
+        self.use_ztsnr = bool(getattr(m, "use_ztsnr", True))
+        self.rho = float(getattr(m, "rho", 7.0))  # B2: ModelConfig has no rho -> function default
+        self.sigma_data = 1.0
+        self.device = device
+        # the reference rebuilds this table on every call (novelai_v3.py:134-137); it is step-invariant
+        self.sigmas = get_karras_sigmas(self.num_timesteps, self.sigma_min,
+                                        20000.0 if self.use_ztsnr else self.sigma_max, self.rho)
+
+    def get_sigmas(self, n: int) -> torch.Tensor:
+        return get_karras_sigmas(n, self.sigma_min, 20000.0 if self.use_ztsnr else self.sigma_max, self.rho)
+
+    def timestep_to_sigma(self, timesteps: torch.Tensor) -> torch.Tensor:
+        return self.sigmas[timesteps.cpu()]
+
+    def get_snr(self, timesteps: torch.Tensor) -> torch.Tensor:
+        return (self.sigma_data / self.timestep_to_sigma(timesteps)) ** 2
+
+    def sample_timesteps(self, batch_size: int, device=None, generator=None) -> torch.Tensor:
+        """novelai_v3.py:139-151 (B1: `device` accepted and ignored; B13: uniform)."""
+        if self.use_ztsnr:
+            u = torch.rand(batch_size, generator=generator)
+            return (u * self.num_timesteps).long()
+        return torch.randint(0, self.num_timesteps, (batch_size,), generator=generator)
+
+
+def sample_logit_normal(shape, dtype=bf16, mean=0.0, std=1.0, generator=None) -> torch.Tensor:
+    """flow_matching_trainer.py:373-385, drawn in the model dtype (B20)."""
+    normal = torch.randn(shape, dtype=dtype, generator=generator)
+    return torch.sigmoid(mean + std * normal)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused loss: noise -> noising -> UNet -> MSE, as ONE autograd node
+# ----------------------------------------------------------------------------------------------------------------
+class _FusedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, core, anchor, args):
+        loss = core._forward(**args)
+        ctx.core = core
+        ctx.saved = core._saved
+        core._saved = None
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        tape, dpred = ctx.saved
+        ctx.saved = None
+        ops.scale_bf16(dpred, grad_out.reshape(1).float().contiguous(), 1.0)
+        ctx.core.unet.engine.backward(dpred, tape)
+        return None, None, None
+
+
+class FusedLossCore:
+    """Device-side part of one micro-step.  `method`: "ddpm" | "flow_matching"."""
+
+    def __init__(self, unet: B200UNet, method: str, prediction_type: str = "v_prediction", use_ztsnr: bool = True,
+                 seed: int = 0):
+        self.unet = unet
+        self.method = method
+        self.prediction_type = prediction_type
+        self.use_ztsnr = use_ztsnr
+        dev = unet.device
+        self.seed_offset = torch.tensor([seed, 0], device=dev, dtype=torch.int64)
+        self.loss_sum = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.ok = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.stats = torch.zeros(6, device=dev, dtype=torch.float64)  # |eps|,eps^2,|pred|,pred^2,|x|,x^2
+        self._anchor = torch.zeros(1, device=dev, requires_grad=True)
+        self._saved = None
+        self.last: Dict[str, torch.Tensor] = {}
+
+    def _forward(self, latents, ctx, pooled, time_ids, t_embed, sig_or_t, weight, loss_scale, noise=None):
+        """latents fp32 NCHW holding bf16-representable values; returns 0-d fp32 loss (device)."""
+        B, Cc, H, W = latents.shape
+        HW = H * W
+        n = B * Cc * HW
+        if noise is None:
+            noise = ops.randn(n, self.seed_offset, 1, round_bf16=True)
+            ops.philox_advance(self.seed_offset, 1)
+        mode = 0 if self.method == "ddpm" else 1
+        noisy, target = ops.make_noisy(latents, noise, sig_or_t, mode, self.prediction_type == "v_prediction",
+                                       self.use_ztsnr, B, Cc, HW, LATENT_PAD)
+        pred = self.unet.engine.forward(noisy, t_embed, ctx, pooled, time_ids, B, H, W)
+        tape = self.unet.engine.detach_tape()
+        dpred = torch.empty_like(pred.d)
+        self.loss_sum.zero_()
+        self.stats.zero_()
+        ops.mse_loss(pred.d, target, weight, self.loss_sum, dpred, loss_scale / n, B, Cc, HW, LATENT_PAD)
+        ops.finalize_loss(self.loss_sum, n, loss_scale, self.loss, self.ok, dpred)
+        ops.abs_sq_sums(noise, self.stats[0:2])
+        ops.abs_sq_sums(pred.d, self.stats[2:4], LATENT_PAD, Cc)
+        ops.abs_sq_sums(latents, self.stats[4:6])
+        self._saved = ((tape[0], tape[1]), dpred)
+        self.last = {"pred": pred.d, "target": target, "noisy": noisy, "noise": noise, "numel": n}
+        return self.loss.clone().reshape(())
+
+    def loss_fn(self, **args) -> torch.Tensor:
+        return _FusedLoss.apply(self, self._anchor, args)
+
+    def step_no_autograd(self, grad_scale: float = 1.0, **args) -> torch.Tensor:
+        """forward + backward without torch autograd (used by the graph-captured bench/step path)."""
+        loss = self._forward(**args)
+        tape, dpred = self._saved
+        self._saved = None
+        if grad_scale != 1.0:
+            ops.scale_bf16(dpred, None, grad_scale)
+        self.unet.engine.backward(dpred, tape)
+        return loss
+
+
+def _prep_batch(batch: Dict[str, Any], device) -> Dict[str, torch.Tensor]:
+    """Batch-dict contract of the reference (dataset.py:209-229; ddpm_trainer.py:284-296).  Tensors may arrive on CPU
+    or GPU in any float dtype; cast to the UNet dtype like the flow path does (flow_matching_trainer.py:288-291, B21)."""
+    required = {"vae_latents", "prompt_embeds", "pooled_prompt_embeds", "time_ids", "metadata"}
+    if not all(k in batch for k in required):
+        raise ValueError(f"Batch missing required keys: {required - set(batch.keys())}")
+    lat = batch["vae_latents"].to(device, non_blocking=True)
+    B = lat.shape[0]
+    return {
+        "latents": lat.to(bf16).float().contiguous(),
+        "ctx": batch["prompt_embeds"].to(device, non_blocking=True).to(bf16).reshape(-1, batch["prompt_embeds"].shape[-1]).contiguous(),
+        "pooled": batch["pooled_prompt_embeds"].to(device, non_blocking=True).to(bf16).reshape(B, -1).contiguous(),
+        "time_ids": batch["time_ids"].to(device, non_blocking=True).float().reshape(B, -1).contiguous(),
+    }
+
+
+def _tag_weight_mean(batch) -> Optional[float]:
+    """ddpm_trainer.py:348-368: mean over samples of the mean tag weight, if every sample has weights."""
+    md = batch.get("metadata")
+    if isinstance(md, (list, tuple)) and md and all(isinstance(m, dict) and "tag_info" in m for m in md):
+        ws = []
+        for m in md:
+            iw = [td["weight"] for tags in m["tag_info"]["tags"].values() for td in tags]
+            if not iw:
+                return None
+            ws.append(sum(iw) / len(iw))
+        return float(sum(ws) / len(ws))
+    return None
+
+
+class _StepBase:
+    """Shared constructor signature of the reference trainers (base_router.py:15-31; sdxl_trainer.py:18-36)."""
+
+    def __init__(self, model, optimizer, train_dataloader=None, device=None, wandb_logger=None, config=None, **kwargs):
+        self.model = model
+        self.unet: B200UNet = getattr(model, "unet", model)
+        if not isinstance(self.unet, B200UNet):
+            raise TypeError("model.unet must be a B200UNet (there is no CPU / diffusers fallback on this path)")
+        self.optimizer = optimizer
+        self.train_dataloader = train_dataloader
+        self.device = torch.device(device) if device is not None else self.unet.device
+        self.wandb_logger = wandb_logger
+        self.config = config
+        tr = getattr(config, "training", None)
+        self.gradient_accumulation_steps = int(getattr(tr, "gradient_accumulation_steps", 1))
+        self.clip_grad_norm = float(getattr(tr, "clip_grad_norm", 1.0))
+        self.prediction_type = getattr(tr, "prediction_type", "v_prediction")
+        self.world_size = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+
+    def _lr(self):
+        try:
+            return float(self.optimizer.param_groups[0]["lr"])
+        except Exception:
+            return 0.0
+
+    # --- accumulate / clip / step protocol (example_method.py:124-148, 191-206; flow_matching_trainer.py:172-189) ---
+    def _execute_training_step(self, batch, accumulate: bool = False, is_last_accumulation_step: bool = True):
+        out = self.compute_loss(batch) if not isinstance(self, B200FlowMatchingTrainer) else self.compute_loss(self.model, batch)
+        loss = out["loss"]
+        if accumulate:
+            loss = loss / self.gradient_accumulation_steps
+        loss.backward()
+        if not accumulate or is_last_accumulation_step:
+            self.optimizer_step()
+        return out["loss"].detach(), out["metrics"]
+
+    def optimizer_step(self):
+        if self.world_size > 1:
+            allreduce_gradients(self.unet)
+        if hasattr(self.optimizer, "fused_step"):
+            self.optimizer.fused_step(max_norm=self.clip_grad_norm, grad_scale=1.0 / self.world_size)
+        else:  # a reference optimizer reading p.grad (adamw_bfloat16/__init__.py:92-119)
+            if self.world_size > 1:
+                self.unet.store.grad.mul_(1.0 / self.world_size)
+            if self.clip_grad_norm and self.clip_grad_norm > 0:
+                torch.nn.utils.clip_grad_norm_(list(self.unet.parameters()), self.clip_grad_norm)
+            self.optimizer.step()
+        self.optimizer.zero_grad()
+
+    def train(self, num_epochs: int):
+        """Minimal loop with the reference's protocol; logging/checkpoint plumbing is out of scope."""
+        N = self.gradient_accumulation_steps
+        history = []
+        self.optimizer.zero_grad()
+        for epoch in range(num_epochs):
+            for step, batch in enumerate(self.train_dataloader):
+                t0 = time.time()
+                try:
+                    loss, metrics = self._execute_training_step(batch, accumulate=N > 1,
+                                                                is_last_accumulation_step=(step + 1) % N == 0)
+                except Exception:
+                    if isinstance(self, B200FlowMatchingTrainer):
+                        raise  # flow loop re-raises (flow_matching_trainer.py:226-228)
+                    continue   # ddpm loop logs and continues (ddpm_trainer.py:202-204)
+                metrics["step_time"] = time.time() - t0
+                history.append(metrics)
+                if self.wandb_logger is not None and hasattr(self.wandb_logger, "log_metrics"):
+                    self.wandb_logger.log_metrics(metrics)
+        return history
+
+
+class B200DDPMTrainer(_StepBase):
+    """`training.method: ddpm` — replaces DDPMTrainer (ddpm_trainer.py:26)."""
+    name = "ddpm"
+
+    def __init__(self, model, optimizer, train_dataloader=None, device=None, wandb_logger=None, config=None, **kwargs):
+        super().__init__(model, optimizer, train_dataloader, device, wandb_logger, config, **kwargs)
+        self.noise_scheduler = NoiseScheduler(config, "cpu")
+        m = getattr(config, "model", None)
+        self.min_snr_gamma = getattr(m, "min_snr_gamma", None)
+        self.core = FusedLossCore(self.unet, "ddpm", self.prediction_type, self.noise_scheduler.use_ztsnr,
+                                  seed=int(kwargs.get("seed", 0)))
+
+    def training_step(self, batch: Dict[str, Any], noise: Optional[torch.Tensor] = None,
+                      timesteps: Optional[torch.Tensor] = None) -> Dict[str, Any]:
+        dev = self.device
+        t = _prep_batch(batch, dev)
+        B = t["latents"].shape[0]
+        if timesteps is None:
+            timesteps = self.noise_scheduler.sample_timesteps(B, device=dev)
+        timesteps = timesteps.cpu().long()
+        sig = self.noise_scheduler.timestep_to_sigma(timesteps).float()
+        weight = None
+        if self.min_snr_gamma is not None:  # B3: intended per-sample broadcast
+            snr = (self.noise_scheduler.sigma_data / sig) ** 2
+            weight = torch.minimum(snr, torch.ones_like(snr) * float(self.min_snr_gamma)).float().to(dev)
+        tw = _tag_weight_mean(batch)
+        loss = self.core.loss_fn(latents=t["latents"], ctx=t["ctx"], pooled=t["pooled"], time_ids=t["time_ids"],
+                                 t_embed=timesteps.float().to(dev), sig_or_t=sig.to(dev), weight=weight,
+                                 loss_scale=1.0 if tw is None else tw,
+                                 noise=None if noise is None else noise.to(dev).to(bf16).float().reshape(-1).contiguous())
+        st = self.core.stats.tolist()  # one D2H for all metrics (the reference does 5 .item() syncs)
+        n = self.core.last["numel"]
+        metrics = {
+            "loss": float(loss.detach()),
+            "lr": self._lr(),
+            "timestep_mean": float(timesteps.float().mean()),
+            "noise_scale": st[0] / n,
+            "pred_scale": st[2] / n,
+            "batch_size": B,
+        }
+        if B > 1:
+            metrics["timestep_std"] = float(timesteps.float().std())
+        return {"loss": loss, "metrics": metrics}
+
+    compute_loss = training_step
+
+
+class B200FlowMatchingTrainer(_StepBase):
+    """`training.method: flow_matching` — replaces FlowMatchingTrainer (flow_matching_trainer.py:23)."""
+    name = "flow_matching"
+
+    def __init__(self, model, optimizer, train_dataloader=None, device=None, wandb_logger=None, config=None, **kwargs):
+        super().__init__(model, optimizer, train_dataloader, device, wandb_logger, config, **kwargs)
+        self.core = FusedLossCore(self.unet, "flow_matching", seed=int(kwargs.get("seed", 0)))
+
+    def compute_loss(self, model, batch: Dict[str, Any], generator: Optional[torch.Generator] = None,
+                     x0: Optional[torch.Tensor] = None, t: Optional[torch.Tensor] = None) -> Dict[str, Any]:
+        dev = self.device
+        tb = _prep_batch(batch, dev)
+        B = tb["latents"].shape[0]
+        if t is None:
+            t = sample_logit_normal((B,), bf16, generator=generator)  # bf16 draw (B20)
+        t = t.to(bf16).cpu()
+        weight = None
+        loss_scale = 1.0
+        if "tag_weights" in batch:  # flow_matching_trainer.py:326-328
+            loss_scale = float(batch["tag_weights"].to(bf16).float().mean())
+        tf = t.float().to(dev)
+        loss = self.core.loss_fn(latents=tb["latents"], ctx=tb["ctx"], pooled=tb["pooled"], time_ids=tb["time_ids"],
+                                 t_embed=tf, sig_or_t=tf, weight=weight, loss_scale=loss_scale,
+                                 noise=None if x0 is None else x0.to(dev).to(bf16).float().reshape(-1).contiguous())
+        st = self.core.stats.tolist()
+        metrics = {
+            "loss": float(loss.detach()),
+            "x0_norm": math.sqrt(st[1]),
+            "x1_norm": math.sqrt(st[5]),
+            "time_mean": float(t.float().mean()),
+            "time_std": float(t.float().std()) if B > 1 else 0.0,
+            "velocity_norm": math.sqrt(st[3]),  # B7: from the single forward's prediction
+            "batch_size": B,
+            "lr": self._lr(),
+        }
+        return {"loss": loss, "metrics": metrics}
+
+
+TRAINER_MAP = {"ddpm": B200DDPMTrainer, "flow_matching": B200FlowMatchingTrainer}
+
+
+def create_trainer(config, model, optimizer, train_dataloader=None, device=None, wandb_logger=None, **kw):
+    """Dispatch on `config.training.method` like SDXLTrainer.__init__ (sdxl_trainer.py:128-152)."""
+    method = str(getattr(getattr(config, "training", None), "method", "ddpm")).lower()
+    if method not in TRAINER_MAP:
+        raise ValueError(f"Unsupported training method: {method}")
+    return TRAINER_MAP[method](model, optimizer, train_dataloader, device, wandb_logger, config, **kw)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# optimizer + data parallel
+# ----------------------------------------------------------------------------------------------------------------
+class B200AdamW:
+    """Fused AdamW over the flat buffers (one launch for 2.57 B parameters), optional fp32 master weights.
+    Exposes the torch-optimizer surface the loops touch: step / zero_grad / param_groups / state_dict."""
+
+    def __init__(self, unet: B200UNet, lr=4e-7, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, master_weights=True):
+        self.unet = unet
+        st = unet.store
+        dev = st.flat.device
+        self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, params=list(unet.parameters()))]
+        self.m = torch.zeros(st.total, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(st.total, device=dev, dtype=torch.float32)
+        self.master = st.flat.float() if master_weights else None
+        self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.steps = 0
+
+    def sync_master(self):
+        if self.master is not None:
+            self.master.copy_(self.unet.store.flat.float())
+
+    def fused_step(self, max_norm: float = 0.0, grad_scale: float = 1.0):
+        st = self.unet.store
+        g = self.param_groups[0]
+        self.steps += 1
+        gn = None
+        if max_norm and max_norm > 0:
+            self.gnorm_sq.zero_()
+            ops.sumsq(st.grad, self.gnorm_sq)
+            gn = self.gnorm_sq
+        ops.adamw(st.flat, self.master, st.grad, self.m, self.v, lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1],
+                  eps=g["eps"], weight_decay=g["weight_decay"], step=self.steps, gnorm_sq=gn, max_norm=max_norm or 0.0,
+                  grad_scale=grad_scale)
+
+    def step(self):
+        self.fused_step()
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.unet.store.grad.zero_()
+
+    def state_dict(self):
+        return {"m": self.m, "v": self.v, "master": self.master, "steps": self.steps,
+                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+
+
+def allreduce_gradients(unet: B200UNet):
+    """ONE collective per optimizer step: sum of the flat bf16 gradient buffer over NVLink."""
+    if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        torch.distributed.all_reduce(unet.store.grad, op=torch.distributed.ReduceOp.SUM)
