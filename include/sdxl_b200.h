@@ -115,6 +115,40 @@ int b2_softmax_fwd(const float* S, void* P, int64_t rows, int n_valid, int64_t l
 int b2_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int n_valid, int64_t lds,
                    int64_t ldp, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused attention (flash style, head dim 64): O = softmax(Q K^T * scale) V with no n x n tensor in HBM.
+ * replaces F.scaled_dot_product_attention in diffusers' AttnProcessor2_0 (BasicTransformerBlock.attn1 / attn2) and
+ *   its autograd backward.  tcgen05: S = Q K^T (SS MMA) -> TMEM; exp2 / rescale in registers; bf16 P written back to
+ *   TMEM and used as the A operand of the PV MMA (TS MMA); O accumulates in TMEM.
+ *   Q/K/V/O (and dO, dQ, dK, dV): bf16, logical [B, n, H, 64]; element (b, i, h, d) at base + b*bs + i*ld + h*64 + d,
+ *   so the fused QKV projection output [B*n, 3C] is consumed in place (ld = 3C, bs = n*3C, K = Q + C, V = Q + 2C).
+ *   TMA constraints (checked): bases 16-byte aligned, ld / bs multiples of 8 elements.
+ *   LSE: float [B, H, n_pad], n_pad = b2_attn_lse_rows(n_q) (= n_q rounded up to 128), log2 domain, written by fwd,
+ *   read by bwd.  D: float [B, H, n_pad] scratch written by bwd.  flags bit 0: debug (drain the MMA pipe between
+ *   query blocks in the dK/dV kernel instead of relying on issue-order execution).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b2_attn_args {
+  const void* Q;
+  const void* K;
+  const void* V;
+  void* O;        /* fwd: output; bwd: input */
+  float* LSE;
+  const void* dO; /* bwd only from here */
+  float* D;
+  void* dQ;
+  void* dK;
+  void* dV;
+  int32_t B, H, n_q, n_k;
+  int64_t ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+  int64_t q_bs, k_bs, v_bs, o_bs, do_bs, dq_bs, dk_bs, dv_bs;
+  float scale;
+  int32_t flags;
+} b2_attn_args;
+
+int b2_attn_lse_rows(int n_q);
+int b2_attn_fwd(const b2_attn_args* args, void* stream);
+int b2_attn_bwd(const b2_attn_args* args, void* stream);
+
 /* GEGLU: z[m, j] = u[m, j] * gelu_erf(u[m, F + j]), u: [M, 2F]. replaces diffusers GEGLU.forward + backward. */
 int b2_geglu_fwd(const void* u, void* z, int64_t M, int F, void* stream);
 int b2_geglu_bwd(const void* u, const void* dz, void* du, int64_t M, int F, void* stream);

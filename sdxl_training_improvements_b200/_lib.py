@@ -26,12 +26,27 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("Q", c_p), ("K", c_p), ("V", c_p), ("O", c_p), ("LSE", c_p), ("dO", c_p), ("D", c_p),
+        ("dQ", c_p), ("dK", c_p), ("dV", c_p),
+        ("B", i32), ("H", i32), ("n_q", i32), ("n_k", i32),
+        ("ldq", i64), ("ldk", i64), ("ldv", i64), ("ldo", i64), ("lddo", i64), ("lddq", i64), ("lddk", i64), ("lddv", i64),
+        ("q_bs", i64), ("k_bs", i64), ("v_bs", i64), ("o_bs", i64), ("do_bs", i64), ("dq_bs", i64), ("dk_bs", i64),
+        ("dv_bs", i64),
+        ("scale", f32), ("flags", i32),
+    ]
+
+
 # name -> argtypes (return type is int unless listed in _RESTYPES); mirrors include/sdxl_b200.h one to one.
 SIGNATURES = {
     "b2_version": [],
     "b2_last_error": [],
     "b2_launch_count": [],
     "b2_gemm": [C.POINTER(GemmArgs), c_p],
+    "b2_attn_lse_rows": [i32],
+    "b2_attn_fwd": [C.POINTER(AttnArgs), c_p],
+    "b2_attn_bwd": [C.POINTER(AttnArgs), c_p],
     "b2_im2col3x3": [c_p, c_p, i32, i32, i32, i32, i32, i32, i64, c_p],
     "b2_col2im3x3": [c_p, c_p, i32, i32, i32, i32, i32, i32, i64, i32, c_p],
     "b2_gn_stats": [c_p, i32, i32, i32, i32, f32, c_p, c_p, c_p, c_p],

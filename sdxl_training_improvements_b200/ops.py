@@ -163,6 +163,44 @@ def softmax_bwd(P, dP, dS, rows, n_valid, scale):
     return dS
 
 
+def _attn_args(q, k, v, o, lse, B, H, n_q, n_k, scale, flags=0):
+    """q/k/v/o: 2-D bf16 views [B*n, ld] whose first H*64 columns are this tensor's heads (row stride = .stride(0))."""
+    a = _lib.AttnArgs()
+    a.Q, a.K, a.V, a.O, a.LSE = _p(q), _p(k), _p(v), _p(o), _p(lse)
+    a.B, a.H, a.n_q, a.n_k = int(B), int(H), int(n_q), int(n_k)
+    a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
+    a.q_bs, a.k_bs, a.v_bs, a.o_bs = n_q * q.stride(0), n_k * k.stride(0), n_k * v.stride(0), n_q * o.stride(0)
+    a.scale, a.flags = float(scale), int(flags)
+    return a
+
+
+def attn_lse_rows(n_q: int) -> int:
+    return (n_q + 127) // 128 * 128
+
+
+def attn_fwd(q, k, v, B, H, n_q, n_k, scale, out=None):
+    """O = softmax(Q K^T * scale) V per (sample, head); head dim 64.  Returns (O [B*n_q, H*64] bf16, LSE fp32)."""
+    _need_cuda(q, k, v)
+    if out is None:
+        out = torch.empty((B * n_q, H * 64), device=q.device, dtype=bf16)
+    lse = torch.empty((B, H, attn_lse_rows(n_q)), device=q.device, dtype=torch.float32)
+    a = _attn_args(q, k, v, out, lse, B, H, n_q, n_k, scale)
+    _lib.check(_lib.load().b2_attn_fwd(C.byref(a), _stream()), "b2_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(q, k, v, o, lse, do, dq, dk, dv, B, H, n_q, n_k, scale, flags=0):
+    """dQ, dK, dV (written, not accumulated) of attn_fwd; dq/dk/dv are 2-D bf16 views like q/k/v."""
+    _need_cuda(q, k, v, o, do, dq, dk, dv)
+    a = _attn_args(q, k, v, o, lse, B, H, n_q, n_k, scale, flags)
+    d = torch.empty_like(lse)
+    a.dO, a.D, a.dQ, a.dK, a.dV = _p(do), _p(d), _p(dq), _p(dk), _p(dv)
+    a.lddo, a.lddq, a.lddk, a.lddv = do.stride(0), dq.stride(0), dk.stride(0), dv.stride(0)
+    a.do_bs, a.dq_bs, a.dk_bs, a.dv_bs = n_q * do.stride(0), n_q * dq.stride(0), n_k * dk.stride(0), n_k * dv.stride(0)
+    _lib.check(_lib.load().b2_attn_bwd(C.byref(a), _stream()), "b2_attn_bwd")
+    return dq, dk, dv
+
+
 # --------------------------------------------------------------------------------------- elementwise
 def geglu_fwd(u, F):
     M = u.shape[0]

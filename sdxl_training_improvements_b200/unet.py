@@ -95,9 +95,6 @@ class UNetEngine:
         maxcol = max(maxcol, (M0 // 4) * 9 * boc[1] * 4)  # Upsample2D(640) writes a 128^2 grid of 9*640
         self.ws("col", maxcol, bf16)
         self.ws("dcol", maxcol, bf16)
-        if maxS:
-            self.ws("S", maxS, torch.float32)
-            self.ws("dS", maxS, bf16)
 
     # ------------------------------------------------------------------ primitive layers
     def _pgrad_norm(self, dgb: torch.Tensor, wname: str, bname: str, Cc: int):
@@ -265,20 +262,17 @@ class UNetEngine:
         return self.conv3x3(a2, B, H, W, Cout, Cout, f"{pfx}.conv2.weight", f"{pfx}.conv2.bias", residual=sc)
 
     def attention(self, xn: Act, res: Act, B, n, Cc, pfx, ctx: Optional[torch.Tensor], n_ctx: int) -> Act:
-        """softmax(Q K^T / 8) V with materialised logits (round-1 path), then to_out + residual."""
+        """x + to_out(softmax(Q K^T / 8) V): fused QKV (self) / Q + KV (cross) projections, the flash-style tcgen05
+        attention core (no n x n tensor in HBM), then to_out + bias + residual in one GEMM epilogue."""
         st = self.store
         heads = Cc // HEAD_DIM
-        d = HEAD_DIM
-        scale = 1.0 / math.sqrt(d)
-        M = B * n
-        dev = xn.d.device
+        scale = 1.0 / math.sqrt(HEAD_DIM)
         is_self = ctx is None
         if is_self:
             nk = n
             Wqkv = st.w(f"{pfx}.to_q.weight", 3 * Cc, Cc)
             qkv = ops.linear_fwd(xn.d, Wqkv)  # [M, 3C]
-            q_t, q_ld, q_bs = qkv, 3 * Cc, (d, n * 3 * Cc)
-            k_t, v_t, kv_ld, kv_bs = qkv[:, Cc:], qkv[:, 2 * Cc:], 3 * Cc, (d, n * 3 * Cc)
+            q_t, k_t, v_t = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
         else:
             nk = n_ctx
             cdim = self.cfg["cross_attention_dim"]
@@ -286,48 +280,21 @@ class UNetEngine:
             Wkv = st.w(f"{pfx}.to_k.weight", 2 * Cc, cdim)
             q = ops.linear_fwd(xn.d, Wq)
             kv = ops.linear_fwd(ctx, Wkv)  # [B*77, 2C]
-            q_t, q_ld, q_bs = q, Cc, (d, n * Cc)
-            k_t, v_t, kv_ld, kv_bs = kv, kv[:, Cc:], 2 * Cc, (d, nk * 2 * Cc)
-        ldk = _ceil8(nk)
-        s_bs = (n * ldk, heads * n * ldk)
-        rows = B * heads * n
-        S = self.ws("S", rows * ldk, torch.float32).view(rows, ldk)
-        ops.gemm_raw(q_t, k_t, S, n, nk, d, lda=q_ld, ldb=kv_ld, ldd=ldk, nb_lo=heads, nb_hi=B, a_bs=q_bs, b_bs=kv_bs,
-                     d_bs=s_bs, alpha=scale, out_fp32=True)
-        P = torch.empty((rows, ldk), device=dev, dtype=bf16)
-        ops.softmax_fwd(S, P, rows, nk)
-        O = torch.empty((M, Cc), device=dev, dtype=bf16)
-        ops.gemm_raw(P, v_t, O, n, d, nk, b_mn=True, lda=ldk, ldb=kv_ld, ldd=Cc, nb_lo=heads, nb_hi=B, a_bs=s_bs,
-                     b_bs=kv_bs, d_bs=(d, n * Cc))
+            q_t, k_t, v_t = q, kv[:, :Cc], kv[:, Cc:]
+        O, lse = ops.attn_fwd(q_t, k_t, v_t, B, heads, n, nk, scale)
         Oa = Act(O)
         out = self.linear(Oa, f"{pfx}.to_out.0.weight", Cc, Cc, f"{pfx}.to_out.0.bias", residual=res)
 
         def bwd():
             dO = Oa.g
-            o_bs = (d, n * Cc)
             if is_self:
                 dqkv = torch.empty_like(qkv)
-                dq_t, dq_ld, dq_bs = dqkv, 3 * Cc, q_bs
-                dk_t, dv_t, dkv_ld = dqkv[:, Cc:], dqkv[:, 2 * Cc:], 3 * Cc
+                dq_t, dk_t, dv_t = dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:]
             else:
                 dq = torch.empty_like(q)
                 dkv = torch.empty_like(kv)
-                dq_t, dq_ld, dq_bs = dq, Cc, q_bs
-                dk_t, dv_t, dkv_ld = dkv, dkv[:, Cc:], 2 * Cc
-            # dV = P^T dO
-            ops.gemm_raw(P, dO, dv_t, nk, d, n, a_mn=True, b_mn=True, lda=ldk, ldb=Cc, ldd=dkv_ld, nb_lo=heads, nb_hi=B,
-                         a_bs=s_bs, b_bs=o_bs, d_bs=kv_bs)
-            # dP = dO V^T   (fp32)
-            dP = self.ws("S", rows * ldk, torch.float32).view(rows, ldk)
-            ops.gemm_raw(dO, v_t, dP, n, nk, d, lda=Cc, ldb=kv_ld, ldd=ldk, nb_lo=heads, nb_hi=B, a_bs=o_bs, b_bs=kv_bs,
-                         d_bs=s_bs, out_fp32=True)
-            dS = self.ws("dS", rows * ldk, bf16).view(rows, ldk)
-            ops.softmax_bwd(P, dP, dS, rows, nk, scale)
-            # dQ = dS K ; dK = dS^T Q
-            ops.gemm_raw(dS, k_t, dq_t, n, d, nk, b_mn=True, lda=ldk, ldb=kv_ld, ldd=dq_ld, nb_lo=heads, nb_hi=B,
-                         a_bs=s_bs, b_bs=kv_bs, d_bs=dq_bs)
-            ops.gemm_raw(dS, q_t, dk_t, nk, d, n, a_mn=True, b_mn=True, lda=ldk, ldb=q_ld, ldd=dkv_ld, nb_lo=heads,
-                         nb_hi=B, a_bs=s_bs, b_bs=q_bs, d_bs=kv_bs)
+                dq_t, dk_t, dv_t = dq, dkv[:, :Cc], dkv[:, Cc:]
+            ops.attn_bwd(q_t, k_t, v_t, O, lse, dO, dq_t, dk_t, dv_t, B, heads, n, nk, scale)
             buf, acc = _gslot(xn)
             if is_self:
                 ops.linear_wgrad(dqkv, xn.d, st.g(f"{pfx}.to_q.weight", 3 * Cc, Cc), accumulate=True)
