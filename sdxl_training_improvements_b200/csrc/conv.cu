@@ -15,9 +15,7 @@ __global__ void im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / kv;
     const int kvi = (int)(i - m * kv);
-    bf16x8 v;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v.v[j] = __floats2bfloat162_rn(0.f, 0.f);
+    bf16x8 v = zero8();
     if (kvi < 9 * cv) {
       const int tap = kvi / cv, c = (kvi - tap * cv) * 8;
       const int kh = tap / 3, kw = tap - kh * 3;

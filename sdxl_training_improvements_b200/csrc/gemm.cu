@@ -265,6 +265,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   return check_launch("b2_gemm");
 }
 
+int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc);  // gemm2.cu: persistent CTA-pair fast path
+
 }  // namespace b2
 
 extern "C" int b2_gemm(const b2_gemm_args* a, void* stream) {
@@ -272,6 +274,10 @@ extern "C" int b2_gemm(const b2_gemm_args* a, void* stream) {
   B2_REQUIRE(a && a->A && a->B && a->D, "b2_gemm: null pointer");
   B2_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "b2_gemm: bad shape %d %d %d", a->M, a->N, a->K);
   B2_REQUIRE(a->nb_lo >= 1 && a->nb_hi >= 1 && (long long)a->nb_lo * a->nb_hi <= 65535, "b2_gemm: bad batch");
+  {
+    int rc2 = 0;
+    if (gemm2_try(a, reinterpret_cast<cudaStream_t>(stream), &rc2)) return rc2;
+  }
   int bn = a->tile_n;
   if (bn == 0) bn = (a->N <= 64) ? 64 : 128;
   B2_REQUIRE(bn == 64 || bn == 128 || bn == 256, "b2_gemm: tile_n must be 64/128/256");

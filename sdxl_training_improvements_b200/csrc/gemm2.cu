@@ -1,0 +1,447 @@
+// b2_gemm fast path: persistent CTA-pair tcgen05 GEMM for sm_100a.
+//
+//   D[m,n] = alpha * sum_k A[m,k] * B[n,k] (+bias) (+residual | +D_old)          bf16 in / bf16 out, fp32 accumulate
+//
+// Why this shape (measured on B200, profiles/r1_gemm_notes.md): a 128x128 single-CTA tile reads 32 KB of smem per
+// 256 MMA cycles and re-fetches every operand tile from L2 once per 128 output rows/cols; it topped out at 27 % of
+// the bf16 peak on the K=1280 shapes that dominate the SDXL step.  Here a cluster of two CTAs (one TPC) computes a
+// 256 x BN tile with cta_group::2 UMMA (M = 256): each CTA stages only its 128 rows of A and its BN/2 rows of B,
+// so smem traffic per flop halves and every operand byte fetched from L2 feeds twice the math.
+//
+//   * persistent: grid = one cluster per SM pair, tiles assigned round-robin; BN (multiple of 16, <= 256) is chosen
+//     on the host so that the tile count fills whole rounds of the 74 clusters (wave quantisation).
+//   * warp 0 (both CTAs)  : TMA producer, 6-stage ring; all transaction bytes are signalled on the LEADER's barrier.
+//   * warp 1 (leader CTA) : single-thread tcgen05.mma.cta_group::2 issuer; tcgen05.commit multicasts the
+//     "stage free" / "accumulator ready" arrivals to both CTAs.  Warp 1 of both CTAs owns the TMEM allocation.
+//   * warps 2..5          : epilogue.  TMEM accumulators are double-buffered (2 x 256 columns) so the epilogue of
+//     tile i overlaps the mainloop of tile i+1.  tcgen05.ld -> registers -> (+bias, +residual) -> bf16 -> SWIZZLE_128B
+//     smem staging -> TMA store (coalesced 128-byte rows, clipped at the M/N edges by the tensor map).  The residual
+//     / accumulate operand comes in through a TMA load into the same staging buffer.
+#include <stdlib.h>
+
+#include "tc.cuh"
+
+namespace b2 {
+
+constexpr int G2_THREADS = 192;
+constexpr int G2_STAGES = 6;
+constexpr int G2_BK = 64;
+constexpr int G2_A_BYTES = 128 * G2_BK * 2;        // 16 KiB: this CTA's 128 rows of A
+constexpr int G2_STAGE_BYTES = 2 * G2_A_BYTES;     // A + up to 128 rows of B
+constexpr int G2_EPI_BYTES = 128 * 64 * 2;         // one 128 x 64 bf16 staging tile
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 2 * G2_EPI_BYTES + 1024;
+constexpr int G2_TMEM_COLS = 512;
+
+struct Gemm2P {
+  int M, N, K;
+  int BN;
+  int a_mn, b_mn;
+  int tiles_m, tiles_n;
+  float alpha;
+  const bf16* bias;
+  int bias_rows_per_group;
+  long long bias_group_stride;
+  int has_res;
+  bf16* D;
+  long long ldd;
+  const bf16* R;
+  long long ldr;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const Gemm2P p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[G2_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[G2_STAGES];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_res[2];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_epi = smem_base + G2_STAGES * G2_STAGE_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = (p.K + G2_BK - 1) / G2_BK;
+  const int halfn = p.BN >> 1;
+  const uint32_t stage_tx = G2_A_BYTES + halfn * 128;  // bytes this CTA's two operand tiles occupy
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    if (p.has_res) tma_prefetch_desc(&tmR);
+#pragma unroll
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_acc_full[b]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[b]), 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(smem_u32(&bar_res[b]), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_slot), G2_TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int mb = t % p.tiles_m, nb = t / p.tiles_m;
+        const int m_base = mb * 256 + (int)rank * 128;
+        const int n_base = nb * p.BN + (int)rank * halfn;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % G2_STAGES;
+          const uint32_t ph = (it / G2_STAGES) & 1;
+          mbar_wait<true>(smem_u32(&bar_empty[s]), ph ^ 1u);
+          const uint32_t full_local = smem_u32(&bar_full[s]);
+          if (leader) mbar_expect_tx(full_local, 2 * stage_tx);
+          const uint32_t full = mapa_u32(full_local, 0);
+          const uint32_t sa = smem_base + s * G2_STAGE_BYTES;
+          const uint32_t sb = sa + G2_A_BYTES;
+          const int k0 = kb * G2_BK;
+          if (!p.a_mn) {
+            tma_load_2d_2sm(sa, &tmA, full, k0, m_base);
+          } else {
+            tma_load_2d_2sm(sa, &tmA, full, m_base, k0);
+            tma_load_2d_2sm(sa + 8192, &tmA, full, m_base + 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
+          } else {
+            for (int j = 0; j < halfn / 64; ++j) tma_load_2d_2sm(sb + j * 8192, &tmB, full, n_base + 64 * j, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = umma_idesc(256, p.BN, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? 8192 : 16, a_kstep = p.a_mn ? 2048 : 32;
+      const uint32_t b_lbo = p.b_mn ? 8192 : 16, b_kstep = p.b_mn ? 2048 : 32;
+      int it = 0, tile_i = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
+        const int buf = tile_i & 1;
+        const uint32_t use = (uint32_t)tile_i >> 1;
+        mbar_wait<true>(smem_u32(&bar_acc_empty[buf]), (use & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * 256;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % G2_STAGES;
+          const uint32_t ph = (it / G2_STAGES) & 1;
+          mbar_wait<true>(smem_u32(&bar_full[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * G2_STAGE_BYTES;
+          const uint32_t sb = sa + G2_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k)
+            umma_bf16_2sm(tacc, umma_desc(sa + k * a_kstep, a_lbo, 1024), umma_desc(sb + k * b_kstep, b_lbo, 1024), idesc,
+                          (kb | k) != 0);
+          umma_commit_2sm(smem_u32(&bar_empty[s]), 3);
+        }
+        umma_commit_2sm(smem_u32(&bar_acc_full[buf]), 3);
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): TMEM -> regs -> smem -> TMA store =====================
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;            // TMEM lane == row of this CTA's 128-row slab
+    const int et = row;                        // epilogue thread id 0..127
+    const uint32_t lane_off = uint32_t(qd * 32) << 16;
+    const uint32_t acc_empty_leader = mapa_u32(smem_u32(&bar_acc_empty[0]), 0);
+    int tile_i = 0;
+    uint32_t chunk_i = 0;
+    uint32_t res_uses[2] = {0, 0};
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
+      const int mb = t % p.tiles_m, nb = t / p.tiles_m;
+      const int m_base = mb * 256 + (int)rank * 128;
+      const int n_tile = nb * p.BN;
+      const int ncols = min(p.BN, p.N - n_tile);
+      const int buf = tile_i & 1;
+      const uint32_t use = (uint32_t)tile_i >> 1;
+      const int gm = m_base + row;
+      const bool row_ok = gm < p.M;
+      const bf16* bias_row =
+          p.bias ? p.bias + (long long)((row_ok ? gm : 0) / p.bias_rows_per_group) * p.bias_group_stride : nullptr;
+      mbar_wait<true>(smem_u32(&bar_acc_full[buf]), use & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * 256 + lane_off;
+      for (int c0 = 0; c0 < ncols; c0 += 64) {
+        const int cw = min(64, ncols - c0);
+        const int n0 = n_tile + c0;
+        uint32_t v0[32], v1[32];
+        tmem_ld32_nowait(tacc + c0, v0);
+        if (cw > 32) tmem_ld32_nowait(tacc + c0 + 32, v1);
+        const bool full_chunk = (cw == 64) || (n_tile + p.BN >= p.N);  // TMA may write the whole 64-wide box
+        if (full_chunk) {
+          const uint32_t sbuf = chunk_i & 1;
+          const uint32_t stage = smem_epi + sbuf * G2_EPI_BYTES;
+          // the previous TMA store that read this staging buffer must have drained
+          if (et == 0) {
+            tma_store_wait_read<1>();
+            if (p.has_res) {
+              mbar_expect_tx(smem_u32(&bar_res[sbuf]), G2_EPI_BYTES);
+              tma_load_2d(stage, &tmR, smem_u32(&bar_res[sbuf]), n0, m_base);
+            }
+          }
+          epi_bar_sync();
+          if (p.has_res) {
+            mbar_wait(smem_u32(&bar_res[sbuf]), res_uses[sbuf] & 1);
+            res_uses[sbuf]++;
+          }
+          tmem_ld_wait();
+          const uint32_t srow = stage + row * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t* v = g < 4 ? v0 + g * 8 : v1 + (g - 4) * 8;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            const bool col_ok = g * 8 < cw;
+            if (bias_row && col_ok) {
+              float tb[8];
+              unpack8(ld8(bias_row + n0 + g * 8), tb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += tb[j];
+            }
+            const uint32_t saddr = srow + ((g ^ (row & 7)) << 4);
+            if (p.has_res) {
+              bf16x8 rv;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(rv.u.x), "=r"(rv.u.y), "=r"(rv.u.z), "=r"(rv.u.w)
+                           : "r"(saddr));
+              float tr[8];
+              unpack8(rv, tr);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += tr[j];
+            }
+            const bf16x8 o = pack8(f);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(o.u.x), "r"(o.u.y), "r"(o.u.z),
+                         "r"(o.u.w)
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          epi_bar_sync();
+          if (et == 0) {
+            tma_store_2d(&tmD, stage, n0, m_base);
+            tma_store_commit();
+          }
+          ++chunk_i;
+        } else {
+          // tile-bounded partial chunk (BN not a multiple of 64): direct 16-byte stores of the valid columns
+          tmem_ld_wait();
+          if (row_ok) {
+            bf16* drow = p.D + (long long)gm * p.ldd + n0;
+            const bf16* rrow = p.R ? p.R + (long long)gm * p.ldr + n0 : nullptr;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (g * 8 < cw) {
+                const uint32_t* v = g < 4 ? v0 + g * 8 : v1 + (g - 4) * 8;
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+                if (bias_row) {
+                  float tb[8];
+                  unpack8(ld8(bias_row + n0 + g * 8), tb);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] += tb[j];
+                }
+                if (rrow) {
+                  float tr[8];
+                  unpack8(ld8(rrow + g * 8), tr);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] += tr[j];
+                }
+                st8(drow + g * 8, pack8(f));
+              }
+            }
+          }
+        }
+      }
+      // accumulator buffer drained: hand it back to the MMA issuer (leader CTA)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty_leader + buf * 8)
+                     : "memory");
+      }
+    }
+    if (et == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, G2_TMEM_COLS);
+  }
+}
+
+// bf16 2-D tiled map (rank 2: the .2d TMA instructions fault on a higher-rank descriptor), SWIZZLE_128B, zero OOB fill
+static int make_map_2d(CUtensorMap* tm, const void* ptr, uint64_t d0, uint64_t d1, long long ld, uint32_t b0, uint32_t b1,
+                       const char* name) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return B2_ERR_TMAP;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 7)) {
+    set_error("b2_gemm: operand %s violates TMA alignment (ptr %p ld %lld)", name, ptr, ld);
+    return B2_ERR_ARG;
+  }
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed: CUresult %d (dims %llu %llu, stride %llu, box %u %u)", name, (int)r,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)strides[0], b0, b1);
+    return B2_ERR_TMAP;
+  }
+  return B2_OK;
+}
+
+// Predicted cycles per k-block of one 256 x bn tile: MMA issue floor vs smem port (TMA write + UMMA read).
+static double tile_cost(int bn) {
+  const double mma = 2.0 * bn;
+  const double smem = (16.0 + bn / 16.0) * 16.0;
+  return (mma > smem ? mma : smem) + 16.0;
+}
+
+int gemm2_pick_bn(int M, int N, int K, int b_mn, int num_clusters) {
+  (void)K;
+  const char* env = getenv("B2_GEMM_BN");
+  if (env && atoi(env) > 0) return atoi(env);
+  const int tiles_m = (M + 255) / 256;
+  int best = 256;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 64; bn -= (b_mn ? 128 : 16)) {
+    if (bn > 64 && bn - 16 >= N && !b_mn) continue;  // no point in a tile wider than N rounded up
+    const int tiles_n = (N + bn - 1) / bn;
+    const long long tiles = (long long)tiles_m * tiles_n;
+    const long long rounds = (tiles + num_clusters - 1) / num_clusters;
+    const double cost = rounds * tile_cost(bn);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+// Returns 1 if the fast path handled the call (rc in *out_rc), 0 if the caller must use the generic kernel.
+int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc) {
+  if (getenv("B2_GEMM_LEGACY")) return 0;
+  if (a->nb_lo != 1 || a->nb_hi != 1 || a->out_fp32) return 0;
+  if (a->M < 256 || a->N < 64 || (a->N & 7) || (a->ldd & 7) || a->K < 64) return 0;
+  if (reinterpret_cast<uintptr_t>(a->D) & 15) return 0;
+  if (a->b_mn && a->N < 128) return 0;
+  const void* R = a->accumulate ? a->D : a->residual;
+  const long long ldr = a->accumulate ? a->ldd : a->ldr;
+  if (a->accumulate && a->residual) return 0;
+  if (R && ((ldr & 7) || (reinterpret_cast<uintptr_t>(R) & 15))) return 0;
+  if (a->bias && ((a->bias_group_stride & 7) || (reinterpret_cast<uintptr_t>(a->bias) & 15))) return 0;
+
+  const int num_clusters = num_sms() / 2;
+  const int bn = gemm2_pick_bn(a->M, a->N, a->K, a->b_mn, num_clusters);
+  if (bn < 32 || bn > 256 || (bn & 15) || (a->b_mn && (bn & 127))) {
+    set_error("b2_gemm: bad BN %d", bn);
+    *out_rc = B2_ERR_ARG;
+    return 1;
+  }
+  CUtensorMap ta, tb, td, tr;
+  int rc;
+  if (!a->a_mn)
+    rc = make_map_2d(&ta, a->A, a->K, a->M, a->lda, 64, 128, "A");
+  else
+    rc = make_map_2d(&ta, a->A, a->M, a->K, a->lda, 64, 64, "A(mn)");
+  if (rc) { *out_rc = rc; return 1; }
+  if (!a->b_mn)
+    rc = make_map_2d(&tb, a->B, a->K, a->N, a->ldb, 64, bn / 2, "B");
+  else
+    rc = make_map_2d(&tb, a->B, a->N, a->K, a->ldb, 64, 64, "B(mn)");
+  if (rc) { *out_rc = rc; return 1; }
+  rc = make_map_2d(&td, a->D, a->N, a->M, a->ldd, 64, 128, "D");
+  if (rc) { *out_rc = rc; return 1; }
+  if (R) {
+    rc = make_map_2d(&tr, R, a->N, a->M, ldr, 64, 128, "R");
+    if (rc) { *out_rc = rc; return 1; }
+  } else {
+    tr = td;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    if (err != cudaSuccess) {
+      set_error("b2_gemm: cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(err));
+      *out_rc = B2_ERR_CUDA;
+      return 1;
+    }
+    configured = true;
+  }
+  Gemm2P p{};
+  p.M = a->M; p.N = a->N; p.K = a->K; p.BN = bn;
+  p.a_mn = a->a_mn ? 1 : 0; p.b_mn = a->b_mn ? 1 : 0;
+  p.tiles_m = (a->M + 255) / 256; p.tiles_n = (a->N + bn - 1) / bn;
+  p.alpha = a->alpha;
+  p.bias = reinterpret_cast<const bf16*>(a->bias);
+  p.bias_rows_per_group = a->bias_rows_per_group > 0 ? a->bias_rows_per_group : 0x7fffffff;
+  p.bias_group_stride = a->bias_group_stride;
+  p.has_res = R ? 1 : 0;
+  p.D = reinterpret_cast<bf16*>(a->D); p.ldd = a->ldd;
+  p.R = reinterpret_cast<const bf16*>(R); p.ldr = ldr;
+  long long tiles = (long long)p.tiles_m * p.tiles_n;
+  int clusters = (int)(tiles < num_clusters ? tiles : num_clusters);
+  gemm2_kernel<<<dim3(2 * clusters), G2_THREADS, G2_SMEM, st>>>(ta, tb, td, tr, p);
+  *out_rc = check_launch("b2_gemm(pair)");
+  return 1;
+}
+
+}  // namespace b2

@@ -25,10 +25,18 @@ SHAPES = [
     ("conv320 wgrad", 320, 2880, 65536, 1, 1),
     ("conv1280 wgr ", 1280, 11520, 4096, 1, 1),
 ]
-tiles = [int(t) for t in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0]
+# configs: "legacy" (single-CTA 128x128 kernel), "auto" (CTA-pair kernel, host-picked BN), "bnNNN" (forced BN)
+tiles = sys.argv[1].split(",") if len(sys.argv) > 1 else ["auto"]
 
 
-def run(M, N, K, a_mn, b_mn, tile):
+def run(M, N, K, a_mn, b_mn, cfg):
+    os.environ.pop("B2_GEMM_LEGACY", None)
+    os.environ.pop("B2_GEMM_BN", None)
+    if cfg == "legacy":
+        os.environ["B2_GEMM_LEGACY"] = "1"
+    elif cfg.startswith("bn"):
+        os.environ["B2_GEMM_BN"] = cfg[2:]
+    tile = 0
     nset = max(2, int(300e6 / (2 * (M * K + N * K + M * N))) + 1)
     nset = min(nset, 8)
     As = [torch.randn((K, M) if a_mn else (M, K), device="cuda").to(bf16) for _ in range(nset)]
@@ -64,7 +72,7 @@ for name, M, N, K, a_mn, b_mn in SHAPES:
     for t in tiles:
         try:
             ms, err = run(M, N, K, a_mn, b_mn, t)
-            line += f"  tile{t}: {ms * 1e3:7.1f} us {2.0 * M * N * K / ms / 1e9:6.0f} TF/s (err {err:.1e})"
+            line += f"  {t}: {ms * 1e3:7.1f} us {2.0 * M * N * K / ms / 1e9:6.0f} TF/s (err {err:.1e})"
         except Exception as ex:  # noqa: BLE001
-            line += f"  tile{t}: FAILED {str(ex)[:60]}"
+            line += f"  {t}: FAILED {str(ex)[:60]}"
     print(line, flush=True)
