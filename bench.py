@@ -121,7 +121,8 @@ def _synthetic_batch(B, H, W, seed, pin=True):
 
 
 def _time_gemm_roofline(ops, peaks):
-    """Dominant kernel = gemm_tcgen05_kernel<128,3>; timed live on the GEGLU up-projection shape (41.7 % of FLOPs)."""
+    """Dominant kernel = gemm2_kernel (persistent CTA-pair tcgen05 GEMM, ~50 % of the step); timed live on the GEGLU
+    up-projection shape (the FFN is 41.7 % of the step's FLOPs)."""
     M, N, K = 4096, 10240, 1280
     nset = 6  # rotate operands: 6 x (26 MB W + 84 MB D) >> 126 MB L2
     x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
@@ -149,7 +150,7 @@ def _time_gemm_roofline(ops, peaks):
             traffic = None
     return {"bound": "tensor", "achieved": round(ach, 1), "peak": peaks["burst"], "unit": "TFLOP/s",
             "frac": round(ach / peaks["burst"], 4), "traffic": traffic,
-            "kernel": "gemm_tcgen05_kernel<128,3> on M=4096,N=10240,K=1280 (GEGLU up-projection), "
+            "kernel": "gemm2_kernel (cta_group::2, 256xBN tiles) on M=4096,N=10240,K=1280 (GEGLU up-projection), "
                       f"{flops / 1e9:.1f} GFLOP/launch, {ms * 1e3:.1f} us/launch, peak = {peaks['src']} burst bf16"}
 
 
