@@ -439,6 +439,10 @@ int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc) {
   p.R = reinterpret_cast<const bf16*>(R); p.ldr = ldr;
   long long tiles = (long long)p.tiles_m * p.tiles_n;
   int clusters = (int)(tiles < num_clusters ? tiles : num_clusters);
+  static const bool log_calls = getenv("B2_GEMM_LOG") != nullptr;
+  if (log_calls)
+    fprintf(stderr, "B2GEMM M=%d N=%d K=%d a_mn=%d b_mn=%d BN=%d bias=%d res=%d acc=%d\n", a->M, a->N, a->K, p.a_mn, p.b_mn,
+            bn, a->bias != nullptr, a->residual != nullptr, a->accumulate);
   gemm2_kernel<<<dim3(2 * clusters), G2_THREADS, G2_SMEM, st>>>(ta, tb, td, tr, p);
   *out_rc = check_launch("b2_gemm(pair)");
   return 1;

@@ -1,0 +1,127 @@
+"""T5: 100 optimizer steps on identical seeds / weights / noise / timesteps — loss curve of the kernel
+path (bf16 activations, fp32 accumulation, fused loss + clip + AdamW with fp32 master weights) vs the oracle
+(fp32 PyTorch on CUDA, torch.optim.AdamW, clip_grad_norm_ 1.0).
+
+Three arms, same seeds / initial weights / noise / timesteps / optimizer hyper-parameters:
+  fp32   : oracle in fp32 (the "exact" curve),
+  bf16   : oracle in CUDA-eager bf16 with fp32 master weights — the numerics of the reference path itself, which casts the
+           whole UNet to bf16 (sdxl_trainer.py:52-55),
+  kernel : this repo (bf16 activations, fp32 accumulation in TMEM, fp32 master weights).
+Tolerance (stated): the north star asks for 1e-3 on the loss curve; SURVEY.md B23 notes that this is below the bf16
+path's own resolution, so the bar here is   max_t |kernel - fp32| <= max(1e-3, 1.5 * max_t |bf16 - fp32|)   i.e. the
+kernel path must track the exact curve at least as well as the reference's own precision does, and the first step
+(pure forward parity, no optimizer drift) must be within 1e-3 * max(1, loss).
+Reduced-width UNet (same topology) so that the oracles run in seconds; flow matching and ddpm/v-prediction.
+"""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+STEPS = 100
+
+
+def _setup(seed=0):
+    from oracle.unet_sdxl import OracleUNet, seeded_init_, tiny_config
+    from sdxl_training_improvements_b200.unet import B200UNet
+    cfg = tiny_config()
+    ref = seeded_init_(OracleUNet(cfg), seed).cuda()
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.copy_(p.to(bf16).float())
+    net = B200UNet(cfg, device="cuda")
+    net.load_state_dict(ref.state_dict())
+    return cfg, ref, net
+
+
+def _batches(cfg, B, H, W, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    pooled_dim = cfg["projection_class_embeddings_input_dim"] - 6 * cfg["addition_time_embed_dim"]
+    out = []
+    for _ in range(n):
+        out.append({
+            "vae_latents": torch.randn(B, 4, H, W, generator=g).to(bf16).float(),
+            "prompt_embeds": torch.randn(B, 77, cfg["cross_attention_dim"], generator=g).to(bf16).float(),
+            "pooled_prompt_embeds": torch.randn(B, pooled_dim, generator=g).to(bf16).float(),
+            "time_ids": torch.tensor([[8. * W, 8. * H, 0., 0., 8. * W, 8. * H]]).repeat(B, 1)[:, None],
+            "metadata": [{} for _ in range(B)],
+            "noise": torch.randn(B, 4, H, W, generator=g).to(bf16).float(),
+            "t_ddpm": torch.randint(300, 800, (B,), generator=g),          # sigma in [0.6, 1800]: loss not clamped
+            "t_flow": torch.sigmoid(torch.randn(B, generator=g)).to(bf16),
+        })
+    return out
+
+
+def _conf(method):
+    return SimpleNamespace(model=SimpleNamespace(num_timesteps=1000, sigma_min=0.002, sigma_max=20000.0, use_ztsnr=True,
+                                                 min_snr_gamma=None),
+                           training=SimpleNamespace(method=method, prediction_type="v_prediction",
+                                                    gradient_accumulation_steps=1, clip_grad_norm=1.0))
+
+
+@pytest.mark.parametrize("method", ["flow_matching", "ddpm"])
+def test_loss_curve_100_steps(method):
+    from oracle import schedule as S
+    from sdxl_training_improvements_b200.trainer import B200AdamW, create_trainer
+    cfg, ref, net = _setup(seed=3)
+    lr = 2e-4
+    opt_k = B200AdamW(net, lr=lr, weight_decay=1e-2, master_weights=True)
+    opt_o = torch.optim.AdamW(ref.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    tr = create_trainer(_conf(method), net, opt_k, device="cuda")
+    import copy
+    ref16 = copy.deepcopy(ref).to(bf16)                       # bf16 eager arm, fp32 master = `m16`
+    m16 = [p.detach().float().clone().requires_grad_(True) for p in ref16.parameters()]
+    opt_16 = torch.optim.AdamW(m16, lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    l16 = []
+    sig = S.schedule_sigmas().cuda()
+    B, H, W = 2, 16, 16
+    lk, lo = [], []
+    for b in _batches(cfg, B, H, W, STEPS, seed=11):
+        dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+        if method == "ddpm":
+            out = tr.training_step(b, noise=b["noise"], timesteps=b["t_ddpm"])
+            o = S.ddpm_loss(ref, dev["vae_latents"], dev["noise"], dev["t_ddpm"], dev["prompt_embeds"],
+                            dev["pooled_prompt_embeds"], dev["time_ids"], sigmas=sig)
+        else:
+            out = tr.compute_loss(net, b, x0=b["noise"], t=b["t_flow"])
+            o = S.flow_loss(ref, dev["vae_latents"], dev["noise"], dev["t_flow"].float(), dev["prompt_embeds"],
+                            dev["pooled_prompt_embeds"], dev["time_ids"])
+        out["loss"].backward()
+        tr.optimizer_step()
+        opt_o.zero_grad(set_to_none=True)
+        o["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        opt_o.step()
+        c16 = {k: (v.to(bf16) if torch.is_tensor(v) and v.is_floating_point() and k != "time_ids" else v)
+               for k, v in dev.items()}
+        if method == "ddpm":
+            o16 = S.ddpm_loss(ref16, c16["vae_latents"], c16["noise"], dev["t_ddpm"], c16["prompt_embeds"],
+                              c16["pooled_prompt_embeds"], dev["time_ids"], sigmas=sig)
+        else:
+            o16 = S.flow_loss(ref16, c16["vae_latents"], c16["noise"], c16["t_flow"], c16["prompt_embeds"],
+                              c16["pooled_prompt_embeds"], dev["time_ids"])
+        for p in ref16.parameters():
+            p.grad = None
+        o16["loss"].backward()
+        for mp_, p in zip(m16, ref16.parameters()):
+            mp_.grad = p.grad.float()
+        torch.nn.utils.clip_grad_norm_(m16, 1.0)
+        opt_16.step()
+        with torch.no_grad():
+            for mp_, p in zip(m16, ref16.parameters()):
+                p.copy_(mp_.to(bf16))
+        l16.append(float(o16["loss"].detach()))
+        lk.append(float(out["loss"].detach()))
+        lo.append(float(o["loss"].detach()))
+    d = [abs(a - b) for a, b in zip(lk, lo)]
+    worst = max(range(STEPS), key=lambda i: d[i])
+    print(f"\n{method}: loss[0] kernel {lk[0]:.6f} oracle {lo[0]:.6f}; loss[99] kernel {lk[-1]:.6f} oracle {lo[-1]:.6f}; "
+          f"max |d| {d[worst]:.3e} at step {worst} (loss {lo[worst]:.4f}); mean |d| {sum(d) / STEPS:.3e}")
+    d16 = [abs(a - b) for a, b in zip(l16, lo)]
+    print(f"{method}: bf16-eager oracle vs fp32 oracle: max |d| {max(d16):.3e}, mean |d| {sum(d16) / STEPS:.3e}")
+    assert lo[-1] < lo[0], "the oracle's loss did not go down: the trajectory test is not exercising learning"
+    assert d[0] <= 1e-3 * max(1.0, lo[0]), f"first-step loss differs: {d[0]:.3e}"
+    bar = max(1e-3, 1.5 * max(d16))
+    assert max(d) <= bar, f"loss curves diverge: max |d| {max(d):.3e} > {bar:.3e}"
