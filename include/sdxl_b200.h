@@ -82,6 +82,33 @@ int b2_im2col3x3(const void* x, void* col, int B, int H, int W, int C, int strid
 int b2_col2im3x3(const void* dcol, void* dx, int B, int H, int W, int C, int stride, int upsample,
                  int64_t ldc, int accumulate, void* stream);
 
+/* Implicit-GEMM 3x3 convolution (stride 1, pad 1) — no im2col buffer in HBM.  The activation operand is gathered by
+ * TMA straight from the NHWC tensor: a 4-D tensor map {C, W, H, B} with a {64, bw, bh, 1} box per pixel block,
+ * shifted by the filter tap; the zero padding is TMA's out-of-bounds fill.  Same persistent CTA-pair tcgen05 kernel
+ * as b2_gemm (gemm2_kernel), same epilogues.
+ * replaces: ResnetBlock2D.conv1 / conv2 (torch Conv2d -> cuDNN fprop / dgrad / wgrad), 34 of the UNet's 40 3x3 convs.
+ *   mode 0 (fwd)  : y[B*H*W, Cout] = conv(x[B,H,W,Cin], w[Cout,3,3,Cin]) + bias (+ residual)
+ *                   bias_per_sample = 1: bias is [B, Cout] (time-embedding row of each sample), else [Cout]
+ *   mode 1 (dgrad): x  (+)= conv_transpose(y = dL/dy, w)          (accumulate selects +=)
+ *   mode 2 (wgrad): w  (+)= sum over pixels of y^T (x) shifted x    (w is the [Cout, 9*Cin] gradient buffer)
+ * Supported when b2_conv3x3_implicit_ok() returns 1: Cin, Cout multiples of 64 (Cin >= 128), H*W a multiple of 128,
+ * W a divisor or a multiple of 128 and of 64.  Other shapes (stride 2, folded upsample, conv_in / conv_out) go through
+ * b2_im2col3x3 + b2_gemm. */
+typedef struct b2_conv3x3_args {
+  void* x;              /* [B*H*W, ldx] bf16 */
+  void* w;              /* [Cout, 9*Cin] bf16, K order (kh, kw, cin) */
+  void* y;              /* [B*H*W, ldy] bf16 */
+  const void* bias;     /* fwd only; bf16 or NULL */
+  const void* residual; /* fwd only; [B*H*W, ldr] bf16 or NULL */
+  int32_t mode;
+  int32_t B, H, W, Cin, Cout;
+  int64_t ldx, ldy, ldr; /* 0 = dense */
+  int32_t bias_per_sample;
+  int32_t accumulate;
+} b2_conv3x3_args;
+int b2_conv3x3_implicit_ok(int B, int H, int W, int Cin, int Cout);
+int b2_conv3x3(const b2_conv3x3_args* args, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU), NHWC.  replaces torch.nn.GroupNorm + F.silu in ResnetBlock2D / Transformer2DModel.norm /
  *   conv_norm_out and their backward.

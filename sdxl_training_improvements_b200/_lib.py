@@ -38,6 +38,15 @@ class AttnArgs(C.Structure):
     ]
 
 
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("x", c_p), ("w", c_p), ("y", c_p), ("bias", c_p), ("residual", c_p),
+        ("mode", i32), ("B", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
+        ("ldx", i64), ("ldy", i64), ("ldr", i64),
+        ("bias_per_sample", i32), ("accumulate", i32),
+    ]
+
+
 # name -> argtypes (return type is int unless listed in _RESTYPES); mirrors include/sdxl_b200.h one to one.
 SIGNATURES = {
     "b2_version": [],
@@ -47,6 +56,8 @@ SIGNATURES = {
     "b2_attn_lse_rows": [i32],
     "b2_attn_fwd": [C.POINTER(AttnArgs), c_p],
     "b2_attn_bwd": [C.POINTER(AttnArgs), c_p],
+    "b2_conv3x3_implicit_ok": [i32, i32, i32, i32, i32],
+    "b2_conv3x3": [C.POINTER(ConvArgs), c_p],
     "b2_im2col3x3": [c_p, c_p, i32, i32, i32, i32, i32, i32, i64, c_p],
     "b2_col2im3x3": [c_p, c_p, i32, i32, i32, i32, i32, i32, i64, i32, c_p],
     "b2_gn_stats": [c_p, i32, i32, i32, i32, f32, c_p, c_p, c_p, c_p],

@@ -46,6 +46,16 @@ struct Gemm2P {
   long long ldd;
   const bf16* R;
   long long ldr;
+  // implicit 3x3 convolution (stride 1, pad 1): one operand is gathered from an NHWC activation [B,H,W,C] through a
+  // 4-D tensor map {C, W, H, B}; a pixel block is a box {64, bw, bh, 1} shifted by the tap, halo zero-filled by TMA.
+  //   conv = 1: A = activation (K-major, k = (tap, c)), 128 pixels per CTA slab      (forward: sign +1, dgrad: sign -1)
+  //   conv = 2: B = activation (MN-major, n = (tap, c), k = pixel), 64 pixels per k-block   (wgrad)
+  int conv;
+  int cv_W, cv_HW;
+  int cv_cpb;    // 64-channel blocks per tap of the gathered operand
+  int cv_sign;   // +1: input pixel = output pixel + (kh-1, kw-1);  -1: minus (dgrad)
+  int cv_btap;   // conv = 1 with MN-major B (dgrad): B column offset per tap (= Cin of the weight)
+  int cv_C;      // conv = 2: channels of the gathered activation (n -> tap = n / C, c = n % C)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
@@ -133,6 +143,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int mb = t % p.tiles_m, nb = t / p.tiles_m;
         const int m_base = mb * 256 + (int)rank * 128;
         const int n_base = nb * p.BN + (int)rank * halfn;
+        // implicit-conv decode of this CTA's pixel slab (conv = 1)
+        int cb = 0, ch0 = 0, cw0 = 0;
+        if (p.conv == 1) {
+          cb = m_base / p.cv_HW;
+          const int rem = m_base - cb * p.cv_HW;
+          ch0 = rem / p.cv_W;
+          cw0 = rem - ch0 * p.cv_W;
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % G2_STAGES;
           const uint32_t ph = (it / G2_STAGES) & 1;
@@ -143,13 +161,37 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t sa = smem_base + s * G2_STAGE_BYTES;
           const uint32_t sb = sa + G2_A_BYTES;
           const int k0 = kb * G2_BK;
+          if (p.conv == 1) {
+            const int tap = kb / p.cv_cpb;
+            const int c0 = (kb - tap * p.cv_cpb) * 64;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d_2sm(sa, &tmA, full, c0, cw0 + p.cv_sign * (kw - 1), ch0 + p.cv_sign * (kh - 1), cb);
+            if (!p.b_mn) {
+              tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
+            } else {
+              for (int j = 0; j < halfn / 64; ++j)
+                tma_load_2d_2sm(sb + j * 8192, &tmB, full, tap * p.cv_btap + n_base + 64 * j, c0);
+            }
+            continue;
+          }
           if (!p.a_mn) {
             tma_load_2d_2sm(sa, &tmA, full, k0, m_base);
           } else {
             tma_load_2d_2sm(sa, &tmA, full, m_base, k0);
             tma_load_2d_2sm(sa + 8192, &tmA, full, m_base + 64, k0);
           }
-          if (!p.b_mn) {
+          if (p.conv == 2) {
+            const int pb = k0 / p.cv_HW;
+            const int rem = k0 - pb * p.cv_HW;
+            const int ph0 = rem / p.cv_W, pw0 = rem - ph0 * p.cv_W;
+            for (int j = 0; j < halfn / 64; ++j) {
+              const int n = n_base + 64 * j;
+              const int tap = n / p.cv_C;
+              const int c0 = n - tap * p.cv_C;
+              const int kh = tap / 3, kw = tap - kh * 3;
+              tma_load_4d_2sm(sb + j * 8192, &tmB, full, c0, pw0 + kw - 1, ph0 + kh - 1, pb);
+            }
+          } else if (!p.b_mn) {
             tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
           } else {
             for (int j = 0; j < halfn / 64; ++j) tma_load_2d_2sm(sb + j * 8192, &tmB, full, n_base + 64 * j, k0);
@@ -376,6 +418,26 @@ int gemm2_pick_bn(int M, int N, int K, int b_mn, int num_clusters) {
   return best;
 }
 
+static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr,
+                        Gemm2P& p, cudaStream_t st, const char* what) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    if (err != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute(gemm2): %s", what, cudaGetErrorString(err));
+      return B2_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int num_clusters = num_sms() / 2;
+  p.tiles_m = (p.M + 255) / 256;
+  p.tiles_n = (p.N + p.BN - 1) / p.BN;
+  const long long tiles = (long long)p.tiles_m * p.tiles_n;
+  const int clusters = (int)(tiles < num_clusters ? tiles : num_clusters);
+  gemm2_kernel<<<dim3(2 * clusters), G2_THREADS, G2_SMEM, st>>>(ta, tb, td, tr, p);
+  return check_launch(what);
+}
+
 // Returns 1 if the fast path handled the call (rc in *out_rc), 0 if the caller must use the generic kernel.
 int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc) {
   if (getenv("B2_GEMM_LEGACY")) return 0;
@@ -416,20 +478,9 @@ int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc) {
   } else {
     tr = td;
   }
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
-    if (err != cudaSuccess) {
-      set_error("b2_gemm: cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(err));
-      *out_rc = B2_ERR_CUDA;
-      return 1;
-    }
-    configured = true;
-  }
   Gemm2P p{};
   p.M = a->M; p.N = a->N; p.K = a->K; p.BN = bn;
   p.a_mn = a->a_mn ? 1 : 0; p.b_mn = a->b_mn ? 1 : 0;
-  p.tiles_m = (a->M + 255) / 256; p.tiles_n = (a->N + bn - 1) / bn;
   p.alpha = a->alpha;
   p.bias = reinterpret_cast<const bf16*>(a->bias);
   p.bias_rows_per_group = a->bias_rows_per_group > 0 ? a->bias_rows_per_group : 0x7fffffff;
@@ -437,15 +488,125 @@ int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc) {
   p.has_res = R ? 1 : 0;
   p.D = reinterpret_cast<bf16*>(a->D); p.ldd = a->ldd;
   p.R = reinterpret_cast<const bf16*>(R); p.ldr = ldr;
-  long long tiles = (long long)p.tiles_m * p.tiles_n;
-  int clusters = (int)(tiles < num_clusters ? tiles : num_clusters);
   static const bool log_calls = getenv("B2_GEMM_LOG") != nullptr;
   if (log_calls)
     fprintf(stderr, "B2GEMM M=%d N=%d K=%d a_mn=%d b_mn=%d BN=%d bias=%d res=%d acc=%d\n", a->M, a->N, a->K, p.a_mn, p.b_mn,
             bn, a->bias != nullptr, a->residual != nullptr, a->accumulate);
-  gemm2_kernel<<<dim3(2 * clusters), G2_THREADS, G2_SMEM, st>>>(ta, tb, td, tr, p);
-  *out_rc = check_launch("b2_gemm(pair)");
+  *out_rc = gemm2_launch(ta, tb, td, tr, p, st, "b2_gemm(pair)");
   return 1;
 }
 
+// bf16 4-D map over an NHWC activation: dims {C, W, H, B}; box {64, bw, bh, 1} = `pix` consecutive pixels of one image
+// row-major (bw = min(W, pix), bh = pix / bw).  Halo / out-of-image pixels are zero-filled.
+static int make_map_conv(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, long long ld, int pix,
+                         const char* name) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return B2_ERR_TMAP;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 7)) {
+    set_error("b2_conv3x3: operand %s violates TMA alignment (ptr %p ld %lld)", name, ptr, ld);
+    return B2_ERR_ARG;
+  }
+  const int bw = W < pix ? W : pix;
+  const int bh = pix / bw;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)(ld * 2), (cuuint64_t)(ld * 2 * W), (cuuint64_t)(ld * 2 * W * H)};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed: CUresult %d (B %d H %d W %d C %d ld %lld box %d x %d)", name, (int)r, B, H,
+              W, C, ld, bw, bh);
+    return B2_ERR_TMAP;
+  }
+  return B2_OK;
+}
+
+static bool conv_geom_ok(int B, int H, int W, int pix) {
+  const long long HW = (long long)H * W;
+  if (HW % pix) return false;
+  if (W <= pix) return (pix % W) == 0 && (pix / W) <= 256;
+  return (W % pix) == 0;
+}
+
 }  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_conv3x3_implicit_ok(int B, int H, int W, int Cin, int Cout) {
+  if (getenv("B2_CONV_EXPLICIT")) return 0;
+  if (B <= 0 || H <= 0 || W <= 0 || Cin < 128 || Cout < 64 || (Cin & 63) || (Cout & 63)) return 0;
+  if (!conv_geom_ok(B, H, W, 128) || !conv_geom_ok(B, H, W, 64)) return 0;
+  return 1;
+}
+
+extern "C" int b2_conv3x3(const b2_conv3x3_args* a, void* stream) {
+  B2_REQUIRE(a && a->x && a->w && a->y, "b2_conv3x3: null pointer");
+  B2_REQUIRE(a->mode >= 0 && a->mode <= 2, "b2_conv3x3: bad mode %d", a->mode);
+  B2_REQUIRE(b2_conv3x3_implicit_ok(a->B, a->H, a->W, a->Cin, a->Cout),
+             "b2_conv3x3: shape B=%d H=%d W=%d Cin=%d Cout=%d not supported by the implicit path (use im2col + b2_gemm)",
+             a->B, a->H, a->W, a->Cin, a->Cout);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int B = a->B, H = a->H, W = a->W, Cin = a->Cin, Cout = a->Cout;
+  const long long pixels = (long long)B * H * W;
+  B2_REQUIRE(pixels < (1ll << 31), "b2_conv3x3: too many pixels");
+  const long long ldx = a->ldx > 0 ? a->ldx : Cin, ldy = a->ldy > 0 ? a->ldy : Cout, ldw = 9ll * Cin;
+  const int num_clusters = num_sms() / 2;
+  CUtensorMap ta, tb, td, tr;
+  Gemm2P p{};
+  p.alpha = 1.f;
+  p.bias_rows_per_group = 0x7fffffff;
+  p.cv_W = W;
+  p.cv_HW = H * W;
+  int rc;
+  if (a->mode == 0) {  // y[pixels, Cout] = conv(x, w) (+bias | +rowbias[b]) (+residual)
+    p.M = (int)pixels; p.N = Cout; p.K = 9 * Cin;
+    p.a_mn = 0; p.b_mn = 0; p.conv = 1; p.cv_sign = 1; p.cv_cpb = Cin / 64;
+    p.BN = gemm2_pick_bn(p.M, p.N, p.K, 0, num_clusters);
+    if ((rc = make_map_conv(&ta, a->x, B, H, W, Cin, ldx, 128, "conv x"))) return rc;
+    if ((rc = make_map_2d(&tb, a->w, 9ull * Cin, Cout, ldw, 64, p.BN / 2, "conv w"))) return rc;
+    if ((rc = make_map_2d(&td, a->y, Cout, pixels, ldy, 64, 128, "conv y"))) return rc;
+    if (a->residual) {
+      const long long ldr = a->ldr > 0 ? a->ldr : Cout;
+      if ((rc = make_map_2d(&tr, a->residual, Cout, pixels, ldr, 64, 128, "conv residual"))) return rc;
+      p.has_res = 1; p.R = reinterpret_cast<const bf16*>(a->residual); p.ldr = ldr;
+    } else {
+      tr = td;
+    }
+    if (a->bias) {
+      B2_REQUIRE(!(reinterpret_cast<uintptr_t>(a->bias) & 15), "b2_conv3x3: bias must be 16-byte aligned");
+      p.bias = reinterpret_cast<const bf16*>(a->bias);
+      if (a->bias_per_sample) {
+        p.bias_rows_per_group = H * W;
+        p.bias_group_stride = Cout;
+      }
+    }
+    p.D = reinterpret_cast<bf16*>(a->y); p.ldd = ldy;
+  } else if (a->mode == 1) {  // dx[pixels, Cin] (+)= conv_transpose(dy, w)
+    B2_REQUIRE(Cin >= 128, "b2_conv3x3 dgrad: Cin < 128");
+    p.M = (int)pixels; p.N = Cin; p.K = 9 * Cout;
+    p.a_mn = 0; p.b_mn = 1; p.conv = 1; p.cv_sign = -1; p.cv_cpb = Cout / 64; p.cv_btap = Cin;
+    p.BN = gemm2_pick_bn(p.M, p.N, p.K, 1, num_clusters);
+    if ((rc = make_map_conv(&ta, a->y, B, H, W, Cout, ldy, 128, "conv dy"))) return rc;
+    if ((rc = make_map_2d(&tb, a->w, 9ull * Cin, Cout, ldw, 64, 64, "conv w(mn)"))) return rc;
+    if ((rc = make_map_2d(&td, a->x, Cin, pixels, ldx, 64, 128, "conv dx"))) return rc;
+    tr = td;
+    if (a->accumulate) { p.has_res = 1; p.R = reinterpret_cast<const bf16*>(a->x); p.ldr = ldx; }
+    p.D = reinterpret_cast<bf16*>(a->x); p.ldd = ldx;
+  } else {  // dw[Cout, 9*Cin] (+)= dy^T (*) x
+    p.M = Cout; p.N = 9 * Cin; p.K = (int)pixels;
+    p.a_mn = 1; p.b_mn = 1; p.conv = 2; p.cv_sign = 1; p.cv_C = Cin;
+    p.BN = gemm2_pick_bn(p.M, p.N, p.K, 1, num_clusters);
+    if ((rc = make_map_2d(&ta, a->y, Cout, pixels, ldy, 64, 64, "conv dy(mn)"))) return rc;
+    if ((rc = make_map_conv(&tb, a->x, B, H, W, Cin, ldx, 64, "conv x(mn)"))) return rc;
+    if ((rc = make_map_2d(&td, a->w, 9ull * Cin, Cout, ldw, 64, 128, "conv dw"))) return rc;
+    tr = td;
+    if (a->accumulate) { p.has_res = 1; p.R = reinterpret_cast<const bf16*>(a->w); p.ldr = ldw; }
+    p.D = reinterpret_cast<bf16*>(a->w); p.ldd = ldw;
+  }
+  return gemm2_launch(ta, tb, td, tr, p, st, "b2_conv3x3");
+}

@@ -104,6 +104,42 @@ def col2im3x3(dcol, dx, B, H, W, Cc, stride=1, upsample=False, accumulate=False)
     return dx
 
 
+def conv3x3_implicit_ok(B, H, W, Cin, Cout) -> bool:
+    return bool(_lib.load().b2_conv3x3_implicit_ok(int(B), int(H), int(W), int(Cin), int(Cout)))
+
+
+def _conv_args(mode, x, w, y, B, H, W, Cin, Cout, bias=None, residual=None, bias_per_sample=False, accumulate=False):
+    _need_cuda(x, w, y, bias, residual)
+    a = _lib.ConvArgs()
+    a.x, a.w, a.y, a.bias, a.residual = _p(x), _p(w), _p(y), _p(bias), _p(residual)
+    a.mode, a.B, a.H, a.W, a.Cin, a.Cout = mode, int(B), int(H), int(W), int(Cin), int(Cout)
+    a.ldx, a.ldy = x.stride(0), y.stride(0)
+    a.ldr = residual.stride(0) if residual is not None else 0
+    a.bias_per_sample, a.accumulate = int(bias_per_sample), int(accumulate)
+    return a
+
+
+def conv3x3_fwd(x, Wk, B, H, W, Cin, Cout, bias=None, residual=None, bias_per_sample=False, out=None):
+    """y[B*H*W, Cout] = conv3x3(x[B*H*W, Cin] NHWC, Wk[Cout, 9*Cin]) + bias (+residual); implicit GEMM, no im2col."""
+    if out is None:
+        out = torch.empty((B * H * W, Cout), device=x.device, dtype=bf16)
+    a = _conv_args(0, x, Wk, out, B, H, W, Cin, Cout, bias, residual, bias_per_sample)
+    _lib.check(_lib.load().b2_conv3x3(C.byref(a), _stream()), "b2_conv3x3 fwd")
+    return out
+
+
+def conv3x3_dgrad(dy, Wk, dx, B, H, W, Cin, Cout, accumulate=False):
+    a = _conv_args(1, dx, Wk, dy, B, H, W, Cin, Cout, accumulate=accumulate)
+    _lib.check(_lib.load().b2_conv3x3(C.byref(a), _stream()), "b2_conv3x3 dgrad")
+    return dx
+
+
+def conv3x3_wgrad(dy, x, dWk, B, H, W, Cin, Cout, accumulate=True):
+    a = _conv_args(2, x, dWk, dy, B, H, W, Cin, Cout, accumulate=accumulate)
+    _lib.check(_lib.load().b2_conv3x3(C.byref(a), _stream()), "b2_conv3x3 wgrad")
+    return dWk
+
+
 # --------------------------------------------------------------------------------------- norms
 def gn_stats(x, B, HW, Cc, G, eps):
     ws = torch.empty(B * G * 2, device=x.device, dtype=torch.float64)

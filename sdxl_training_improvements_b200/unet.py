@@ -174,23 +174,35 @@ class UNetEngine:
         M = B * Ho * Wo
         K = 9 * Cin
         N = Npad or Cout
+        implicit = (stride == 1 and not up and Wk is None and Npad is None
+                    and ops.conv3x3_implicit_ok(B, H, W, Cin, Cout))
         Wk = st.w(wname, Cout, K) if Wk is None else Wk
         gWk = st.g(wname, Cout, K) if gWk is None else gWk
-        col = ops.im2col3x3(x.d, B, H, W, Cin, stride, up, out=self.ws("col", M * K, bf16).view(M, K))
-        y = torch.empty((M, N), device=x.d.device, dtype=bf16)
         res = residual.d if residual is not None else None
-        if rowbias is not None:
-            ops.gemm_raw(col, Wk, y, M, N, K, lda=K, ldb=K, ldd=N, bias=rowbias.d, residual=res, ldr=N,
-                         bias_rows_per_group=Ho * Wo, bias_group_stride=N)
+        if implicit:
+            # implicit GEMM: TMA gathers the shifted pixel blocks straight from the NHWC activation (no col buffer)
+            if rowbias is not None:
+                y = ops.conv3x3_fwd(x.d, Wk, B, H, W, Cin, Cout, bias=rowbias.d, residual=res, bias_per_sample=True)
+            else:
+                y = ops.conv3x3_fwd(x.d, Wk, B, H, W, Cin, Cout, bias=st.v(bname), residual=res)
         else:
-            bias = bias_t if bias_t is not None else st.v(bname)
-            ops.gemm_raw(col, Wk, y, M, N, K, lda=K, ldb=K, ldd=N, bias=bias, residual=res, ldr=N)
+            col = ops.im2col3x3(x.d, B, H, W, Cin, stride, up, out=self.ws("col", M * K, bf16).view(M, K))
+            y = torch.empty((M, N), device=x.d.device, dtype=bf16)
+            if rowbias is not None:
+                ops.gemm_raw(col, Wk, y, M, N, K, lda=K, ldb=K, ldd=N, bias=rowbias.d, residual=res, ldr=N,
+                             bias_rows_per_group=Ho * Wo, bias_group_stride=N)
+            else:
+                bias = bias_t if bias_t is not None else st.v(bname)
+                ops.gemm_raw(col, Wk, y, M, N, K, lda=K, ldb=K, ldd=N, bias=bias, residual=res, ldr=N)
         out = Act(y)
 
         def bwd():
             dy = out.g
-            colb = ops.im2col3x3(x.d, B, H, W, Cin, stride, up, out=self.ws("col", M * K, bf16).view(M, K))
-            ops.gemm_raw(dy, colb, gWk, N, K, M, a_mn=True, b_mn=True, lda=N, ldb=K, ldd=K, accumulate=True)
+            if implicit:
+                ops.conv3x3_wgrad(dy, x.d, gWk, B, H, W, Cin, Cout, accumulate=True)
+            else:
+                colb = ops.im2col3x3(x.d, B, H, W, Cin, stride, up, out=self.ws("col", M * K, bf16).view(M, K))
+                ops.gemm_raw(dy, colb, gWk, N, K, M, a_mn=True, b_mn=True, lda=N, ldb=K, ldd=K, accumulate=True)
             if rowbias is not None:
                 if rowbias.g is None:
                     rowbias.g = torch.empty_like(rowbias.d)
@@ -203,10 +215,13 @@ class UNetEngine:
             elif bias_t is None:
                 ops.colsum(dy, st.gv(bname), accumulate=True)
             if need_dx:
-                dcol = self.ws("dcol", M * K, bf16).view(M, K)
-                ops.gemm_raw(dy, Wk, dcol, M, K, N, b_mn=True, lda=N, ldb=K, ldd=K)
                 buf, acc = _gslot(x)
-                ops.col2im3x3(dcol, buf, B, H, W, Cin, stride, up, accumulate=acc)
+                if implicit:
+                    ops.conv3x3_dgrad(dy, Wk, buf, B, H, W, Cin, Cout, accumulate=acc)
+                else:
+                    dcol = self.ws("dcol", M * K, bf16).view(M, K)
+                    ops.gemm_raw(dy, Wk, dcol, M, K, N, b_mn=True, lda=N, ldb=K, ldd=K)
+                    ops.col2im3x3(dcol, buf, B, H, W, Cin, stride, up, accumulate=acc)
             if residual is not None:
                 self._add_grad(residual, dy)
 

@@ -143,6 +143,68 @@ def test_conv3x3_via_im2col(ops, stride, up, B, H, W, Cin, Cout):
     _close(dx.view(B, H, W, Cin).permute(0, 3, 1, 2), xn.grad, atol=3e-2, what="conv dgrad")
 
 
+IMPLICIT_CONV_SHAPES = [
+    # B, H, W, Cin, Cout
+    (2, 16, 16, 128, 64),     # W < 128: box {64, 16, 8}; dgrad with a single 128-wide N tile
+    (1, 32, 32, 192, 320),    # Cout not a multiple of 128 (ragged N tile in fwd, M tail in wgrad)
+    (2, 8, 16, 256, 128),     # H != W, one 128-pixel slab per image
+    (1, 128, 128, 128, 64),   # W == 128: one image row per slab, half a row per wgrad k-block
+    (1, 2, 256, 128, 64),     # W > 128: two slabs per image row
+    (4, 32, 32, 320, 320),    # SDXL-like (320 = 5 x 64 channel blocks per tap)
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", IMPLICIT_CONV_SHAPES)
+def test_conv3x3_implicit(ops, B, H, W, Cin, Cout):
+    """b2_conv3x3 (TMA-gathered implicit GEMM) fwd / dgrad / wgrad vs F.conv2d autograd on the same bf16 inputs."""
+    assert ops.conv3x3_implicit_ok(B, H, W, Cin, Cout)
+    M = B * H * W
+    x = _rand(M, Cin, seed=30)
+    w = _rand(Cout, Cin, 3, 3, scale=1 / math.sqrt(9 * Cin), seed=31)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    bias = _rand(Cout, seed=32)
+    rowb = _rand(B, Cout, seed=33)
+    res = _rand(M, Cout, seed=34)
+
+    def nchw(t, Cc):
+        return t.float().view(B, H, W, Cc).permute(0, 3, 1, 2)
+
+    xn = nchw(x, Cin).clone().requires_grad_(True)
+    wn = w.float().clone().requires_grad_(True)
+    ref = F.conv2d(xn, wn, padding=1)
+    y = ops.conv3x3_fwd(x, wk, B, H, W, Cin, Cout, bias=bias)
+    _close(nchw(y, Cout), ref + bias.float().view(1, -1, 1, 1), what="implicit fwd + bias")
+    y = ops.conv3x3_fwd(x, wk, B, H, W, Cin, Cout, bias=rowb, residual=res, bias_per_sample=True)
+    _close(nchw(y, Cout), ref + rowb.float().view(B, Cout, 1, 1) + nchw(res, Cout), what="implicit fwd + rowbias + res")
+    dy = _rand(M, Cout, seed=35)
+    ref.backward(nchw(dy, Cout))
+    dx = torch.empty_like(x)
+    ops.conv3x3_dgrad(dy, wk, dx, B, H, W, Cin, Cout)
+    _close(nchw(dx, Cin), xn.grad, atol=3e-2, what="implicit dgrad")
+    ops.conv3x3_dgrad(dy, wk, dx, B, H, W, Cin, Cout, accumulate=True)
+    _close(nchw(dx, Cin), 2 * xn.grad, rtol=2 ** -6, atol=6e-2, what="implicit dgrad accumulate")
+    dwk = torch.zeros_like(wk)
+    ops.conv3x3_wgrad(dy, x, dwk, B, H, W, Cin, Cout, accumulate=False)
+    refw = wn.grad.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)
+    _close(dwk, refw, atol=2e-2 * math.sqrt(M / 128), what="implicit wgrad")
+    ops.conv3x3_wgrad(dy, x, dwk, B, H, W, Cin, Cout, accumulate=True)
+    _close(dwk, 2 * refw, rtol=2 ** -6, atol=4e-2 * math.sqrt(M / 128), what="implicit wgrad accumulate")
+    torch.cuda.synchronize()
+
+
+def test_conv3x3_implicit_matches_im2col_path(ops):
+    """Both conv paths share the GEMM kernel; on identical inputs they must agree to the last bit of the fp32 sum order
+    (same k order (kh, kw, cin), same tiles) — checked as exact equality of the bf16 outputs."""
+    B, H, W, Cin, Cout = 2, 32, 32, 128, 128
+    x = _rand(B * H * W, Cin, seed=36)
+    wk = _rand(Cout, 9 * Cin, scale=1 / math.sqrt(9 * Cin), seed=37)
+    y1 = ops.conv3x3_fwd(x, wk, B, H, W, Cin, Cout)
+    y2 = ops.linear_fwd(ops.im2col3x3(x, B, H, W, Cin), wk)
+    assert torch.equal(y1, y2)
+    assert not ops.conv3x3_implicit_ok(1, 12, 20, 128, 128)   # ragged geometry -> im2col path
+    assert not ops.conv3x3_implicit_ok(1, 16, 16, 8, 64)      # conv_in
+
+
 @pytest.mark.parametrize("B,HW,Cc,silu", [(2, 256, 320, True), (2, 100, 64, False), (1, 64, 2560, True), (3, 77, 960, True)])
 def test_groupnorm(ops, B, HW, Cc, silu):
     G = 32
