@@ -65,6 +65,9 @@ typedef struct b2_gemm_args {
   int32_t bias_rows_per_group;
   int64_t bias_group_stride;
   int32_t tile_n;        /* 0 = auto, else 64 / 128 / 256 */
+  int32_t allow_split_k; /* 1: gradient GEMM — the kernel may split K across CTA pairs and combine the bf16 partials
+                            with TMA reduce-adds into D (one extra bf16 rounding per split; D zero-filled first when
+                            !accumulate).  0: single-pass, single-rounding epilogue (forward activations). */
 } b2_gemm_args;
 
 int b2_gemm(const b2_gemm_args* args, void* stream);

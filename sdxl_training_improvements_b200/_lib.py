@@ -22,7 +22,7 @@ class GemmArgs(C.Structure):
         ("d_bs_lo", i64), ("d_bs_hi", i64), ("r_bs_lo", i64), ("r_bs_hi", i64),
         ("alpha", f32), ("accumulate", i32), ("out_fp32", i32),
         ("bias_rows_per_group", i32), ("bias_group_stride", i64),
-        ("tile_n", i32),
+        ("tile_n", i32), ("allow_split_k", i32),
     ]
 
 

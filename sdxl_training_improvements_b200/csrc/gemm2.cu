@@ -56,6 +56,10 @@ struct Gemm2P {
   int cv_sign;   // +1: input pixel = output pixel + (kh-1, kw-1);  -1: minus (dgrad)
   int cv_btap;   // conv = 1 with MN-major B (dgrad): B column offset per tap (= Cin of the weight)
   int cv_C;      // conv = 2: channels of the gathered activation (n -> tap = n / C, c = n % C)
+  // split-K (gradient GEMMs only): work unit = (tile, split); each unit reduces k-blocks [split*kb_per, +kb_per) and
+  // its epilogue adds the bf16 partial into D with a TMA reduce (cp.reduce.async.bulk.tensor .add), so units of one
+  // tile may run concurrently on different clusters.  D must hold the value to accumulate onto (zeros if none).
+  int splits, kb_per;
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
@@ -72,6 +76,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(tm)),
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
@@ -107,7 +117,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int num_tiles = p.tiles_m * p.tiles_n;
-  const int num_kb = (p.K + G2_BK - 1) / G2_BK;
+  const int num_units = num_tiles * p.splits;
+  const int num_kb_total = (p.K + G2_BK - 1) / G2_BK;
   const int halfn = p.BN >> 1;
   const uint32_t stage_tx = G2_A_BYTES + halfn * 128;  // bytes this CTA's two operand tiles occupy
 
@@ -138,39 +149,80 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
-      int it = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cv_cend = p.cv_cpb * 64;
+      const int nblk = halfn / 64;  // 64-column blocks of an MN-major B half-tile (<= 2)
+      for (int u = cluster_id; u < num_units; u += num_clusters) {
+        const int t = u % num_tiles, split = u / num_tiles;
+        const int kb0 = split * p.kb_per, kb1 = min(num_kb_total, kb0 + p.kb_per);
         const int mb = t % p.tiles_m, nb = t / p.tiles_m;
         const int m_base = mb * 256 + (int)rank * 128;
         const int n_base = nb * p.BN + (int)rank * halfn;
-        // implicit-conv decode of this CTA's pixel slab (conv = 1)
-        int cb = 0, ch0 = 0, cw0 = 0;
+        // Implicit-conv address state.  Everything below is strength-reduced to counters: this loop runs on ONE
+        // thread and must issue a k-block's TMAs in well under the k-block's MMA time (256..512 cycles); runtime
+        // integer divisions here (~40 dependent instructions each) made the first version producer-bound.
+        int cb = 0, ch0 = 0, cw0 = 0;          // conv = 1: this CTA's pixel slab -> (image, row, col)
+        int tapc[2] = {0, 0}, tdw[2] = {0, 0}, tdh[2] = {0, 0};  // conv = 2: per 64-column block (channel, dw, dh)
         if (p.conv == 1) {
           cb = m_base / p.cv_HW;
           const int rem = m_base - cb * p.cv_HW;
           ch0 = rem / p.cv_W;
           cw0 = rem - ch0 * p.cv_W;
+        } else if (p.conv == 2) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (j >= nblk) break;
+            const int n = n_base + 64 * j;
+            const int tap = n / p.cv_C;
+            tapc[j] = n - tap * p.cv_C;
+            const int kh = tap / 3;
+            tdh[j] = kh - 1;
+            tdw[j] = tap - kh * 3 - 1;
+          }
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % G2_STAGES;
-          const uint32_t ph = (it / G2_STAGES) & 1;
-          mbar_wait<true>(smem_u32(&bar_empty[s]), ph ^ 1u);
-          const uint32_t full_local = smem_u32(&bar_full[s]);
+        int c0 = 0, kw = 0, kh = 0, tapoff = 0;  // conv = 1 k-block walk: channel block, tap
+        int pw0 = 0, ph0 = 0, pb = 0;            // conv = 2 k-block walk: 64-pixel block -> (col, row, image)
+        const int rows_per_kb = p.cv_W >= 64 ? 1 : 64 / (p.cv_W > 0 ? p.cv_W : 64);
+        const int cv_H = p.conv ? p.cv_HW / p.cv_W : 0;
+        if (kb0 > 0) {  // split-K: start the walk at this unit's first k-block
+          if (p.conv == 1) {
+            const int tap = kb0 / p.cv_cpb;
+            c0 = (kb0 - tap * p.cv_cpb) * 64;
+            kh = tap / 3;
+            kw = tap - kh * 3;
+            tapoff = tap * p.cv_btap;
+          } else if (p.conv == 2) {
+            const int px = kb0 * 64;
+            pb = px / p.cv_HW;
+            const int rem = px - pb * p.cv_HW;
+            ph0 = rem / p.cv_W;
+            pw0 = rem - ph0 * p.cv_W;
+          }
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait<true>(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full_local = smem_u32(&bar_full[stage]);
           if (leader) mbar_expect_tx(full_local, 2 * stage_tx);
           const uint32_t full = mapa_u32(full_local, 0);
-          const uint32_t sa = smem_base + s * G2_STAGE_BYTES;
+          const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
           const uint32_t sb = sa + G2_A_BYTES;
           const int k0 = kb * G2_BK;
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
           if (p.conv == 1) {
-            const int tap = kb / p.cv_cpb;
-            const int c0 = (kb - tap * p.cv_cpb) * 64;
-            const int kh = tap / 3, kw = tap - kh * 3;
             tma_load_4d_2sm(sa, &tmA, full, c0, cw0 + p.cv_sign * (kw - 1), ch0 + p.cv_sign * (kh - 1), cb);
             if (!p.b_mn) {
               tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
             } else {
-              for (int j = 0; j < halfn / 64; ++j)
-                tma_load_2d_2sm(sb + j * 8192, &tmB, full, tap * p.cv_btap + n_base + 64 * j, c0);
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                if (j < nblk) tma_load_2d_2sm(sb + j * 8192, &tmB, full, tapoff + n_base + 64 * j, c0);
+            }
+            c0 += 64;
+            if (c0 == cv_cend) {
+              c0 = 0;
+              tapoff += p.cv_btap;
+              if (++kw == 3) { kw = 0; ++kh; }
             }
             continue;
           }
@@ -181,20 +233,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_load_2d_2sm(sa + 8192, &tmA, full, m_base + 64, k0);
           }
           if (p.conv == 2) {
-            const int pb = k0 / p.cv_HW;
-            const int rem = k0 - pb * p.cv_HW;
-            const int ph0 = rem / p.cv_W, pw0 = rem - ph0 * p.cv_W;
-            for (int j = 0; j < halfn / 64; ++j) {
-              const int n = n_base + 64 * j;
-              const int tap = n / p.cv_C;
-              const int c0 = n - tap * p.cv_C;
-              const int kh = tap / 3, kw = tap - kh * 3;
-              tma_load_4d_2sm(sb + j * 8192, &tmB, full, c0, pw0 + kw - 1, ph0 + kh - 1, pb);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              if (j < nblk) tma_load_4d_2sm(sb + j * 8192, &tmB, full, tapc[j], pw0 + tdw[j], ph0 + tdh[j], pb);
+            if (p.cv_W >= 64) {
+              pw0 += 64;
+              if (pw0 == p.cv_W) { pw0 = 0; ++ph0; }
+            } else {
+              ph0 += rows_per_kb;
             }
+            if (ph0 == cv_H) { ph0 = 0; ++pb; }
           } else if (!p.b_mn) {
             tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
           } else {
-            for (int j = 0; j < halfn / 64; ++j) tma_load_2d_2sm(sb + j * 8192, &tmB, full, n_base + 64 * j, k0);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              if (j < nblk) tma_load_2d_2sm(sb + j * 8192, &tmB, full, n_base + 64 * j, k0);
           }
         }
       }
@@ -205,25 +259,29 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t idesc = umma_idesc(256, p.BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? 8192 : 16, a_kstep = p.a_mn ? 2048 : 32;
       const uint32_t b_lbo = p.b_mn ? 8192 : 16, b_kstep = p.b_mn ? 2048 : 32;
-      int it = 0, tile_i = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
+      // descriptors differ between stages / k-steps only in their 14-bit start-address field: one add each
+      const uint64_t adesc0 = umma_desc(smem_base, a_lbo, 1024);
+      const uint64_t bdesc0 = umma_desc(smem_base + G2_A_BYTES, b_lbo, 1024);
+      const uint32_t a_k16 = a_kstep >> 4, b_k16 = b_kstep >> 4;
+      int tile_i = 0, stage = 0;
+      uint32_t phase = 0;
+      for (int u = cluster_id; u < num_units; u += num_clusters, ++tile_i) {
+        const int split = u / num_tiles;
+        const int kb0 = split * p.kb_per, kb1 = min(num_kb_total, kb0 + p.kb_per);
         const int buf = tile_i & 1;
         const uint32_t use = (uint32_t)tile_i >> 1;
         mbar_wait<true>(smem_u32(&bar_acc_empty[buf]), (use & 1) ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * 256;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % G2_STAGES;
-          const uint32_t ph = (it / G2_STAGES) & 1;
-          mbar_wait<true>(smem_u32(&bar_full[s]), ph);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait<true>(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * G2_STAGE_BYTES;
-          const uint32_t sb = sa + G2_A_BYTES;
+          const uint64_t so = (uint64_t)((uint32_t)(stage * G2_STAGE_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < G2_BK / 16; ++k)
-            umma_bf16_2sm(tacc, umma_desc(sa + k * a_kstep, a_lbo, 1024), umma_desc(sb + k * b_kstep, b_lbo, 1024), idesc,
-                          (kb | k) != 0);
-          umma_commit_2sm(smem_u32(&bar_empty[s]), 3);
+            umma_bf16_2sm(tacc, adesc0 + so + k * a_k16, bdesc0 + so + k * b_k16, idesc, ((kb - kb0) | k) != 0);
+          umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit_2sm(smem_u32(&bar_acc_full[buf]), 3);
       }
@@ -238,7 +296,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int tile_i = 0;
     uint32_t chunk_i = 0;
     uint32_t res_uses[2] = {0, 0};
-    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
+    const bool reduce_out = p.splits > 1;
+    for (int u = cluster_id; u < num_units; u += num_clusters, ++tile_i) {
+      const int t = u % num_tiles;
       const int mb = t % p.tiles_m, nb = t / p.tiles_m;
       const int m_base = mb * 256 + (int)rank * 128;
       const int n_tile = nb * p.BN;
@@ -309,7 +369,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           fence_proxy_async_smem();
           epi_bar_sync();
           if (et == 0) {
-            tma_store_2d(&tmD, stage, n0, m_base);
+            if (reduce_out)
+              tma_reduce_add_2d(&tmD, stage, n0, m_base);
+            else
+              tma_store_2d(&tmD, stage, n0, m_base);
             tma_store_commit();
           }
           ++chunk_i;
@@ -418,6 +481,57 @@ int gemm2_pick_bn(int M, int N, int K, int b_mn, int num_clusters) {
   return best;
 }
 
+struct G2Plan { int bn, splits, kb_per; };
+
+// Tile width + K split for a gradient GEMM.  Model: a unit costs kb_per * tile_cost(bn) + a fixed hand-over bubble;
+// units run in rounds of `num_clusters`.  Splitting pays when the tile grid cannot fill the machine (wgrad: small
+// output, long reduction) or quantises badly (80 tiles on 74 clusters).
+static G2Plan gemm2_plan(int M, int N, int K, int b_mn, int num_clusters, bool may_split, bool needs_zero_fill) {
+  G2Plan best{gemm2_pick_bn(M, N, K, b_mn, num_clusters), 1, (K + G2_BK - 1) / G2_BK};
+  const char* env = getenv("B2_GEMM_SPLITK");
+  if (!may_split || (env && atoi(env) == 0)) return best;
+  const int num_kb = (K + G2_BK - 1) / G2_BK;
+  const int tiles_m = (M + 255) / 256;
+  auto unit_cost = [&](int bn, int splits, int kb_per) {
+    const long long units = (long long)tiles_m * ((N + bn - 1) / bn) * splits;
+    const long long rounds = (units + num_clusters - 1) / num_clusters;
+    return rounds * (kb_per * tile_cost(bn) + 1200.0 + (splits > 1 ? 600.0 : 0.0)) +
+           ((splits > 1 && needs_zero_fill) ? 3000.0 : 0.0);
+  };
+  double best_cost = unit_cost(best.bn, 1, num_kb);
+  static const int cand[] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
+  for (int bn = 256; bn >= 128; bn -= 64) {
+    if (b_mn && (bn & 127)) continue;
+    if (bn > 128 && bn - 64 >= N) continue;
+    for (int s : cand) {
+      const int kb_per = (num_kb + s - 1) / s;
+      if (kb_per < 8) break;
+      const int splits = (num_kb + kb_per - 1) / kb_per;
+      const double c = unit_cost(bn, splits, kb_per);
+      if (c < best_cost * 0.93) {  // demand a real gain before giving up the single-rounding epilogue
+        best_cost = c;
+        best = G2Plan{bn, splits, kb_per};
+      }
+    }
+  }
+  if (env && atoi(env) > 1) {
+    const int s = atoi(env);
+    const int kb_per = (num_kb + s - 1) / s;
+    best = G2Plan{b_mn ? 256 : 256, (num_kb + kb_per - 1) / kb_per, kb_per};
+  }
+  return best;
+}
+
+// split-K accumulates into D with reduce-adds: when the caller did not ask for `+=`, D starts from zero
+static int gemm2_zero_fill(void* D, long long ldd, int M, int N, cudaStream_t st) {
+  cudaError_t e = cudaMemset2DAsync(D, (size_t)ldd * 2, 0, (size_t)N * 2, (size_t)M, st);
+  if (e != cudaSuccess) {
+    set_error("b2_gemm split-K zero fill: %s", cudaGetErrorString(e));
+    return B2_ERR_CUDA;
+  }
+  return B2_OK;
+}
+
 static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr,
                         Gemm2P& p, cudaStream_t st, const char* what) {
   static bool configured = false;
@@ -432,7 +546,12 @@ static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   const int num_clusters = num_sms() / 2;
   p.tiles_m = (p.M + 255) / 256;
   p.tiles_n = (p.N + p.BN - 1) / p.BN;
-  const long long tiles = (long long)p.tiles_m * p.tiles_n;
+  if (p.splits < 1) {
+    p.splits = 1;
+    p.kb_per = (p.K + G2_BK - 1) / G2_BK;
+  }
+  if (p.splits > 1) p.has_res = 0;  // the reduce-add epilogue is the accumulation
+  const long long tiles = (long long)p.tiles_m * p.tiles_n * p.splits;
   const int clusters = (int)(tiles < num_clusters ? tiles : num_clusters);
   gemm2_kernel<<<dim3(2 * clusters), G2_THREADS, G2_SMEM, st>>>(ta, tb, td, tr, p);
   return check_launch(what);
@@ -452,7 +571,9 @@ int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc) {
   if (a->bias && ((a->bias_group_stride & 7) || (reinterpret_cast<uintptr_t>(a->bias) & 15))) return 0;
 
   const int num_clusters = num_sms() / 2;
-  const int bn = gemm2_pick_bn(a->M, a->N, a->K, a->b_mn, num_clusters);
+  const bool may_split = a->allow_split_k && !a->bias && !a->residual && a->alpha == 1.f;
+  const G2Plan plan = gemm2_plan(a->M, a->N, a->K, a->b_mn, num_clusters, may_split, !a->accumulate);
+  const int bn = plan.bn;
   if (bn < 32 || bn > 256 || (bn & 15) || (a->b_mn && (bn & 127))) {
     set_error("b2_gemm: bad BN %d", bn);
     *out_rc = B2_ERR_ARG;
@@ -488,10 +609,14 @@ int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc) {
   p.has_res = R ? 1 : 0;
   p.D = reinterpret_cast<bf16*>(a->D); p.ldd = a->ldd;
   p.R = reinterpret_cast<const bf16*>(R); p.ldr = ldr;
+  p.splits = plan.splits; p.kb_per = plan.kb_per;
+  if (plan.splits > 1 && !a->accumulate) {
+    if ((rc = gemm2_zero_fill(a->D, a->ldd, a->M, a->N, st))) { *out_rc = rc; return 1; }
+  }
   static const bool log_calls = getenv("B2_GEMM_LOG") != nullptr;
   if (log_calls)
-    fprintf(stderr, "B2GEMM M=%d N=%d K=%d a_mn=%d b_mn=%d BN=%d bias=%d res=%d acc=%d\n", a->M, a->N, a->K, p.a_mn, p.b_mn,
-            bn, a->bias != nullptr, a->residual != nullptr, a->accumulate);
+    fprintf(stderr, "B2GEMM M=%d N=%d K=%d a_mn=%d b_mn=%d BN=%d splits=%d bias=%d res=%d acc=%d\n", a->M, a->N, a->K, p.a_mn,
+            p.b_mn, bn, plan.splits, a->bias != nullptr, a->residual != nullptr, a->accumulate);
   *out_rc = gemm2_launch(ta, tb, td, tr, p, st, "b2_gemm(pair)");
   return 1;
 }
@@ -590,7 +715,11 @@ extern "C" int b2_conv3x3(const b2_conv3x3_args* a, void* stream) {
     B2_REQUIRE(Cin >= 128, "b2_conv3x3 dgrad: Cin < 128");
     p.M = (int)pixels; p.N = Cin; p.K = 9 * Cout;
     p.a_mn = 0; p.b_mn = 1; p.conv = 1; p.cv_sign = -1; p.cv_cpb = Cout / 64; p.cv_btap = Cin;
-    p.BN = gemm2_pick_bn(p.M, p.N, p.K, 1, num_clusters);
+    {
+      const G2Plan plan = gemm2_plan(p.M, p.N, p.K, 1, num_clusters, true, !a->accumulate);
+      p.BN = plan.bn; p.splits = plan.splits; p.kb_per = plan.kb_per;
+      if (plan.splits > 1 && !a->accumulate && (rc = gemm2_zero_fill(a->x, ldx, p.M, p.N, st))) return rc;
+    }
     if ((rc = make_map_conv(&ta, a->y, B, H, W, Cout, ldy, 128, "conv dy"))) return rc;
     if ((rc = make_map_2d(&tb, a->w, 9ull * Cin, Cout, ldw, 64, 64, "conv w(mn)"))) return rc;
     if ((rc = make_map_2d(&td, a->x, Cin, pixels, ldx, 64, 128, "conv dx"))) return rc;
@@ -600,7 +729,11 @@ extern "C" int b2_conv3x3(const b2_conv3x3_args* a, void* stream) {
   } else {  // dw[Cout, 9*Cin] (+)= dy^T (*) x
     p.M = Cout; p.N = 9 * Cin; p.K = (int)pixels;
     p.a_mn = 1; p.b_mn = 1; p.conv = 2; p.cv_sign = 1; p.cv_C = Cin;
-    p.BN = gemm2_pick_bn(p.M, p.N, p.K, 1, num_clusters);
+    {
+      const G2Plan plan = gemm2_plan(p.M, p.N, p.K, 1, num_clusters, true, !a->accumulate);
+      p.BN = plan.bn; p.splits = plan.splits; p.kb_per = plan.kb_per;
+      if (plan.splits > 1 && !a->accumulate && (rc = gemm2_zero_fill(a->w, ldw, p.M, p.N, st))) return rc;
+    }
     if ((rc = make_map_2d(&ta, a->y, Cout, pixels, ldy, 64, 64, "conv dy(mn)"))) return rc;
     if ((rc = make_map_conv(&tb, a->x, B, H, W, Cin, ldx, 64, "conv x(mn)"))) return rc;
     if ((rc = make_map_2d(&td, a->w, 9ull * Cin, Cout, ldw, 64, 128, "conv dw"))) return rc;

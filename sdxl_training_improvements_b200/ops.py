@@ -32,7 +32,7 @@ def _need_cuda(*ts):
 # --------------------------------------------------------------------------------------- GEMM
 def gemm_raw(A, B, D, M, N, K, *, a_mn=False, b_mn=False, lda, ldb, ldd, bias=None, residual=None, ldr=0,
              nb_lo=1, nb_hi=1, a_bs=(0, 0), b_bs=(0, 0), d_bs=(0, 0), r_bs=(0, 0), alpha=1.0, accumulate=False,
-             out_fp32=False, bias_rows_per_group=0, bias_group_stride=0, tile_n=0):
+             out_fp32=False, bias_rows_per_group=0, bias_group_stride=0, tile_n=0, allow_split_k=False):
     _need_cuda(A, B, D, bias, residual)
     lib = _lib.load()
     g = _lib.GemmArgs()
@@ -49,6 +49,7 @@ def gemm_raw(A, B, D, M, N, K, *, a_mn=False, b_mn=False, lda, ldb, ldd, bias=No
     g.accumulate, g.out_fp32 = int(accumulate), int(out_fp32)
     g.bias_rows_per_group, g.bias_group_stride = int(bias_rows_per_group), int(bias_group_stride)
     g.tile_n = int(tile_n)
+    g.allow_split_k = int(allow_split_k)
     _lib.check(lib.b2_gemm(C.byref(g), _stream()), "b2_gemm")
     return D
 
@@ -72,7 +73,7 @@ def linear_dgrad(dy, W, dx=None, accumulate=False, *, K=None, ldw=None):
         dx = torch.empty((M, K), device=dy.device, dtype=bf16)
         accumulate = False
     return gemm_raw(dy, W, dx, M, K, N, a_mn=False, b_mn=True, lda=dy.stride(0), ldb=(ldw or W.stride(0)),
-                    ldd=dx.stride(0), accumulate=accumulate)
+                    ldd=dx.stride(0), accumulate=accumulate, allow_split_k=True)
 
 
 def linear_wgrad(dy, x, dW, accumulate=True, *, ldw=None, K=None):
@@ -80,7 +81,7 @@ def linear_wgrad(dy, x, dW, accumulate=True, *, ldw=None, K=None):
     M, N = dy.shape
     K = K or x.shape[1]
     return gemm_raw(dy, x, dW, N, K, M, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0),
-                    ldd=(ldw or dW.stride(0)), accumulate=accumulate)
+                    ldd=(ldw or dW.stride(0)), accumulate=accumulate, allow_split_k=True)
 
 
 # --------------------------------------------------------------------------------------- conv staging

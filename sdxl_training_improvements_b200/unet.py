@@ -202,7 +202,8 @@ class UNetEngine:
                 ops.conv3x3_wgrad(dy, x.d, gWk, B, H, W, Cin, Cout, accumulate=True)
             else:
                 colb = ops.im2col3x3(x.d, B, H, W, Cin, stride, up, out=self.ws("col", M * K, bf16).view(M, K))
-                ops.gemm_raw(dy, colb, gWk, N, K, M, a_mn=True, b_mn=True, lda=N, ldb=K, ldd=K, accumulate=True)
+                ops.gemm_raw(dy, colb, gWk, N, K, M, a_mn=True, b_mn=True, lda=N, ldb=K, ldd=K, accumulate=True,
+                             allow_split_k=True)
             if rowbias is not None:
                 if rowbias.g is None:
                     rowbias.g = torch.empty_like(rowbias.d)

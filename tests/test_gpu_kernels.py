@@ -143,6 +143,41 @@ def test_conv3x3_via_im2col(ops, stride, up, B, H, W, Cin, Cout):
     _close(dx.view(B, H, W, Cin).permute(0, 3, 1, 2), xn.grad, atol=3e-2, what="conv dgrad")
 
 
+SPLITK_SHAPES = [
+    # M (rows of x / dy), N (out features), K (in features): wgrad reduces over M, dgrad over N
+    (16384, 640, 640),     # wgrad: 3x3 tiles, 256 k-blocks -> split 8
+    (4096, 1280, 1280),    # wgrad: 25 tiles -> split 2
+    (4096, 10240, 1280),   # dgrad: N_gemm = 1280 -> 80 tiles on 74 clusters, K_gemm = 10240 -> split
+    (65536, 320, 320),     # conv-like wgrad: 2x2 tiles, 1024 k-blocks
+]
+
+
+@pytest.mark.parametrize("M,N,K", SPLITK_SHAPES)
+def test_gemm_split_k_gradients(ops, M, N, K):
+    """Gradient GEMMs whose tile grid cannot fill 74 CTA pairs split K and combine bf16 partials with TMA reduce-adds.
+    Checked against fp32 matmul, with and without accumulation, and against the unsplit kernel (allow_split_k=False)."""
+    x = _rand(M, K, seed=40)
+    W = _rand(N, K, scale=1 / math.sqrt(K), seed=41)
+    dy = _rand(M, N, scale=0.25, seed=42)
+    ref_dx = dy.float() @ W.float()
+    dx = torch.full((M, K), 7.0, device="cuda", dtype=bf16)     # must be overwritten (zero-filled by the call)
+    ops.linear_dgrad(dy, W, dx, accumulate=False)
+    _close(dx, ref_dx, atol=3e-2, what="split-K dgrad")
+    ops.linear_dgrad(dy, W, dx, accumulate=True)
+    _close(dx, 2 * ref_dx, rtol=2 ** -6, atol=6e-2, what="split-K dgrad accumulate")
+    ref_dw = dy.float().t() @ x.float()
+    dW = torch.full((N, K), -3.0, device="cuda", dtype=bf16)
+    ops.linear_wgrad(dy, x, dW, accumulate=False)
+    scale = float(ref_dw.abs().max())
+    _close(dW, ref_dw, rtol=2 ** -6, atol=2e-3 * scale, what="split-K wgrad")
+    dW1 = torch.zeros_like(dW)
+    ops.gemm_raw(dy, x, dW1, N, K, M, a_mn=True, b_mn=True, lda=N, ldb=K, ldd=K, allow_split_k=False)
+    _close(dW, dW1, rtol=2 ** -6, atol=2e-3 * scale, what="split vs unsplit")
+    ops.linear_wgrad(dy, x, dW, accumulate=True)
+    _close(dW, 2 * ref_dw, rtol=2 ** -5, atol=4e-3 * scale, what="split-K wgrad accumulate")
+    torch.cuda.synchronize()
+
+
 IMPLICIT_CONV_SHAPES = [
     # B, H, W, Cin, Cout
     (2, 16, 16, 128, 64),     # W < 128: box {64, 16, 8}; dgrad with a single 128-wide N tile
