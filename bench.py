@@ -242,7 +242,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from sdxl_training_improvements_b200 import _lib, ops
     from sdxl_training_improvements_b200.flops import train_step_flops
-    from sdxl_training_improvements_b200.trainer import B200AdamW, create_trainer
+    from sdxl_training_improvements_b200.trainer import B200AdamW, B200AdamWBF16, create_trainer
     from sdxl_training_improvements_b200.unet import B200UNet
 
     peaks = _peaks()
@@ -250,8 +250,12 @@ def run_ours(args):
     cfg = _config_ns(args.method)
     unet = B200UNet(device=f"cuda:{local}")
     _init_weights_(unet, seed=1234)  # identical on every rank (replicated parameters)
-    opt = B200AdamW(unet, lr=4e-7, weight_decay=1e-2, master_weights=True)
-    trainer = create_trainer(cfg, unet, opt, device=f"cuda:{local}", seed=1000 + rank)
+    if args.optimizer == "adamw_bf16":  # the reference's default (src/config.yaml: optimizer_type adamw_bf16)
+        opt = B200AdamWBF16(unet, lr=4e-7, weight_decay=1e-2, seed=4321)
+    else:
+        opt = B200AdamW(unet, lr=4e-7, weight_decay=1e-2, master_weights=True)
+    use_graph = not args.no_graph
+    trainer = create_trainer(cfg, unet, opt, device=f"cuda:{local}", seed=1000 + rank, cuda_graph=use_graph)
     batch = _synthetic_batch(B, H, W, seed=77 + rank)
     h2d = sum(v.numel() * v.element_size() for k, v in batch.items() if torch.is_tensor(v))
 
@@ -281,6 +285,8 @@ def run_ours(args):
         t_embed = [t.float().cuda() for t in ts]
         sig = t_embed
     core = trainer.core
+    gm = next(iter(trainer._micro_graphs.values())) if use_graph else None
+    og = trainer._opt_graph if use_graph else None
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = _lib.launch_count()
@@ -288,16 +294,25 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        core.step_no_autograd(latents=dev_batch["latents"], ctx=dev_batch["ctx"], pooled=dev_batch["pooled"],
-                              time_ids=dev_batch["time_ids"], t_embed=t_embed[i], sig_or_t=sig[i], weight=None,
-                              loss_scale=1.0)
-        if world > 1:
-            allreduce_gradients(unet)
-        opt.fused_step(max_norm=1.0, grad_scale=1.0 / world)
-        opt.zero_grad()
+        if use_graph:  # one graph launch per micro-step, one per optimizer step; inputs already resident in HBM
+            gm.load(dev_batch["latents"], dev_batch["ctx"], dev_batch["pooled"], dev_batch["time_ids"], t_embed[i], sig[i])
+            gm.replay()
+            if world > 1:
+                allreduce_gradients(unet)
+            og.replay()
+        else:
+            core.step_no_autograd(latents=dev_batch["latents"], ctx=dev_batch["ctx"], pooled=dev_batch["pooled"],
+                                  time_ids=dev_batch["time_ids"], t_embed=t_embed[i], sig_or_t=sig[i], weight=None,
+                                  loss_scale=1.0)
+            if world > 1:
+                allreduce_gradients(unet)
+            opt.fused_step(max_norm=1.0, grad_scale=1.0 / world)
+            opt.zero_grad()
     e1.record()
     barrier()
     launches = _lib.launch_count() - launches0
+    if use_graph:
+        launches = K * (gm.launches_per_replay + og.launches_per_replay)
     ms_dev = e0.elapsed_time(e1) / K
 
     # ---- (2) end-to-end through the plugin API with host buffers: `e2e` ----
@@ -332,13 +347,15 @@ def run_ours(args):
                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev, 2), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                "config": {"workload": f"SDXL-base UNet, {args.method} v_prediction, bs=4/GPU, 1024^2 (latent 128x128), "
-                                      "bf16, full fwd+bwd+loss+clip+AdamW (configs[1])",
+                                      f"bf16, full fwd+bwd+loss+clip+{args.optimizer} (configs[1])",
+                          "cuda_graph": use_graph,
                           "global_batch": B * world, "parallelism": f"dp{world}",
                           "l2": "working set >> L2: 5.1 GB of weights + ~40 GB activations streamed every step",
                           "last_loss": last_loss},
                "e2e": {"value": round(e2e_v, 4), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": 4 + 6 * 8, "ms_per_step": round(ms_e2e, 2),
-                       "api": "B200DDPMTrainer._execute_training_step(batch) with pinned host tensors"},
+                       "api": "B200DDPMTrainer._execute_training_step(batch) with pinned host tensors"
+                              + (" (cuda_graph=True)" if use_graph else "")},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb}
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -353,6 +370,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--method", default="ddpm", choices=["ddpm", "flow_matching"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="adamw_bf16", choices=["adamw_bf16", "adamw_fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -236,7 +236,8 @@ int b2_abs_sq_sums(const void* x, int is_fp32, int64_t n, int period, int valid,
 int b2_scale_bf16(void* x, int64_t n, const float* dev_scale, float host_scale, void* stream);
 int b2_adamw(void* p, float* master /* fp32 master weights or NULL */, const void* g, float* m, float* v, int64_t n,
              float lr, float beta1, float beta2, float eps, float weight_decay, int step, const double* gnorm_sq,
-             float max_norm, float grad_scale, void* stream);
+             float max_norm, float grad_scale, const uint64_t* dev_step /* used when step <= 0: the step counter is read
+             from device memory, so a captured CUDA graph advances it per replay (b2_philox_advance) */, void* stream);
 
 /* AdamWBF16 — the reference's default optimizer (src/config.yaml `optimizer_type: adamw_bf16`;
  * src/training/optimizers/adamw_bfloat16/__init__.py:86-197, stochastic/__init__.py:46-124) as one fused launch over
@@ -245,6 +246,7 @@ int b2_adamw(void* p, float* master /* fp32 master weights or NULL */, const voi
  * torch.nn.utils.clip_grad_norm_).  18 bytes of HBM traffic per parameter.
  *   as_written = 1 keeps add_stochastic_'s operand order as the reference wrote it (exp_avg <- SR(g + (1-b1) b1 m)).
  *   rng_mode: 0 Philox(seed_offset[0], step); 1/2/3 deterministic patterns for parity tests (3: int32 [4,n] buffer).
+ *   step <= 0: the step is read from seed_offset[1] on the device (CUDA-graph replays; advance with b2_philox_advance).
  * b2_axpy_bf16: y <- bf16(y + alpha x) — the deferred weight decay `shift.add_(p, alpha=-decay)` (:191-192). */
 int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shift, int64_t n, float lr, float beta1, float beta2,
                   float eps, int step, const double* gnorm_sq, float max_norm, float grad_scale,

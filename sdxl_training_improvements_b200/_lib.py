@@ -89,7 +89,7 @@ SIGNATURES = {
     "b2_sumsq": [c_p, i64, c_p, c_p],
     "b2_adamw_bf16": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, i32, c_p, f32, f32, c_p, i32, i32, c_p, c_p],
     "b2_axpy_bf16": [c_p, c_p, i64, f32, c_p],
-    "b2_adamw": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, c_p, f32, f32, c_p],
+    "b2_adamw": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, c_p, f32, f32, c_p, c_p],
 }
 _RESTYPES = {"b2_last_error": C.c_char_p, "b2_launch_count": C.c_longlong}
 

@@ -162,7 +162,13 @@ __global__ void sumsq_kernel(const bf16* __restrict__ g, long long n, double* ou
 
 __global__ void adamw_kernel(bf16* __restrict__ p, float* __restrict__ master, const bf16* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd, float bc1,
-                             float bc2, const double* gnorm_sq, float max_norm, float grad_scale) {
+                             float bc2, const double* gnorm_sq, float max_norm, float grad_scale,
+                             const uint64_t* __restrict__ dev_step) {
+  if (dev_step) {  // step counter lives on the device so that a captured CUDA graph advances it on every replay
+    const float st = (float)dev_step[0];
+    bc1 = 1.f - powf(b1, st);
+    bc2 = 1.f - powf(b2, st);
+  }
   float clip = grad_scale;
   if (gnorm_sq && max_norm > 0.f) {
     const float norm = (float)sqrt(*gnorm_sq) * grad_scale;
@@ -279,10 +285,11 @@ extern "C" int b2_sumsq(const void* g, int64_t n, double* out, void* stream) {
 }
 extern "C" int b2_adamw(void* p, float* master, const void* g, float* m, float* v, int64_t n, float lr, float beta1,
                         float beta2, float eps, float weight_decay, int step, const double* gnorm_sq, float max_norm,
-                        float grad_scale, void* stream) {
-  B2_REQUIRE(p && g && m && v && n > 0 && step >= 1, "b2_adamw: bad args");
+                        float grad_scale, const uint64_t* dev_step, void* stream) {
+  B2_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || dev_step), "b2_adamw: bad args");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adamw_kernel<<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>((bf16*)p, master, (const bf16*)g, m, v, n, lr, beta1, beta2,
-                                                                eps, weight_decay, bc1, bc2, gnorm_sq, max_norm, grad_scale);
+                                                                eps, weight_decay, bc1, bc2, gnorm_sq, max_norm, grad_scale,
+                                                                step >= 1 ? nullptr : dev_step);
   return check_launch("adamw");
 }

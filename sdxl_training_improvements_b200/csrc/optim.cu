@@ -37,7 +37,9 @@ __device__ __forceinline__ float sr_bf16(float x, uint32_t r16) {
 
 struct AdamBF16P {
   float b1, b2, eps;
-  float step_size;  // -lr * sqrt(1 - beta2^step)
+  float step_size;  // -lr * sqrt(1 - beta2^step)   (host step)
+  float lr;         // device step (seed_offset[1]): step_size is recomputed in the kernel
+  int dev_step;
   float max_norm, grad_scale;
   int as_written;
   int rng_mode;     // 0: Philox; 1: rand16 = 0 (truncate); 2: rand16 = 0xFFFF; 3: rand16 read from `test_rand16`
@@ -80,6 +82,10 @@ adamw_bf16_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __rest
   }
   const uint64_t seed = seed_offset ? seed_offset[0] : 0;
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  if (a.dev_step) {  // CUDA-graph replays advance seed_offset[1] on the device
+    step = seed_offset[1];
+    a.step_size = (float)(-(double)a.lr * sqrt(1.0 - pow((double)a.b2, (double)step)));
+  }
   const long long nv = n >> 3;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += (long long)gridDim.x * blockDim.x) {
     float fp[8], fg[8], fm[8], fv[8], fs[8];
@@ -153,7 +159,7 @@ extern "C" int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shi
                              float beta2, float eps, int step, const double* gnorm_sq, float max_norm, float grad_scale,
                              const uint64_t* seed_offset, int as_written, int rng_mode, const int32_t* test_rand16,
                              void* stream) {
-  B2_REQUIRE(p && g && m && v && shift && n > 0 && step >= 1, "b2_adamw_bf16: bad args");
+  B2_REQUIRE(p && g && m && v && shift && n > 0 && (step >= 1 || seed_offset), "b2_adamw_bf16: bad args");
   B2_REQUIRE(!((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                 reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(shift)) & 15),
              "b2_adamw_bf16: buffers must be 16-byte aligned");
@@ -162,6 +168,7 @@ extern "C" int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shi
   a.b1 = beta1; a.b2 = beta2; a.eps = eps;
   // python: value = -lr * (1 - beta2**step) ** 0.5  (double), passed to a float kernel argument
   a.step_size = (float)(-(double)lr * sqrt(1.0 - pow((double)beta2, (double)step)));
+  a.lr = lr; a.dev_step = step >= 1 ? 0 : 1;
   a.max_norm = max_norm; a.grad_scale = grad_scale;
   a.as_written = as_written; a.rng_mode = rng_mode;
   long long blocks = ((n >> 3) + 255) / 256;

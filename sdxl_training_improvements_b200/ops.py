@@ -367,10 +367,11 @@ def sumsq(g, out):
 
 
 def adamw(p, master, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, step=1, gnorm_sq=None,
-          max_norm=0.0, grad_scale=1.0):
+          max_norm=0.0, grad_scale=1.0, dev_step=None):
+    """step >= 1: host step; step = 0: read the step from the device counter `dev_step` (uint64, CUDA-graph safe)."""
     _lib.check(_lib.load().b2_adamw(_p(p), _p(master), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps,
                                    weight_decay, int(step), _p(gnorm_sq), float(max_norm), float(grad_scale),
-                                   _stream()), "adamw")
+                                   _p(dev_step), _stream()), "adamw")
 
 
 def adamw_bf16(p, g, m, v, shift, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, gnorm_sq=None, max_norm=0.0,

@@ -97,6 +97,18 @@ class _FusedLoss(torch.autograd.Function):
         return None, None, None
 
 
+class _PrecomputedBackward(torch.autograd.Function):
+    """Loss of a graph-replayed micro-step: gradients are already in p.grad, so backward is a no-op."""
+
+    @staticmethod
+    def forward(ctx, loss, anchor):
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, None
+
+
 class FusedLossCore:
     """Device-side part of one micro-step.  `method`: "ddpm" | "flow_matching"."""
 
@@ -144,15 +156,116 @@ class FusedLossCore:
     def loss_fn(self, **args) -> torch.Tensor:
         return _FusedLoss.apply(self, self._anchor, args)
 
-    def step_no_autograd(self, grad_scale: float = 1.0, **args) -> torch.Tensor:
-        """forward + backward without torch autograd (used by the graph-captured bench/step path)."""
+    def step_no_autograd(self, grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None, **args) -> torch.Tensor:
+        """forward + backward without torch autograd (used by the graph-captured bench/step path).  `grad_scale_dev`
+        (1-element fp32 device tensor) carries autograd's upstream scalar (1 / accumulation steps) in graph replays."""
         loss = self._forward(**args)
         tape, dpred = self._saved
         self._saved = None
-        if grad_scale != 1.0:
+        if grad_scale_dev is not None:
+            ops.scale_bf16(dpred, grad_scale_dev, 1.0)
+        elif grad_scale != 1.0:
             ops.scale_bf16(dpred, None, grad_scale)
         self.unet.engine.backward(dpred, tape)
         return loss
+
+
+class GraphedMicroStep:
+    """One micro-step (Philox noise -> noising -> UNet forward -> loss -> UNet backward into the flat gradient buffer)
+    captured as a CUDA graph for a fixed (B, H, W): ~4,700 kernel launches become one graph launch, and the kernels run
+    back to back without the stream-launch gaps.  Inputs live in static device buffers (`load()` copies into them);
+    everything that varies per step (noise counter, sigma / t, grad scale) is read from device memory."""
+
+    def __init__(self, core: "FusedLossCore", B: int, H: int, W: int, n_ctx: int = 77):
+        self.core = core
+        cfg = core.unet.config
+        dev = core.unet.device
+        self.shape = (B, H, W)
+        pooled_dim = cfg["projection_class_embeddings_input_dim"] - 6 * cfg["addition_time_embed_dim"]
+        self.latents = torch.zeros(B, cfg["in_channels"], H, W, device=dev, dtype=torch.float32)
+        self.ctx = torch.zeros(B * n_ctx, cfg["cross_attention_dim"], device=dev, dtype=bf16)
+        self.pooled = torch.zeros(B, pooled_dim, device=dev, dtype=bf16)
+        self.time_ids = torch.zeros(B, 6, device=dev, dtype=torch.float32)
+        self.t_embed = torch.zeros(B, device=dev, dtype=torch.float32)
+        self.sig_or_t = torch.ones(B, device=dev, dtype=torch.float32)
+        self.weight = torch.ones(B, device=dev, dtype=torch.float32)
+        self.grad_scale = torch.ones(1, device=dev, dtype=torch.float32)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.loss: Optional[torch.Tensor] = None
+        self.launches_per_replay = 0
+
+    def _run(self):
+        return self.core.step_no_autograd(grad_scale_dev=self.grad_scale, latents=self.latents, ctx=self.ctx,
+                                          pooled=self.pooled, time_ids=self.time_ids, t_embed=self.t_embed,
+                                          sig_or_t=self.sig_or_t, weight=self.weight, loss_scale=1.0)
+
+    def capture(self):
+        """Call at an optimizer-step boundary: the warm-up passes accumulate into the gradient buffer, which is zeroed
+        again afterwards."""
+        from . import _lib
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):  # lazy one-time setup (function attributes, grow-only workspaces) must not be captured
+                self._run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._run()
+        self.launches_per_replay = _lib.launch_count() - n0
+        self.core.unet.store.grad.zero_()
+        torch.cuda.synchronize()
+        return self
+
+    def load(self, latents, ctx, pooled, time_ids, t_embed, sig_or_t, weight=None, grad_scale: float = 1.0):
+        self.latents.copy_(latents, non_blocking=True)
+        self.ctx.copy_(ctx, non_blocking=True)
+        self.pooled.copy_(pooled, non_blocking=True)
+        self.time_ids.copy_(time_ids, non_blocking=True)
+        self.t_embed.copy_(t_embed, non_blocking=True)
+        self.sig_or_t.copy_(sig_or_t, non_blocking=True)
+        if weight is None:
+            self.weight.fill_(1.0)
+        else:
+            self.weight.copy_(weight, non_blocking=True)
+        self.grad_scale.fill_(float(grad_scale))
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.loss
+
+
+class GraphedOptimizerStep:
+    """grad-norm + clip + fused optimizer update + gradient zeroing as one CUDA graph (the step counter and the clip
+    coefficient are device-side, so replays stay correct).  Host-side bookkeeping that cannot be captured (the
+    reference's per-tensor deferred weight decay) runs after the replay via `optimizer.after_graph_step()`."""
+
+    def __init__(self, optimizer, max_norm: float, grad_scale: float):
+        self.optimizer = optimizer
+        self.max_norm, self.gscale = max_norm, grad_scale
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_replay = 0
+
+    def capture(self):
+        """Captures WITHOUT executing: optimizer state is not advanced by the capture itself."""
+        from . import _lib
+        opt = self.optimizer
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            opt.fused_step(max_norm=self.max_norm, grad_scale=self.gscale, _in_graph=True)
+            opt.zero_grad()
+        self.launches_per_replay = _lib.launch_count() - n0
+        torch.cuda.synchronize()
+        return self
+
+    def replay(self):
+        self.graph.replay()
+        self.optimizer.after_graph_step()
 
 
 def _prep_batch(batch: Dict[str, Any], device) -> Dict[str, torch.Tensor]:
@@ -203,6 +316,13 @@ class _StepBase:
         self.clip_grad_norm = float(getattr(tr, "clip_grad_norm", 1.0))
         self.prediction_type = getattr(tr, "prediction_type", "v_prediction")
         self.world_size = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        # cuda_graph=True: the micro-step (forward + backward) and the optimizer step replay captured CUDA graphs, one
+        # per latent shape.  In that mode the backward pass runs inside compute_loss() (gradients accumulate into
+        # p.grad with the 1/accumulation scale the step protocol announces), and `loss.backward()` is a no-op.
+        self.cuda_graph = bool(kwargs.get("cuda_graph", False))
+        self._micro_graphs: Dict[Any, GraphedMicroStep] = {}
+        self._opt_graph: Optional[GraphedOptimizerStep] = None
+        self._pending_grad_scale = 1.0
 
     def _lr(self):
         try:
@@ -212,6 +332,7 @@ class _StepBase:
 
     # --- accumulate / clip / step protocol (example_method.py:124-148, 191-206; flow_matching_trainer.py:172-189) ---
     def _execute_training_step(self, batch, accumulate: bool = False, is_last_accumulation_step: bool = True):
+        self._pending_grad_scale = 1.0 / self.gradient_accumulation_steps if accumulate else 1.0
         out = self.compute_loss(batch) if not isinstance(self, B200FlowMatchingTrainer) else self.compute_loss(self.model, batch)
         loss = out["loss"]
         if accumulate:
@@ -221,9 +342,35 @@ class _StepBase:
             self.optimizer_step()
         return out["loss"].detach(), out["metrics"]
 
+    def _graphed_loss(self, t: Dict[str, torch.Tensor], t_embed, sig_or_t, weight) -> torch.Tensor:
+        """Replay (capturing on first use) the micro-step graph for this latent shape; returns a loss tensor whose
+        `.backward()` does nothing because the backward pass already ran inside the graph."""
+        B, _, H, W = t["latents"].shape
+        key = (B, H, W, t["ctx"].shape[0] // B)
+        gm = self._micro_graphs.get(key)
+        if gm is None:
+            chk = torch.zeros(1, device=self.unet.device, dtype=torch.float64)
+            ops.sumsq(self.unet.store.grad, chk)
+            if float(chk) != 0.0:
+                raise RuntimeError("cuda_graph capture must happen at an optimizer-step boundary (gradients not zero)")
+            torch.cuda.empty_cache()
+            gm = GraphedMicroStep(self.core, B, H, W, key[3])
+            gm.load(t["latents"], t["ctx"], t["pooled"], t["time_ids"], t_embed, sig_or_t, weight, 1.0)
+            gm.capture()
+            self._micro_graphs[key] = gm
+        gm.load(t["latents"], t["ctx"], t["pooled"], t["time_ids"], t_embed, sig_or_t, weight, self._pending_grad_scale)
+        loss = gm.replay()
+        self.core.last = {"numel": t["latents"].numel()}
+        return _PrecomputedBackward.apply(loss.reshape(()), self.core._anchor)
+
     def optimizer_step(self):
         if self.world_size > 1:
             allreduce_gradients(self.unet)
+        if self.cuda_graph and hasattr(self.optimizer, "fused_step"):
+            if self._opt_graph is None:
+                self._opt_graph = GraphedOptimizerStep(self.optimizer, self.clip_grad_norm, 1.0 / self.world_size).capture()
+            self._opt_graph.replay()
+            return
         if hasattr(self.optimizer, "fused_step"):
             self.optimizer.fused_step(max_norm=self.clip_grad_norm, grad_scale=1.0 / self.world_size)
         else:  # a reference optimizer reading p.grad (adamw_bfloat16/__init__.py:92-119)
@@ -282,10 +429,13 @@ class B200DDPMTrainer(_StepBase):
             snr = (self.noise_scheduler.sigma_data / sig) ** 2
             weight = torch.minimum(snr, torch.ones_like(snr) * float(self.min_snr_gamma)).float().to(dev)
         tw = _tag_weight_mean(batch)
-        loss = self.core.loss_fn(latents=t["latents"], ctx=t["ctx"], pooled=t["pooled"], time_ids=t["time_ids"],
-                                 t_embed=timesteps.float().to(dev), sig_or_t=sig.to(dev), weight=weight,
-                                 loss_scale=1.0 if tw is None else tw,
-                                 noise=None if noise is None else noise.to(dev).to(bf16).float().reshape(-1).contiguous())
+        if self.cuda_graph and noise is None and tw is None:
+            loss = self._graphed_loss(t, timesteps.float(), sig, weight)
+        else:
+            loss = self.core.loss_fn(latents=t["latents"], ctx=t["ctx"], pooled=t["pooled"], time_ids=t["time_ids"],
+                                     t_embed=timesteps.float().to(dev), sig_or_t=sig.to(dev), weight=weight,
+                                     loss_scale=1.0 if tw is None else tw,
+                                     noise=None if noise is None else noise.to(dev).to(bf16).float().reshape(-1).contiguous())
         st = self.core.stats.tolist()  # one D2H for all metrics (the reference does 5 .item() syncs)
         n = self.core.last["numel"]
         metrics = {
@@ -324,9 +474,12 @@ class B200FlowMatchingTrainer(_StepBase):
         if "tag_weights" in batch:  # flow_matching_trainer.py:326-328
             loss_scale = float(batch["tag_weights"].to(bf16).float().mean())
         tf = t.float().to(dev)
-        loss = self.core.loss_fn(latents=tb["latents"], ctx=tb["ctx"], pooled=tb["pooled"], time_ids=tb["time_ids"],
-                                 t_embed=tf, sig_or_t=tf, weight=weight, loss_scale=loss_scale,
-                                 noise=None if x0 is None else x0.to(dev).to(bf16).float().reshape(-1).contiguous())
+        if self.cuda_graph and x0 is None and loss_scale == 1.0:
+            loss = self._graphed_loss(tb, tf, tf, weight)
+        else:
+            loss = self.core.loss_fn(latents=tb["latents"], ctx=tb["ctx"], pooled=tb["pooled"], time_ids=tb["time_ids"],
+                                     t_embed=tf, sig_or_t=tf, weight=weight, loss_scale=loss_scale,
+                                     noise=None if x0 is None else x0.to(dev).to(bf16).float().reshape(-1).contiguous())
         st = self.core.stats.tolist()
         metrics = {
             "loss": float(loss.detach()),
@@ -369,23 +522,29 @@ class B200AdamW:
         self.master = st.flat.float() if master_weights else None
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.steps = 0
+        self.step_ctr = torch.zeros(2, device=dev, dtype=torch.int64)  # [1] = step, advanced on the device (graph-safe)
 
     def sync_master(self):
         if self.master is not None:
             self.master.copy_(self.unet.store.flat.float())
 
-    def fused_step(self, max_norm: float = 0.0, grad_scale: float = 1.0):
+    def fused_step(self, max_norm: float = 0.0, grad_scale: float = 1.0, _in_graph: bool = False):
         st = self.unet.store
         g = self.param_groups[0]
-        self.steps += 1
         gn = None
         if max_norm and max_norm > 0:
             self.gnorm_sq.zero_()
             ops.sumsq(st.grad, self.gnorm_sq)
             gn = self.gnorm_sq
+        ops.philox_advance(self.step_ctr, 1)
         ops.adamw(st.flat, self.master, st.grad, self.m, self.v, lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1],
-                  eps=g["eps"], weight_decay=g["weight_decay"], step=self.steps, gnorm_sq=gn, max_norm=max_norm or 0.0,
-                  grad_scale=grad_scale)
+                  eps=g["eps"], weight_decay=g["weight_decay"], step=0, gnorm_sq=gn, max_norm=max_norm or 0.0,
+                  grad_scale=grad_scale, dev_step=self.step_ctr[1:])
+        if not _in_graph:
+            self.after_graph_step()
+
+    def after_graph_step(self):
+        self.steps += 1
 
     def step(self):
         self.fused_step()
@@ -431,22 +590,38 @@ class B200AdamWBF16:
         g = torch.Generator().manual_seed(seed)
         # each tensor starts its decay accumulator at a random phase (:110-116)
         self.accumulated_decay = {name: float(torch.rand([], generator=g)) * self.decay_threshold for name, _ in st.specs}
+        self._min_headroom = 0.0  # steps can skip the per-tensor scan while no accumulator can reach the threshold
 
-    def fused_step(self, max_norm: float = 0.0, grad_scale: float = 1.0, rng_mode: int = 0, test_rand16=None):
+    def fused_step(self, max_norm: float = 0.0, grad_scale: float = 1.0, rng_mode: int = 0, test_rand16=None,
+                   _in_graph: bool = False):
         st = self.unet.store
         g = self.param_groups[0]
-        self.steps += 1
         gn = None
         if max_norm and max_norm > 0:
             self.gnorm_sq.zero_()
             ops.sumsq(st.grad, self.gnorm_sq)
             gn = self.gnorm_sq
+        ops.philox_advance(self.seed_offset, 1)  # seed_offset[1] = optimizer step, kept on the device (graph-safe)
         ops.adamw_bf16(st.flat, st.grad, self.exp_avg, self.exp_avg_sq, self.shift, lr=g["lr"], beta1=g["betas"][0],
-                       beta2=g["betas"][1], eps=g["eps"], step=self.steps, gnorm_sq=gn, max_norm=max_norm or 0.0,
+                       beta2=g["betas"][1], eps=g["eps"], step=0, gnorm_sq=gn, max_norm=max_norm or 0.0,
                        grad_scale=grad_scale, seed_offset=self.seed_offset, as_written=self.as_written,
                        rng_mode=rng_mode, test_rand16=test_rand16)
+        if not _in_graph:
+            self.after_graph_step()
+
+    def after_graph_step(self):
+        """Host-side part of a step: the per-tensor deferred weight decay (adamw_bfloat16/__init__.py:118-128, 191-192)."""
+        st = self.unet.store
+        g = self.param_groups[0]
+        self.steps += 1
         inc = g["weight_decay"] * g["lr"]
         if inc > 0:
+            self._min_headroom -= inc
+            if self._min_headroom > 0:  # nothing can trip yet: defer the per-tensor adds (same trip step up to host float rounding)
+                self._lazy_inc = getattr(self, "_lazy_inc", 0.0) + inc
+                return
+            inc += getattr(self, "_lazy_inc", 0.0)
+            self._lazy_inc = 0.0
             for name, _ in st.specs:
                 acc = self.accumulated_decay[name] + inc
                 if acc > self.decay_threshold:
@@ -456,6 +631,7 @@ class B200AdamWBF16:
                     ops.axpy_bf16(self.shift[off:off + numel], st.flat[off:off + numel], alpha)
                     acc = 0.0
                 self.accumulated_decay[name] = acc
+            self._min_headroom = self.decay_threshold - max(self.accumulated_decay.values())
 
     def step(self, zero_grad: bool = False):
         self.fused_step()
@@ -472,7 +648,7 @@ class B200AdamWBF16:
             off, numel = st.offsets[name], st._numel[name]
             state[name] = {"step": float(self.steps), "exp_avg": self.exp_avg[off:off + numel],
                            "exp_avg_sq": self.exp_avg_sq[off:off + numel], "shift": self.shift[off:off + numel],
-                           "accumulated_decay": self.accumulated_decay[name]}
+                           "accumulated_decay": self.accumulated_decay[name] + getattr(self, "_lazy_inc", 0.0)}
         return {"state": state, "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
 
 
