@@ -248,8 +248,8 @@ int b2_adamw(void* p, float* master /* fp32 master weights or NULL */, const voi
  *   rng_mode: 0 Philox(seed_offset[0], step); 1/2/3 deterministic patterns for parity tests (3: int32 [4,n] buffer).
  *   step <= 0: the step is read from seed_offset[1] on the device (CUDA-graph replays; advance with b2_philox_advance).
  * b2_axpy_bf16: y <- bf16(y + alpha x) — the deferred weight decay `shift.add_(p, alpha=-decay)` (:191-192). */
-int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shift, int64_t n, float lr, float beta1, float beta2,
-                  float eps, int step, const double* gnorm_sq, float max_norm, float grad_scale,
+int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shift, int64_t n, double lr, double beta1, double beta2,
+                  double eps, int step, const double* gnorm_sq, float max_norm, float grad_scale,
                   const uint64_t* seed_offset, int as_written, int rng_mode, const int32_t* test_rand16, void* stream);
 int b2_axpy_bf16(void* y, const void* x, int64_t n, float alpha, void* stream);
 

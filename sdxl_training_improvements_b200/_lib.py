@@ -87,7 +87,7 @@ SIGNATURES = {
     "b2_abs_sq_sums": [c_p, i32, i64, i32, i32, c_p, c_p],
     "b2_scale_bf16": [c_p, i64, c_p, f32, c_p],
     "b2_sumsq": [c_p, i64, c_p, c_p],
-    "b2_adamw_bf16": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, i32, c_p, f32, f32, c_p, i32, i32, c_p, c_p],
+    "b2_adamw_bf16": [c_p, c_p, c_p, c_p, c_p, i64, f64, f64, f64, f64, i32, c_p, f32, f32, c_p, i32, i32, c_p, c_p],
     "b2_axpy_bf16": [c_p, c_p, i64, f32, c_p],
     "b2_adamw": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, c_p, f32, f32, c_p, c_p],
 }

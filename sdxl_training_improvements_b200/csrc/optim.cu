@@ -37,8 +37,9 @@ __device__ __forceinline__ float sr_bf16(float x, uint32_t r16) {
 
 struct AdamBF16P {
   float b1, b2, eps;
+  float omb1, omb2;  // (float)(1.0 - beta) evaluated in double like the Python scalars `1 - beta1`, `1 - beta2`
   float step_size;  // -lr * sqrt(1 - beta2^step)   (host step)
-  float lr;         // device step (seed_offset[1]): step_size is recomputed in the kernel
+  double lr, b2d;   // device step (seed_offset[1]): step_size is recomputed in the kernel
   int dev_step;
   float max_norm, grad_scale;
   int as_written;
@@ -52,13 +53,13 @@ __device__ __forceinline__ void adam_bf16_elem(float& p, float g, float& m, floa
   const float gi = clip == 1.f ? g : rn_bf16(__fmul_rn(g, clip));
   // exp_avg.mul_(beta1); add_stochastic_(exp_avg, grad, alpha=1-beta1)
   const float m1 = rn_bf16(__fmul_rn(m, a.b1));
-  const float one_b1 = 1.f - a.b1;
+  const float one_b1 = a.omb1;
   // torch's add-with-alpha is a fused multiply-add (vec::fmadd on CPU, nvcc contraction on CUDA)
   const float mr = a.as_written ? fmaf(one_b1, m1, gi) : fmaf(one_b1, gi, m1);
   m = sr_bf16(mr, r01 & 0xffffu);
   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
   const float v1 = rn_bf16(__fmul_rn(v, a.b2));
-  v = rn_bf16(__fadd_rn(v1, __fmul_rn(__fmul_rn(1.f - a.b2, gi), gi)));
+  v = rn_bf16(__fadd_rn(v1, __fmul_rn(__fmul_rn(a.omb2, gi), gi)));
   // denom = exp_avg_sq.sqrt().add_(eps)
   const float den = rn_bf16(__fadd_rn(rn_bf16(__fsqrt_rn(v)), a.eps));
   // addcdiv_stochastic_(shift, exp_avg, denom, value=-lr*denom_correction)
@@ -84,7 +85,7 @@ adamw_bf16_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __rest
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   if (a.dev_step) {  // CUDA-graph replays advance seed_offset[1] on the device
     step = seed_offset[1];
-    a.step_size = (float)(-(double)a.lr * sqrt(1.0 - pow((double)a.b2, (double)step)));
+    a.step_size = (float)(-a.lr * sqrt(1.0 - pow(a.b2d, (double)step)));
   }
   const long long nv = n >> 3;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += (long long)gridDim.x * blockDim.x) {
@@ -155,8 +156,8 @@ __global__ void axpy_bf16_kernel(bf16* __restrict__ y, const bf16* __restrict__ 
 
 using namespace b2;
 
-extern "C" int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shift, int64_t n, float lr, float beta1,
-                             float beta2, float eps, int step, const double* gnorm_sq, float max_norm, float grad_scale,
+extern "C" int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shift, int64_t n, double lr, double beta1,
+                             double beta2, double eps, int step, const double* gnorm_sq, float max_norm, float grad_scale,
                              const uint64_t* seed_offset, int as_written, int rng_mode, const int32_t* test_rand16,
                              void* stream) {
   B2_REQUIRE(p && g && m && v && shift && n > 0 && (step >= 1 || seed_offset), "b2_adamw_bf16: bad args");
@@ -165,10 +166,13 @@ extern "C" int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shi
              "b2_adamw_bf16: buffers must be 16-byte aligned");
   B2_REQUIRE(rng_mode >= 0 && rng_mode <= 3 && (rng_mode != 3 || test_rand16), "b2_adamw_bf16: bad rng_mode");
   AdamBF16P a;
-  a.b1 = beta1; a.b2 = beta2; a.eps = eps;
+  // hyper-parameters arrive as doubles (Python floats) and are narrowed exactly where torch narrows them
+  a.b1 = (float)beta1; a.b2 = (float)beta2; a.eps = (float)eps;
+  a.omb1 = (float)(1.0 - beta1);
+  a.omb2 = (float)(1.0 - beta2);
   // python: value = -lr * (1 - beta2**step) ** 0.5  (double), passed to a float kernel argument
-  a.step_size = (float)(-(double)lr * sqrt(1.0 - pow((double)beta2, (double)step)));
-  a.lr = lr; a.dev_step = step >= 1 ? 0 : 1;
+  a.step_size = (float)(-lr * sqrt(1.0 - pow(beta2, (double)step)));
+  a.lr = lr; a.b2d = beta2; a.dev_step = step >= 1 ? 0 : 1;
   a.max_norm = max_norm; a.grad_scale = grad_scale;
   a.as_written = as_written; a.rng_mode = rng_mode;
   long long blocks = ((n >> 3) + 255) / 256;

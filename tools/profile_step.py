@@ -13,7 +13,8 @@ method = sys.argv[1] if len(sys.argv) > 1 else "ddpm"
 warm = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 unet = B200UNet(device="cuda:0")
 bench._init_weights_(unet, 1234)
-opt = B200AdamW(unet, lr=4e-7)
+from sdxl_training_improvements_b200.trainer import B200AdamWBF16
+opt = B200AdamWBF16(unet, lr=4e-7, weight_decay=1e-2)
 tr = create_trainer(bench._config_ns(method), unet, opt, device="cuda:0", seed=1)
 batch = bench._synthetic_batch(4, 128, 128, 77)
 for _ in range(warm):
