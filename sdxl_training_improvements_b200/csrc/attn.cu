@@ -15,6 +15,7 @@
 // LSE is kept in the log2 domain: L2[i] = m_i + log2(sum_j 2^(s_ij*c - m_i)), c = scale*log2(e); P_ij = 2^(s_ij*c - L2[i]).
 // LSE / D are laid out [B, H, n_pad] with n_pad = ceil(n_q/128)*128; pad rows hold L2 = +inf (P = 0) and D = 0.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tc.cuh"
 
@@ -210,6 +211,222 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward, v2: two query tiles per CTA, ping-pong between the tensor pipe and two softmax warp groups
+//   The v1 kernel alternates "MMA, then exp2" inside one CTA and leans on a second resident CTA for overlap; its
+//   tensor pipe sat idle for most of every key block (ncu: 19 % tensor-pipe active, 80 us per n = 1024 layer call).
+//   Here one CTA owns the whole SM: 256 queries (tiles t = 0, 1), TMEM = S0 | S1 | O0 | O1 (384 columns), the bf16
+//   probabilities P_t are written IN PLACE over the first 64 columns of S_t, and the single MMA thread interleaves
+//       PV_0(j), S_0(j+1), PV_1(j), S_1(j+1)
+//   so that while softmax group 0 chews on S_0 the tensor pipe serves tile 1 and vice versa.  The exp2 throughput
+//   of the SFUs (16 / clk / SM) is the bound for head dim 64: 32768 exp2 per 128-key block pair = 2048 cycles against
+//   1024 cycles of MMA.
+//   Ordering argument for the in-place P / O rescale: tcgen05.commit arrives only after ALL previously issued MMAs of
+//   the issuing thread completed, and S_t(j+1) is issued after PV_t(j); hence "S_t(j+1) ready" implies PV_t(j) has
+//   finished reading P_t(j) and accumulating into O_t, so group t may overwrite S_t / rescale O_t.  PV_t(j+1) is issued
+//   only after group t signalled P_t(j+1).
+// warps: 0 = TMA, 1 = MMA issuer + TMEM allocator, 2..5 = softmax group 0, 6..9 = softmax group 1.
+// ---------------------------------------------------------------------------------------------
+constexpr int F2_THREADS = 320;
+constexpr int F2_STAGES = 3;
+constexpr int F2_SMEM = 2 * AT_TILE128 + F2_STAGES * 2 * AT_TILE128 + 1024;
+constexpr int F2_TMEM_COLS = 512;
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnP p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q, bar_full[F2_STAGES], bar_empty[F2_STAGES], bar_s[2], bar_p[2], bar_o;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sKV = smem_base + 2 * AT_TILE128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int nkb = (p.n_k + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(smem_u32(&bar_q), 1);
+#pragma unroll
+    for (int s = 0; s < F2_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&bar_s[t]), 1);
+      mbar_init(smem_u32(&bar_p[t]), 128);
+    }
+    mbar_init(smem_u32(&bar_o), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), F2_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(&bar_q), 2 * AT_TILE128);
+      tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
+      tma_load_4d(sQ + AT_TILE128, &tmQ, smem_u32(&bar_q), 0, q0 + 128, h, b);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&bar_full[s]);
+        mbar_expect_tx(full, 2 * AT_TILE128);
+        tma_load_4d(sKV + s * 2 * AT_TILE128, &tmK, full, 0, j * 128, h, b);
+        tma_load_4d(sKV + s * 2 * AT_TILE128 + AT_TILE128, &tmV, full, 0, j * 128, h, b);
+        if (++s == F2_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idS = umma_idesc(128, 128, 0, 0);
+      constexpr uint32_t idO = umma_idesc(128, AT_D, 0, 1);
+      const uint32_t tS0 = tmem_base, tS1 = tmem_base + 128, tO0 = tmem_base + 256, tO1 = tmem_base + 320;
+      auto issue_S = [&](uint32_t tS, uint32_t sQt, uint32_t sK) {
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_bf16(tS, umma_desc(sQt + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
+      };
+      auto issue_PV = [&](uint32_t tO, uint32_t tP, uint32_t sV, bool first) {
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k)
+          umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (!first) || k != 0);
+      };
+      mbar_wait(smem_u32(&bar_q), 0);
+      mbar_wait(smem_u32(&bar_full[0]), 0);
+      tc_fence_after();
+      issue_S(tS0, sQ, sKV);
+      umma_commit(smem_u32(&bar_s[0]));
+      issue_S(tS1, sQ + AT_TILE128, sKV);
+      umma_commit(smem_u32(&bar_s[1]));
+      int s = 0;           // stage of block j
+      uint32_t ph = 0;     // its phase
+      for (int j = 0; j < nkb; ++j) {
+        int sn = s + 1;    // stage / phase of block j + 1
+        uint32_t phn = ph;
+        if (sn == F2_STAGES) { sn = 0; phn ^= 1u; }
+        const uint32_t sV = sKV + s * 2 * AT_TILE128 + AT_TILE128;
+        const uint32_t sKn = sKV + sn * 2 * AT_TILE128;
+        const bool more = j + 1 < nkb;
+        // ---- tile 0
+        mbar_wait(smem_u32(&bar_p[0]), j & 1);
+        tc_fence_after();
+        issue_PV(tO0, tS0, sV, j == 0);
+        if (more) {
+          mbar_wait(smem_u32(&bar_full[sn]), phn);
+          tc_fence_after();
+          issue_S(tS0, sQ, sKn);
+          umma_commit(smem_u32(&bar_s[0]));
+        }
+        // ---- tile 1
+        mbar_wait(smem_u32(&bar_p[1]), j & 1);
+        tc_fence_after();
+        issue_PV(tO1, tS1, sV, j == 0);
+        umma_commit(smem_u32(&bar_empty[s]));  // K_j (both S MMAs) and V_j (both PV MMAs) consumed
+        if (more) {
+          issue_S(tS1, sQ + AT_TILE128, sKn);
+          umma_commit(smem_u32(&bar_s[1]));
+        }
+        s = sn;
+        ph = phn;
+      }
+      umma_commit(smem_u32(&bar_o));
+    }
+  } else {
+    const int t = (warp - 2) >> 2;             // softmax group == query tile
+    const int qd = warp & 3;                   // TMEM lane quarter this warp may touch
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = uint32_t(qd * 32) << 16;
+    const uint32_t tS = tmem_base + t * 128 + lane_off;   // P_t aliases the first 64 columns
+    const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
+    const uint32_t bs = smem_u32(&bar_s[t]), bp = smem_u32(&bar_p[t]);
+    float m_used = 0.f, l = 0.f;
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(bs, j & 1);
+      tc_fence_after();
+      const int valid = min(128, p.n_k - j * 128);
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tS + cc * 32, r);
+        if (valid >= 128) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cc * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      mx *= p.c;
+      float factor = 1.f;
+      if (j == 0) {
+        m_used = mx;
+      } else if (mx > m_used + 8.f) {  // lazy rescale: a stale max is fine while 2^(s - m) <= 2^8
+        factor = fast_exp2(m_used - mx);
+        m_used = mx;
+      }
+      if (j > 0 && __any_sync(AT_FULL, factor != 1.f)) {
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(tO + cc * 32, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
+          tmem_st32(tO + cc * 32, r);
+        }
+        l *= factor;
+      }
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32], pk[16];
+        tmem_ld32(tS + cc * 32, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.c, -m_used));
+          float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.c, -m_used));
+          if (valid < 128) {
+            if (cc * 32 + 2 * i >= valid) p0 = 0.f;
+            if (cc * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+          }
+          l += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(tS + cc * 16, pk);   // in place: columns [16cc, 16cc+16) were consumed at iteration <= cc
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bp);
+    }
+    mbar_wait(smem_u32(&bar_o), 0);
+    tc_fence_after();
+    uint32_t r0[32], r1[32];
+    tmem_ld32_nowait(tO, r0);
+    tmem_ld32_nowait(tO + 32, r1);
+    tmem_ld_wait();
+    const int gq = q0 + t * 128 + row;
+    const float inv = 1.f / l;
+    if (gq < p.n_q) store_row64(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D, r0, r1, inv);
+    if (gq < p.n_pad) p.LSE[((long long)b * p.H + h) * p.n_pad + gq] = gq < p.n_q ? m_used + log2f(l) : INFINITY;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, F2_TMEM_COLS);
   }
 }
 
@@ -566,6 +783,17 @@ extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
   p.scale = a->scale; p.c = a->scale * 1.4426950408889634f;
   p.LSE = a->LSE; p.D = nullptr;
   p.out0 = (bf16*)a->O; p.ld0 = a->ldo; p.bs0 = a->o_bs;
+  static const bool legacy = getenv("B2_ATTN_LEGACY") != nullptr;
+  if (!legacy) {
+    static bool configured2 = false;
+    if (!configured2) {
+      if ((rc = set_smem(attn_fwd2_kernel, F2_SMEM, "b2_attn_fwd"))) return rc;
+      configured2 = true;
+    }
+    dim3 grid2((a->n_q + 255) / 256, a->H, a->B);
+    attn_fwd2_kernel<<<grid2, F2_THREADS, F2_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    return check_launch("b2_attn_fwd");
+  }
   dim3 grid((a->n_q + 127) / 128, a->H, a->B);
   attn_fwd_kernel<<<grid, AT_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
   return check_launch("b2_attn_fwd");
