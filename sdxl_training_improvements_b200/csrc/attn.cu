@@ -215,37 +215,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward, v2: two query tiles per CTA, ping-pong between the tensor pipe and two softmax warp groups
-//   The v1 kernel alternates "MMA, then exp2" inside one CTA and leans on a second resident CTA for overlap; its
-//   tensor pipe sat idle for most of every key block (ncu: 19 % tensor-pipe active, 80 us per n = 1024 layer call).
-//   Here one CTA owns the whole SM: 256 queries (tiles t = 0, 1), TMEM = S0 | S1 | O0 | O1 (384 columns), the bf16
-//   probabilities P_t are written IN PLACE over the first 64 columns of S_t, and the single MMA thread interleaves
-//       PV_0(j), S_0(j+1), PV_1(j), S_1(j+1)
-//   so that while softmax group 0 chews on S_0 the tensor pipe serves tile 1 and vice versa.  The exp2 throughput
-//   of the SFUs (16 / clk / SM) is the bound for head dim 64: 32768 exp2 per 128-key block pair = 2048 cycles against
-//   1024 cycles of MMA.
-//   Ordering argument for the in-place P / O rescale: tcgen05.commit arrives only after ALL previously issued MMAs of
-//   the issuing thread completed, and S_t(j+1) is issued after PV_t(j); hence "S_t(j+1) ready" implies PV_t(j) has
-//   finished reading P_t(j) and accumulating into O_t, so group t may overwrite S_t / rescale O_t.  PV_t(j+1) is issued
-//   only after group t signalled P_t(j+1).
-// warps: 0 = TMA, 1 = MMA issuer + TMEM allocator, 2..5 = softmax group 0, 6..9 = softmax group 1.
+// v3 kernels: one CTA per SM, a RING of three S (or S/dP) accumulators in TMEM, two softmax warp groups that take
+// alternate key (query) blocks.
+//   What the measurements said (profiles/r1_attention_notes.md): the v1 kernels (MMA -> exp2 -> MMA inside a CTA, two
+//   CTAs per SM) and a first ping-pong rewrite both sat at ~2x the exp2 bound; the time went to the HAND-OFF, not to the
+//   math: "P written -> mbarrier -> MMA thread -> PV + next S MMA -> commit -> mbarrier -> softmax warps" costs about
+//   as much as the exp2 work of a whole block, and every block paid it.  With three S buffers the MMA thread runs up to
+//   three blocks ahead, so a group that finishes block j finds S(j+2) already waiting; the hand-off only gates how far
+//   ahead the tensor pipe may run.
+//   Softmax loops hold a whole block row in registers (ONE tcgen05.ld round trip per block), reduce with four
+//   independent chains, and write the bf16 result in place over the columns they have just consumed.
+// warps (320 threads): 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = group 0, 6..9 = group 1.
 // ---------------------------------------------------------------------------------------------
-constexpr int F2_THREADS = 320;
-constexpr int F2_STAGES = 3;
-constexpr int F2_SMEM = 2 * AT_TILE128 + F2_STAGES * 2 * AT_TILE128 + 1024;
-constexpr int F2_TMEM_COLS = 512;
+constexpr int A3_THREADS = 320;
+constexpr int A3_TMEM_COLS = 512;
 
-__global__ void __launch_bounds__(F2_THREADS, 1)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__device__ __forceinline__ void a3_group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void store_row32(bf16* dst, const float* f) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) st8(dst + g * 8, pack8(f + g * 8));
+}
+
+// forward: CTA = 128 queries x key blocks of 128.   TMEM: S ring [0,384) (P in place, 64 columns each), O_0 [384,448),
+// O_1 [448,512): each group keeps its own online-softmax state (m, l, O) over its alternate blocks; the two partial
+// results are merged at the end like a split-KV decode (exact: O = (w0 O_0 + w1 O_1) / (w0 l_0 + w1 l_1)).
+constexpr int F3_STAGES = 5;
+constexpr int F3_SMEM = AT_TILE128 + F3_STAGES * 2 * AT_TILE128 + 1024;
+
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnP p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_full[F2_STAGES], bar_empty[F2_STAGES], bar_s[2], bar_p[2], bar_o;
+  __shared__ __align__(8) uint64_t bar_q, bar_full[F3_STAGES], bar_empty[F3_STAGES], bar_s[3], bar_p[3], bar_pv[2], bar_o;
   __shared__ uint32_t tmem_slot;
+  __shared__ float2 ml[2][128];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
-  const uint32_t sKV = smem_base + 2 * AT_TILE128;
+  const uint32_t sKV = smem_base + AT_TILE128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nkb = (p.n_k + 127) / 128;
 
   if (threadIdx.x == 0) {
@@ -254,19 +263,21 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_prefetch_desc(&tmV);
     mbar_init(smem_u32(&bar_q), 1);
 #pragma unroll
-    for (int s = 0; s < F2_STAGES; ++s) {
+    for (int s = 0; s < F3_STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(smem_u32(&bar_s[t]), 1);
-      mbar_init(smem_u32(&bar_p[t]), 128);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(smem_u32(&bar_s[i]), 1);
+      mbar_init(smem_u32(&bar_p[i]), 128);
     }
+    mbar_init(smem_u32(&bar_pv[0]), 1);
+    mbar_init(smem_u32(&bar_pv[1]), 1);
     mbar_init(smem_u32(&bar_o), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), F2_TMEM_COLS);
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -274,9 +285,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(smem_u32(&bar_q), 2 * AT_TILE128);
+      mbar_expect_tx(smem_u32(&bar_q), AT_TILE128);
       tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
-      tma_load_4d(sQ + AT_TILE128, &tmQ, smem_u32(&bar_q), 0, q0 + 128, h, b);
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nkb; ++j) {
@@ -285,86 +295,79 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_expect_tx(full, 2 * AT_TILE128);
         tma_load_4d(sKV + s * 2 * AT_TILE128, &tmK, full, 0, j * 128, h, b);
         tma_load_4d(sKV + s * 2 * AT_TILE128 + AT_TILE128, &tmV, full, 0, j * 128, h, b);
-        if (++s == F2_STAGES) { s = 0; ph ^= 1u; }
+        if (++s == F3_STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idS = umma_idesc(128, 128, 0, 0);
       constexpr uint32_t idO = umma_idesc(128, AT_D, 0, 1);
-      const uint32_t tS0 = tmem_base, tS1 = tmem_base + 128, tO0 = tmem_base + 256, tO1 = tmem_base + 320;
-      auto issue_S = [&](uint32_t tS, uint32_t sQt, uint32_t sK) {
+      auto issue_S = [&](int buf, int stage) {
+        const uint32_t tS = tmem_base + buf * 128, sK = sKV + stage * 2 * AT_TILE128;
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sQt + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
-      };
-      auto issue_PV = [&](uint32_t tO, uint32_t tP, uint32_t sV, bool first) {
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k)
-          umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (!first) || k != 0);
+          umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
       };
       mbar_wait(smem_u32(&bar_q), 0);
-      mbar_wait(smem_u32(&bar_full[0]), 0);
-      tc_fence_after();
-      issue_S(tS0, sQ, sKV);
-      umma_commit(smem_u32(&bar_s[0]));
-      issue_S(tS1, sQ + AT_TILE128, sKV);
-      umma_commit(smem_u32(&bar_s[1]));
-      int s = 0;           // stage of block j
-      uint32_t ph = 0;     // its phase
+      // run-ahead: S(0), S(1), S(2)
+      int ls = 0;          // stage / phase of the next block whose S gets issued
+      uint32_t lph = 0;
+      int issued = 0;
+      for (; issued < 3 && issued < nkb; ++issued) {
+        mbar_wait(smem_u32(&bar_full[ls]), lph);
+        tc_fence_after();
+        issue_S(issued, ls);
+        umma_commit(smem_u32(&bar_s[issued]));
+        if (++ls == F3_STAGES) { ls = 0; lph ^= 1u; }
+      }
+      int buf = 0, cs = 0;  // ring slot and KV stage of block j
+      uint32_t ppar = 0;    // parity of bar_p[buf] for block j (flips when buf wraps)
       for (int j = 0; j < nkb; ++j) {
-        int sn = s + 1;    // stage / phase of block j + 1
-        uint32_t phn = ph;
-        if (sn == F2_STAGES) { sn = 0; phn ^= 1u; }
-        const uint32_t sV = sKV + s * 2 * AT_TILE128 + AT_TILE128;
-        const uint32_t sKn = sKV + sn * 2 * AT_TILE128;
-        const bool more = j + 1 < nkb;
-        // ---- tile 0
-        mbar_wait(smem_u32(&bar_p[0]), j & 1);
+        const int g = j & 1;
+        mbar_wait(smem_u32(&bar_p[buf]), ppar);
         tc_fence_after();
-        issue_PV(tO0, tS0, sV, j == 0);
-        if (more) {
-          mbar_wait(smem_u32(&bar_full[sn]), phn);
+        const uint32_t tP = tmem_base + buf * 128, tO = tmem_base + 384 + g * 64;
+        const uint32_t sV = sKV + cs * 2 * AT_TILE128 + AT_TILE128;
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k)
+          umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (j >= 2) || k != 0);
+        umma_commit(smem_u32(&bar_pv[g]));
+        umma_commit(smem_u32(&bar_empty[cs]));
+        if (issued < nkb) {  // refill this ring slot with S(j + 3)
+          mbar_wait(smem_u32(&bar_full[ls]), lph);
           tc_fence_after();
-          issue_S(tS0, sQ, sKn);
-          umma_commit(smem_u32(&bar_s[0]));
+          issue_S(buf, ls);
+          umma_commit(smem_u32(&bar_s[buf]));
+          if (++ls == F3_STAGES) { ls = 0; lph ^= 1u; }
+          ++issued;
         }
-        // ---- tile 1
-        mbar_wait(smem_u32(&bar_p[1]), j & 1);
-        tc_fence_after();
-        issue_PV(tO1, tS1, sV, j == 0);
-        umma_commit(smem_u32(&bar_empty[s]));  // K_j (both S MMAs) and V_j (both PV MMAs) consumed
-        if (more) {
-          issue_S(tS1, sQ + AT_TILE128, sKn);
-          umma_commit(smem_u32(&bar_s[1]));
-        }
-        s = sn;
-        ph = phn;
+        if (++cs == F3_STAGES) cs = 0;
+        if (++buf == 3) { buf = 0; ppar ^= 1u; }
       }
       umma_commit(smem_u32(&bar_o));
     }
   } else {
-    const int t = (warp - 2) >> 2;             // softmax group == query tile
-    const int qd = warp & 3;                   // TMEM lane quarter this warp may touch
+    const int g = (warp - 2) >> 2;
+    const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    const uint32_t tS = tmem_base + t * 128 + lane_off;   // P_t aliases the first 64 columns
-    const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
-    const uint32_t bs = smem_u32(&bar_s[t]), bp = smem_u32(&bar_p[t]);
-    float m_used = 0.f, l = 0.f;
-    for (int j = 0; j < nkb; ++j) {
-      mbar_wait(bs, j & 1);
+    const uint32_t tOg = tmem_base + 384 + g * 64 + lane_off;
+    float m_used = -INFINITY, l = 0.f;
+    int buf = g;          // ring slot of block j = g, g + 2, ...
+    uint32_t spar = 0;    // parity of bar_s[buf] for that block
+    int kown = 0;         // own blocks done
+    for (int j = g; j < nkb; j += 2, ++kown) {
+      mbar_wait(smem_u32(&bar_s[buf]), spar);
       tc_fence_after();
+      const uint32_t tS = tmem_base + buf * 128 + lane_off;
       const int valid = min(128, p.n_k - j * 128);
-      // The whole 128-key row lives in registers: ONE TMEM round trip per block (the two-pass version paid eight), and
-      // the max / sum reductions run as four independent chains (two warps per scheduler cannot hide a 128-long one).
       uint32_t r[128];
       tmem_ld32_nowait(tS, r);
       tmem_ld32_nowait(tS + 32, r + 32);
       tmem_ld32_nowait(tS + 64, r + 64);
       tmem_ld32_nowait(tS + 96, r + 96);
       tmem_ld_wait();
-      if (valid < 128) {  // ragged last key block: -inf logits give P = 0 without per-element predicates later
+      if (valid < 128) {  // ragged last key block: -inf logits -> P = 0
 #pragma unroll
         for (int i = 0; i < 128; ++i)
           if (i >= valid) r[i] = 0xff800000u;
@@ -379,20 +382,23 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.c;
       float factor = 1.f;
-      if (j == 0) {
+      if (kown == 0) {
         m_used = mx;
       } else if (mx > m_used + 8.f) {  // lazy rescale: a stale max is fine while 2^(s - m) <= 2^8
         factor = fast_exp2(m_used - mx);
         m_used = mx;
       }
-      if (j > 0 && __any_sync(AT_FULL, factor != 1.f)) {
+      if (kown > 0 && __any_sync(AT_FULL, factor != 1.f)) {
+        // O_g is being accumulated by this group's previous PV MMA: wait for it before touching the accumulator
+        mbar_wait(smem_u32(&bar_pv[g]), (uint32_t)(kown - 1) & 1u);
+        tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t o[32];
-          tmem_ld32(tO + cc * 32, o);
+          tmem_ld32(tOg + cc * 32, o);
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-          tmem_st32(tO + cc * 32, o);
+          tmem_st32(tOg + cc * 32, o);
         }
         l *= factor;
       }
@@ -410,30 +416,45 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           pk[i] = pack_bf16x2(p0, p1);
           pk[i + 1] = pack_bf16x2(p2, p3);
         }
-        tmem_st16(tS + cc * 16, pk);   // in place over S: this thread's row was read out completely above
+        tmem_st16(tS + cc * 16, pk);  // in place: this thread's row was read out completely above
       }
       l += (l0 + l1) + (l2 + l3);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bp);
+      mbar_arrive(smem_u32(&bar_p[buf]));
+      buf += 2;
+      if (buf >= 3) { buf -= 3; spar ^= 1u; }
     }
+    // ---- merge the two groups' partial results (split-KV combine), 32 output columns per group
+    ml[g][row] = make_float2(m_used, l);
     mbar_wait(smem_u32(&bar_o), 0);
     tc_fence_after();
-    uint32_t r0[32], r1[32];
-    tmem_ld32_nowait(tO, r0);
-    tmem_ld32_nowait(tO + 32, r1);
+    a3_group_sync();
+    const float2 s0 = ml[0][row], s1 = ml[1][row];
+    const bool has1 = nkb > 1;
+    const float m = has1 ? fmaxf(s0.x, s1.x) : s0.x;
+    const float w0 = fast_exp2(s0.x - m), w1 = has1 ? fast_exp2(s1.x - m) : 0.f;
+    const float lt = s0.y * w0 + s1.y * w1;
+    const float inv = 1.f / lt;
+    const uint32_t tO0 = tmem_base + 384 + g * 32 + lane_off, tO1 = tO0 + 64;
+    uint32_t a[32], c[32];
+    float f[32];
+    tmem_ld32_nowait(tO0, a);
+    if (has1) tmem_ld32_nowait(tO1, c);
     tmem_ld_wait();
-    const int gq = q0 + t * 128 + row;
-    const float inv = 1.f / l;
-    if (gq < p.n_q) store_row64(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D, r0, r1, inv);
-    if (gq < p.n_pad) p.LSE[((long long)b * p.H + h) * p.n_pad + gq] = gq < p.n_q ? m_used + log2f(l) : INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      f[i] = (__uint_as_float(a[i]) * w0 + (has1 ? __uint_as_float(c[i]) * w1 : 0.f)) * inv;
+    const int gq = q0 + row;
+    if (gq < p.n_q) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + g * 32, f);
+    if (g == 0 && gq < p.n_pad) p.LSE[((long long)b * p.H + h) * p.n_pad + gq] = gq < p.n_q ? m + log2f(lt) : INFINITY;
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, F2_TMEM_COLS);
+    tmem_dealloc(tmem_base, A3_TMEM_COLS);
   }
 }
 
@@ -750,30 +771,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// backward v2: same ping-pong structure as attn_fwd2_kernel (one CTA per SM, two tiles, two softmax warp groups, the MMA
-// thread interleaving the tiles), bf16 dS / P^T written in place over the fp32 S / dP columns.
-//   dq2 : CTA = 256 queries (2 tiles) x key blocks of 64.    TMEM per tile: S | dP | dQ            (3 x 64 columns)
-//   dkv2: CTA = 256 keys    (2 tiles) x query blocks of 64.  TMEM per tile: S^T | dP^T | dV | dK   (4 x 64 columns)
-// Per 64-wide block and tile the tensor pipe needs 384 (dq) / 512 (dkv) cycles and the SFUs 512 cycles (8192 exp2).
-// ---------------------------------------------------------------------------------------------
-constexpr int B2_THREADS = 320;
-constexpr int B2_STAGES = 4;
-constexpr int B2_SMEM = 4 * AT_TILE128 + B2_STAGES * 2 * AT_TILE64 + 1024;
-constexpr int B2_TMEM_COLS = 512;
+// backward dQ: CTA = 128 queries x key blocks of 64.  TMEM: ring of three {S | dP} pairs [0,384) (bf16 dS written in
+// place over S), dQ accumulator [384,448).  Both groups feed the same dQ accumulator (the blocks are independent given
+// LSE and D), so no merge is needed.
+constexpr int Q3_STAGES = 6;
+constexpr int Q3_SMEM = 2 * AT_TILE128 + Q3_STAGES * 2 * AT_TILE64 + 1024;
 
-__global__ void __launch_bounds__(B2_THREADS, 1)
-attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                     const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnP p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_full[B2_STAGES], bar_empty[B2_STAGES], bar_s[2], bar_p[2], bar_o;
+  __shared__ __align__(8) uint64_t bar_q, bar_full[Q3_STAGES], bar_empty[Q3_STAGES], bar_s[3], bar_p[3], bar_o;
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base, sdO = smem_base + 2 * AT_TILE128, sKV = smem_base + 4 * AT_TILE128;
+  const uint32_t sQ = smem_base, sdO = smem_base + AT_TILE128, sKV = smem_base + 2 * AT_TILE128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nkb = (p.n_k + 63) / 64;
-  const bool two = q0 + 128 < p.n_q;  // second query tile holds real rows
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -782,19 +796,19 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmV);
     mbar_init(smem_u32(&bar_q), 1);
 #pragma unroll
-    for (int s = 0; s < B2_STAGES; ++s) {
+    for (int s = 0; s < Q3_STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(smem_u32(&bar_s[t]), 1);
-      mbar_init(smem_u32(&bar_p[t]), 128);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(smem_u32(&bar_s[i]), 1);
+      mbar_init(smem_u32(&bar_p[i]), 128);
     }
     mbar_init(smem_u32(&bar_o), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), B2_TMEM_COLS);
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -802,11 +816,9 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(smem_u32(&bar_q), 4 * AT_TILE128);
+      mbar_expect_tx(smem_u32(&bar_q), 2 * AT_TILE128);
       tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
-      tma_load_4d(sQ + AT_TILE128, &tmQ, smem_u32(&bar_q), 0, q0 + 128, h, b);
       tma_load_4d(sdO, &tmdO, smem_u32(&bar_q), 0, q0, h, b);
-      tma_load_4d(sdO + AT_TILE128, &tmdO, smem_u32(&bar_q), 0, q0 + 128, h, b);
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nkb; ++j) {
@@ -815,145 +827,135 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_expect_tx(full, 2 * AT_TILE64);
         tma_load_4d(sKV + s * 2 * AT_TILE64, &tmK, full, 0, j * 64, h, b);
         tma_load_4d(sKV + s * 2 * AT_TILE64 + AT_TILE64, &tmV, full, 0, j * 64, h, b);
-        if (++s == B2_STAGES) { s = 0; ph ^= 1u; }
+        if (++s == Q3_STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
       constexpr uint32_t idQ = umma_idesc(128, AT_D, 0, 1);
-      auto issue_SdP = [&](int t, uint32_t sK, uint32_t sV) {
-        const uint32_t tS = tmem_base + t * 192, tdP = tS + 64;
-        const uint32_t sQt = sQ + t * AT_TILE128, sdOt = sdO + t * AT_TILE128;
+      auto issue_SdP = [&](int buf, int stage) {
+        const uint32_t tS = tmem_base + buf * 128, tdP = tS + 64;
+        const uint32_t sK = sKV + stage * 2 * AT_TILE64, sV = sK + AT_TILE64;
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sQt + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
+          umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tdP, umma_desc(sdOt + k * 32, 16, 1024), umma_desc(sV + k * 32, 16, 1024), idS, k != 0);
-      };
-      auto issue_dQ = [&](int t, uint32_t sK, bool first) {
-        const uint32_t tdS = tmem_base + t * 192, tdQ = tdS + 128;
-#pragma unroll
-        for (int k = 0; k < 64 / 16; ++k)
-          umma_bf16_ts(tdQ, tdS + k * 8, umma_desc(sK + k * 2048, 8192, 1024), idQ, (!first) || k != 0);
+          umma_bf16(tdP, umma_desc(sdO + k * 32, 16, 1024), umma_desc(sV + k * 32, 16, 1024), idS, k != 0);
       };
       mbar_wait(smem_u32(&bar_q), 0);
-      mbar_wait(smem_u32(&bar_full[0]), 0);
-      tc_fence_after();
-      issue_SdP(0, sKV, sKV + AT_TILE64);
-      umma_commit(smem_u32(&bar_s[0]));
-      if (two) {
-        issue_SdP(1, sKV, sKV + AT_TILE64);
-        umma_commit(smem_u32(&bar_s[1]));
-      }
-      int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nkb; ++j) {
-        int sn = s + 1;
-        uint32_t phn = ph;
-        if (sn == B2_STAGES) { sn = 0; phn ^= 1u; }
-        const uint32_t sK = sKV + s * 2 * AT_TILE64;
-        const uint32_t sKn = sKV + sn * 2 * AT_TILE64, sVn = sKn + AT_TILE64;
-        const bool more = j + 1 < nkb;
-        mbar_wait(smem_u32(&bar_p[0]), j & 1);
+      int ls = 0, issued = 0;
+      uint32_t lph = 0;
+      for (; issued < 3 && issued < nkb; ++issued) {
+        mbar_wait(smem_u32(&bar_full[ls]), lph);
         tc_fence_after();
-        issue_dQ(0, sK, j == 0);
-        if (more) {
-          mbar_wait(smem_u32(&bar_full[sn]), phn);
+        issue_SdP(issued, ls);
+        umma_commit(smem_u32(&bar_s[issued]));
+        if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
+      }
+      int buf = 0, cs = 0;
+      uint32_t ppar = 0;
+      const uint32_t tdQ = tmem_base + 384;
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(smem_u32(&bar_p[buf]), ppar);
+        tc_fence_after();
+        const uint32_t tdS = tmem_base + buf * 128;
+        const uint32_t sK = sKV + cs * 2 * AT_TILE64;
+#pragma unroll
+        for (int k = 0; k < 64 / 16; ++k)
+          umma_bf16_ts(tdQ, tdS + k * 8, umma_desc(sK + k * 2048, 8192, 1024), idQ, (j | k) != 0);
+        umma_commit(smem_u32(&bar_empty[cs]));
+        if (issued < nkb) {
+          mbar_wait(smem_u32(&bar_full[ls]), lph);
           tc_fence_after();
-          issue_SdP(0, sKn, sVn);
-          umma_commit(smem_u32(&bar_s[0]));
+          issue_SdP(buf, ls);
+          umma_commit(smem_u32(&bar_s[buf]));
+          if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
+          ++issued;
         }
-        if (two) {
-          mbar_wait(smem_u32(&bar_p[1]), j & 1);
-          tc_fence_after();
-          issue_dQ(1, sK, j == 0);
-        }
-        umma_commit(smem_u32(&bar_empty[s]));
-        if (more && two) {
-          issue_SdP(1, sKn, sVn);
-          umma_commit(smem_u32(&bar_s[1]));
-        }
-        s = sn;
-        ph = phn;
+        if (++cs == Q3_STAGES) cs = 0;
+        if (++buf == 3) { buf = 0; ppar ^= 1u; }
       }
       umma_commit(smem_u32(&bar_o));
     }
   } else {
-    const int t = (warp - 2) >> 2;
+    const int g = (warp - 2) >> 2;
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    const int gq = q0 + t * 128 + row;
-    if (t == 0 || two) {
-      const uint32_t tS = tmem_base + t * 192 + lane_off, tdP = tS + 64, tdQ = tS + 128;
-      const uint32_t bs = smem_u32(&bar_s[t]), bp = smem_u32(&bar_p[t]);
-      const long long sidx = ((long long)b * p.H + h) * p.n_pad + gq;
-      const float L2 = gq < p.n_pad ? p.LSE[sidx] : INFINITY;  // +inf on pad rows -> P = 0
-      const float Dr = gq < p.n_pad ? p.D[sidx] : 0.f;
-      for (int j = 0; j < nkb; ++j) {
-        mbar_wait(bs, j & 1);
-        tc_fence_after();
-        const int valid = min(64, p.n_k - j * 64);
-        // whole 64-key block in registers: one TMEM round trip, then 64 independent exp2 / dS evaluations
-        uint32_t rs[64], rd[64];
-        tmem_ld32_nowait(tS, rs);
-        tmem_ld32_nowait(tS + 32, rs + 32);
-        tmem_ld32_nowait(tdP, rd);
-        tmem_ld32_nowait(tdP + 32, rd + 32);
-        tmem_ld_wait();
-        if (valid < 64) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i >= valid) rs[i] = 0xff800000u;  // -inf logit -> P = 0 -> dS = 0
-        }
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(rs[cc * 32 + 2 * i]), p.c, -L2));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(rs[cc * 32 + 2 * i + 1]), p.c, -L2));
-            pk[i] = pack_bf16x2(p0 * (__uint_as_float(rd[cc * 32 + 2 * i]) - Dr),
-                                p1 * (__uint_as_float(rd[cc * 32 + 2 * i + 1]) - Dr));
-          }
-          tmem_st16(tS + cc * 16, pk);  // dS (bf16) in place over the consumed S columns
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(bp);
-      }
-      mbar_wait(smem_u32(&bar_o), 0);
+    const int gq = q0 + row;
+    const long long sidx = ((long long)b * p.H + h) * p.n_pad + gq;
+    const float L2 = p.LSE[sidx];   // n_pad is a multiple of 128: in bounds; +inf on pad rows -> P = 0
+    const float Dr = p.D[sidx];
+    int buf = g;
+    uint32_t spar = 0;
+    for (int j = g; j < nkb; j += 2) {
+      mbar_wait(smem_u32(&bar_s[buf]), spar);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld32_nowait(tdQ, r0);
-      tmem_ld32_nowait(tdQ + 32, r1);
+      const uint32_t tS = tmem_base + buf * 128 + lane_off, tdP = tS + 64;
+      const int valid = min(64, p.n_k - j * 64);
+      uint32_t rs[64], rd[64];
+      tmem_ld32_nowait(tS, rs);
+      tmem_ld32_nowait(tS + 32, rs + 32);
+      tmem_ld32_nowait(tdP, rd);
+      tmem_ld32_nowait(tdP + 32, rd + 32);
       tmem_ld_wait();
-      if (gq < p.n_q) store_row64(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D, r0, r1, p.scale);
+      if (valid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) rs[i] = 0xff800000u;  // -inf logit -> P = 0 -> dS = 0
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(rs[cc * 32 + 2 * i]), p.c, -L2));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(rs[cc * 32 + 2 * i + 1]), p.c, -L2));
+          pk[i] = pack_bf16x2(p0 * (__uint_as_float(rd[cc * 32 + 2 * i]) - Dr),
+                              p1 * (__uint_as_float(rd[cc * 32 + 2 * i + 1]) - Dr));
+        }
+        tmem_st16(tS + cc * 16, pk);  // dS (bf16) in place over the consumed S columns
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_p[buf]));
+      buf += 2;
+      if (buf >= 3) { buf -= 3; spar ^= 1u; }
     }
+    mbar_wait(smem_u32(&bar_o), 0);
+    tc_fence_after();
+    uint32_t a[32];
+    float f[32];
+    tmem_ld32(tmem_base + 384 + g * 32 + lane_off, a);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(a[i]) * p.scale;
+    if (gq < p.n_q) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + g * 32, f);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, B2_TMEM_COLS);
+    tmem_dealloc(tmem_base, A3_TMEM_COLS);
   }
 }
 
-__global__ void __launch_bounds__(B2_THREADS, 1)
-attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+// backward dK / dV: CTA = 128 keys x query blocks of 64.  TMEM: ring of three {S^T | dP^T} pairs [0,384) (bf16 P^T / dS^T
+// in place), dV [384,448), dK [448,512).  The S^T / dP^T MMAs that refill a ring slot are issued after the dV / dK MMAs
+// that read it as their A operand; tcgen05.mma instructions of one thread execute in issue order.
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO, const AttnP p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_kv, bar_full[B2_STAGES], bar_empty[B2_STAGES], bar_s[2], bar_p[2], bar_o;
+  __shared__ __align__(8) uint64_t bar_kv, bar_full[Q3_STAGES], bar_empty[Q3_STAGES], bar_s[3], bar_p[3], bar_o;
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sK = smem_base, sV = smem_base + 2 * AT_TILE128, sQdO = smem_base + 4 * AT_TILE128;
+  const uint32_t sK = smem_base, sV = smem_base + AT_TILE128, sQdO = smem_base + 2 * AT_TILE128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nqb = (p.n_q + 63) / 64;
-  const bool two = k0 + 128 < p.n_k;  // cross-attention (77 keys): only tile 0 holds real keys
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmK);
@@ -962,19 +964,19 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     tma_prefetch_desc(&tmdO);
     mbar_init(smem_u32(&bar_kv), 1);
 #pragma unroll
-    for (int s = 0; s < B2_STAGES; ++s) {
+    for (int s = 0; s < Q3_STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(smem_u32(&bar_s[t]), 1);
-      mbar_init(smem_u32(&bar_p[t]), 128);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(smem_u32(&bar_s[i]), 1);
+      mbar_init(smem_u32(&bar_p[i]), 128);
     }
     mbar_init(smem_u32(&bar_o), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), B2_TMEM_COLS);
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -982,11 +984,9 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(smem_u32(&bar_kv), 4 * AT_TILE128);
+      mbar_expect_tx(smem_u32(&bar_kv), 2 * AT_TILE128);
       tma_load_4d(sK, &tmK, smem_u32(&bar_kv), 0, k0, h, b);
-      tma_load_4d(sK + AT_TILE128, &tmK, smem_u32(&bar_kv), 0, k0 + 128, h, b);
       tma_load_4d(sV, &tmV, smem_u32(&bar_kv), 0, k0, h, b);
-      tma_load_4d(sV + AT_TILE128, &tmV, smem_u32(&bar_kv), 0, k0 + 128, h, b);
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nqb; ++i) {
@@ -995,140 +995,129 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
         mbar_expect_tx(full, 2 * AT_TILE64);
         tma_load_4d(sQdO + s * 2 * AT_TILE64, &tmQ, full, 0, i * 64, h, b);
         tma_load_4d(sQdO + s * 2 * AT_TILE64 + AT_TILE64, &tmdO, full, 0, i * 64, h, b);
-        if (++s == B2_STAGES) { s = 0; ph ^= 1u; }
+        if (++s == Q3_STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
       constexpr uint32_t idG = umma_idesc(128, AT_D, 0, 1);
-      auto issue_SdP = [&](int t, uint32_t sQb, uint32_t sdOb) {
-        const uint32_t tS = tmem_base + t * 256, tdP = tS + 64;
-        const uint32_t sKt = sK + t * AT_TILE128, sVt = sV + t * AT_TILE128;
+      auto issue_SdP = [&](int buf, int stage) {
+        const uint32_t tS = tmem_base + buf * 128, tdP = tS + 64;
+        const uint32_t sQb = sQdO + stage * 2 * AT_TILE64, sdOb = sQb + AT_TILE64;
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sKt + k * 32, 16, 1024), umma_desc(sQb + k * 32, 16, 1024), idS, k != 0);
+          umma_bf16(tS, umma_desc(sK + k * 32, 16, 1024), umma_desc(sQb + k * 32, 16, 1024), idS, k != 0);
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tdP, umma_desc(sVt + k * 32, 16, 1024), umma_desc(sdOb + k * 32, 16, 1024), idS, k != 0);
-      };
-      auto issue_dVdK = [&](int t, uint32_t sQb, uint32_t sdOb, bool first) {
-        const uint32_t tS = tmem_base + t * 256, tdP = tS + 64, tdV = tS + 128, tdK = tS + 192;
-#pragma unroll
-        for (int k = 0; k < 64 / 16; ++k)
-          umma_bf16_ts(tdV, tS + k * 8, umma_desc(sdOb + k * 2048, 8192, 1024), idG, (!first) || k != 0);
-#pragma unroll
-        for (int k = 0; k < 64 / 16; ++k)
-          umma_bf16_ts(tdK, tdP + k * 8, umma_desc(sQb + k * 2048, 8192, 1024), idG, (!first) || k != 0);
+          umma_bf16(tdP, umma_desc(sV + k * 32, 16, 1024), umma_desc(sdOb + k * 32, 16, 1024), idS, k != 0);
       };
       mbar_wait(smem_u32(&bar_kv), 0);
-      mbar_wait(smem_u32(&bar_full[0]), 0);
-      tc_fence_after();
-      issue_SdP(0, sQdO, sQdO + AT_TILE64);
-      umma_commit(smem_u32(&bar_s[0]));
-      if (two) {
-        issue_SdP(1, sQdO, sQdO + AT_TILE64);
-        umma_commit(smem_u32(&bar_s[1]));
-      }
-      int s = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < nqb; ++i) {
-        int sn = s + 1;
-        uint32_t phn = ph;
-        if (sn == B2_STAGES) { sn = 0; phn ^= 1u; }
-        const uint32_t sQb = sQdO + s * 2 * AT_TILE64, sdOb = sQb + AT_TILE64;
-        const uint32_t sQn = sQdO + sn * 2 * AT_TILE64, sdOn = sQn + AT_TILE64;
-        const bool more = i + 1 < nqb;
-        mbar_wait(smem_u32(&bar_p[0]), i & 1);
+      int ls = 0, issued = 0;
+      uint32_t lph = 0;
+      for (; issued < 3 && issued < nqb; ++issued) {
+        mbar_wait(smem_u32(&bar_full[ls]), lph);
         tc_fence_after();
-        issue_dVdK(0, sQb, sdOb, i == 0);
-        if (more) {
-          mbar_wait(smem_u32(&bar_full[sn]), phn);
+        issue_SdP(issued, ls);
+        umma_commit(smem_u32(&bar_s[issued]));
+        if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
+      }
+      int buf = 0, cs = 0;
+      uint32_t ppar = 0;
+      const uint32_t tdV = tmem_base + 384, tdK = tmem_base + 448;
+      for (int i = 0; i < nqb; ++i) {
+        mbar_wait(smem_u32(&bar_p[buf]), ppar);
+        tc_fence_after();
+        const uint32_t tP = tmem_base + buf * 128, tdS = tP + 64;
+        const uint32_t sQb = sQdO + cs * 2 * AT_TILE64, sdOb = sQb + AT_TILE64;
+#pragma unroll
+        for (int k = 0; k < 64 / 16; ++k)
+          umma_bf16_ts(tdV, tP + k * 8, umma_desc(sdOb + k * 2048, 8192, 1024), idG, (i | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 64 / 16; ++k)
+          umma_bf16_ts(tdK, tdS + k * 8, umma_desc(sQb + k * 2048, 8192, 1024), idG, (i | k) != 0);
+        umma_commit(smem_u32(&bar_empty[cs]));
+        if (issued < nqb) {
+          mbar_wait(smem_u32(&bar_full[ls]), lph);
           tc_fence_after();
-          issue_SdP(0, sQn, sdOn);
-          umma_commit(smem_u32(&bar_s[0]));
+          issue_SdP(buf, ls);
+          umma_commit(smem_u32(&bar_s[buf]));
+          if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
+          ++issued;
         }
-        if (two) {
-          mbar_wait(smem_u32(&bar_p[1]), i & 1);
-          tc_fence_after();
-          issue_dVdK(1, sQb, sdOb, i == 0);
-        }
-        umma_commit(smem_u32(&bar_empty[s]));
-        if (more && two) {
-          issue_SdP(1, sQn, sdOn);
-          umma_commit(smem_u32(&bar_s[1]));
-        }
-        s = sn;
-        ph = phn;
+        if (++cs == Q3_STAGES) cs = 0;
+        if (++buf == 3) { buf = 0; ppar ^= 1u; }
       }
       umma_commit(smem_u32(&bar_o));
     }
   } else {
-    const int t = (warp - 2) >> 2;
+    const int g = (warp - 2) >> 2;
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    if (t == 0 || two) {
-      const uint32_t tS = tmem_base + t * 256 + lane_off, tdP = tS + 64, tdV = tS + 128, tdK = tS + 192;
-      const uint32_t bs = smem_u32(&bar_s[t]), bp = smem_u32(&bar_p[t]);
-      const float* Lp = p.LSE + ((long long)b * p.H + h) * p.n_pad;
-      const float* Dp = p.D + ((long long)b * p.H + h) * p.n_pad;
-      for (int i = 0; i < nqb; ++i) {
-        mbar_wait(bs, i & 1);
-        tc_fence_after();
-        // whole 64-query block in registers (one TMEM round trip); LSE / D of the 64 queries are warp-uniform loads
-        uint32_t rs[64], rd[64];
-        tmem_ld32_nowait(tS, rs);
-        tmem_ld32_nowait(tS + 32, rs + 32);
-        tmem_ld32_nowait(tdP, rd);
-        tmem_ld32_nowait(tdP + 32, rd + 32);
-        // n_pad is a multiple of 128 and the last 64-query block starts below n_q <= n_pad: always in bounds
-        const float4* L4 = reinterpret_cast<const float4*>(Lp + i * 64);
-        const float4* D4 = reinterpret_cast<const float4*>(Dp + i * 64);
-        tmem_ld_wait();
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t pp[16], pd[16];
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 lv = __ldg(L4 + cc * 8 + g), dv = __ldg(D4 + cc * 8 + g);
-            const int o = cc * 32 + 4 * g;
-            const float p0 = fast_exp2(fmaf(__uint_as_float(rs[o + 0]), p.c, -lv.x));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(rs[o + 1]), p.c, -lv.y));
-            const float p2 = fast_exp2(fmaf(__uint_as_float(rs[o + 2]), p.c, -lv.z));
-            const float p3 = fast_exp2(fmaf(__uint_as_float(rs[o + 3]), p.c, -lv.w));
-            pp[2 * g] = pack_bf16x2(p0, p1);
-            pp[2 * g + 1] = pack_bf16x2(p2, p3);
-            pd[2 * g] = pack_bf16x2(p0 * (__uint_as_float(rd[o + 0]) - dv.x), p1 * (__uint_as_float(rd[o + 1]) - dv.y));
-            pd[2 * g + 1] = pack_bf16x2(p2 * (__uint_as_float(rd[o + 2]) - dv.z), p3 * (__uint_as_float(rd[o + 3]) - dv.w));
-          }
-          tmem_st16(tS + cc * 16, pp);
-          tmem_st16(tdP + cc * 16, pd);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(bp);
-      }
-      mbar_wait(smem_u32(&bar_o), 0);
+    const float* Lp = p.LSE + ((long long)b * p.H + h) * p.n_pad;
+    const float* Dp = p.D + ((long long)b * p.H + h) * p.n_pad;
+    int buf = g;
+    uint32_t spar = 0;
+    for (int i = g; i < nqb; i += 2) {
+      mbar_wait(smem_u32(&bar_s[buf]), spar);
       tc_fence_after();
-      const int gk = k0 + t * 128 + row;
-      uint32_t r0[32], r1[32];
-      tmem_ld32_nowait(tdV, r0);
-      tmem_ld32_nowait(tdV + 32, r1);
+      const uint32_t tS = tmem_base + buf * 128 + lane_off, tdP = tS + 64;
+      uint32_t rs[64], rd[64];
+      tmem_ld32_nowait(tS, rs);
+      tmem_ld32_nowait(tS + 32, rs + 32);
+      tmem_ld32_nowait(tdP, rd);
+      tmem_ld32_nowait(tdP + 32, rd + 32);
+      // n_pad is a multiple of 128 and the last 64-query block starts below n_q <= n_pad: always in bounds; pad rows
+      // hold LSE = +inf (P = 0) and D = 0
+      const float4* L4 = reinterpret_cast<const float4*>(Lp + i * 64);
+      const float4* D4 = reinterpret_cast<const float4*>(Dp + i * 64);
       tmem_ld_wait();
-      if (gk < p.n_k) store_row64(p.out1 + (long long)b * p.bs1 + (long long)gk * p.ld1 + h * AT_D, r0, r1, 1.f);
-      tmem_ld32_nowait(tdK, r0);
-      tmem_ld32_nowait(tdK + 32, r1);
-      tmem_ld_wait();
-      if (gk < p.n_k) store_row64(p.out0 + (long long)b * p.bs0 + (long long)gk * p.ld0 + h * AT_D, r0, r1, p.scale);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 lv = __ldg(L4 + cc * 8 + q), dv = __ldg(D4 + cc * 8 + q);
+          const int o = cc * 32 + 4 * q;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(rs[o + 0]), p.c, -lv.x));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(rs[o + 1]), p.c, -lv.y));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(rs[o + 2]), p.c, -lv.z));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(rs[o + 3]), p.c, -lv.w));
+          pp[2 * q] = pack_bf16x2(p0, p1);
+          pp[2 * q + 1] = pack_bf16x2(p2, p3);
+          pd[2 * q] = pack_bf16x2(p0 * (__uint_as_float(rd[o + 0]) - dv.x), p1 * (__uint_as_float(rd[o + 1]) - dv.y));
+          pd[2 * q + 1] = pack_bf16x2(p2 * (__uint_as_float(rd[o + 2]) - dv.z), p3 * (__uint_as_float(rd[o + 3]) - dv.w));
+        }
+        tmem_st16(tS + cc * 16, pp);
+        tmem_st16(tdP + cc * 16, pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_p[buf]));
+      buf += 2;
+      if (buf >= 3) { buf -= 3; spar ^= 1u; }
     }
+    mbar_wait(smem_u32(&bar_o), 0);
+    tc_fence_after();
+    const int gk = k0 + row;
+    uint32_t a[32];
+    float f[32];
+    tmem_ld32(tmem_base + 384 + g * 32 + lane_off, a);  // dV
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(a[i]);
+    if (gk < p.n_k) store_row32(p.out1 + (long long)b * p.bs1 + (long long)gk * p.ld1 + h * AT_D + g * 32, f);
+    tmem_ld32(tmem_base + 448 + g * 32 + lane_off, a);  // dK
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(a[i]) * p.scale;
+    if (gk < p.n_k) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gk * p.ld0 + h * AT_D + g * 32, f);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, B2_TMEM_COLS);
+    tmem_dealloc(tmem_base, A3_TMEM_COLS);
   }
 }
 
@@ -1176,11 +1165,11 @@ extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
   if (!legacy) {
     static bool configured2 = false;
     if (!configured2) {
-      if ((rc = set_smem(attn_fwd2_kernel, F2_SMEM, "b2_attn_fwd"))) return rc;
+      if ((rc = set_smem(attn_fwd3_kernel, F3_SMEM, "b2_attn_fwd"))) return rc;
       configured2 = true;
     }
-    dim3 grid2((a->n_q + 255) / 256, a->H, a->B);
-    attn_fwd2_kernel<<<grid2, F2_THREADS, F2_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    dim3 grid3((a->n_q + 127) / 128, a->H, a->B);
+    attn_fwd3_kernel<<<grid3, A3_THREADS, F3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
     return check_launch("b2_attn_fwd");
   }
   dim3 grid((a->n_q + 127) / 128, a->H, a->B);
@@ -1215,8 +1204,8 @@ extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
   if (!legacy && !(a->flags & 1)) {
     static bool configured2 = false;
     if (!configured2) {
-      if ((rc = set_smem(attn_bwd_dq2_kernel, B2_SMEM, "b2_attn_bwd"))) return rc;
-      if ((rc = set_smem(attn_bwd_dkv2_kernel, B2_SMEM, "b2_attn_bwd"))) return rc;
+      if ((rc = set_smem(attn_bwd_dq3_kernel, Q3_SMEM, "b2_attn_bwd"))) return rc;
+      if ((rc = set_smem(attn_bwd_dkv3_kernel, Q3_SMEM, "b2_attn_bwd"))) return rc;
       configured2 = true;
     }
     CUtensorMap tq128, tdo128, tk64, tv64, tk128, tv128, tq64, tdo64;
@@ -1230,13 +1219,13 @@ extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
     if ((rc = make_map_bf16_4d(&tdo64, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 64, "attn dO64"))) return rc;
     AttnP pq = p;
     pq.out0 = (bf16*)a->dQ; pq.ld0 = a->lddq; pq.bs0 = a->dq_bs;
-    attn_bwd_dq2_kernel<<<dim3((a->n_q + 255) / 256, a->H, a->B), B2_THREADS, B2_SMEM, st>>>(tq128, tdo128, tk64, tv64, pq);
-    if ((rc = check_launch("b2_attn_bwd dq2"))) return rc;
+    attn_bwd_dq3_kernel<<<dim3((a->n_q + 127) / 128, a->H, a->B), A3_THREADS, Q3_SMEM, st>>>(tq128, tdo128, tk64, tv64, pq);
+    if ((rc = check_launch("b2_attn_bwd dq3"))) return rc;
     AttnP pk = p;
     pk.out0 = (bf16*)a->dK; pk.ld0 = a->lddk; pk.bs0 = a->dk_bs;
     pk.out1 = (bf16*)a->dV; pk.ld1 = a->lddv; pk.bs1 = a->dv_bs;
-    attn_bwd_dkv2_kernel<<<dim3((a->n_k + 255) / 256, a->H, a->B), B2_THREADS, B2_SMEM, st>>>(tk128, tv128, tq64, tdo64, pk);
-    return check_launch("b2_attn_bwd dkv2");
+    attn_bwd_dkv3_kernel<<<dim3((a->n_k + 127) / 128, a->H, a->B), A3_THREADS, Q3_SMEM, st>>>(tk128, tv128, tq64, tdo64, pk);
+    return check_launch("b2_attn_bwd dkv3");
   }
   {
     CUtensorMap tq, tdo, tk, tv;
