@@ -178,6 +178,8 @@ typedef struct b2_attn_args {
 int b2_attn_lse_rows(int n_q);
 int b2_attn_fwd(const b2_attn_args* args, void* stream);
 int b2_attn_bwd(const b2_attn_args* args, void* stream);
+/* Profiling hook: device buffer of 32 uint64 per-phase cycle counters accumulated by the forward kernel (NULL = off). */
+int b2_attn_set_debug(void* counters);
 
 /* GEGLU: z[m, j] = u[m, j] * gelu_erf(u[m, F + j]), u: [M, 2F]. replaces diffusers GEGLU.forward + backward. */
 int b2_geglu_fwd(const void* u, void* z, int64_t M, int F, void* stream);

@@ -21,6 +21,13 @@
 
 namespace b2 {
 
+static unsigned long long* g_attn_dbg = nullptr;
+__device__ __forceinline__ unsigned long long clk() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
+
 constexpr int AT_THREADS = 192;
 constexpr int AT_D = 64;                        // head dim
 constexpr int AT_TILE128 = 128 * AT_D * 2;      // 16 KiB: 128 rows x 64 bf16
@@ -37,6 +44,7 @@ struct AttnP {
   bf16* out0;   // fwd: O ; bwd_dq: dQ ; bwd_dkv: dK
   bf16* out1;   //                        bwd_dkv: dV
   long long ld0, bs0, ld1, bs1;
+  unsigned long long* dbg;  // optional per-phase cycle counters (b2_attn_set_debug), NULL in production
 };
 
 __device__ __forceinline__ void store_row64(bf16* dst, const uint32_t* r0, const uint32_t* r1, float mul) {
@@ -322,22 +330,32 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       int buf = 0, cs = 0;  // ring slot and KV stage of block j
       uint32_t ppar = 0;    // parity of bar_p[buf] for block j (flips when buf wraps)
+      unsigned long long m_waitp = 0, m_waitf = 0, m_pv = 0, m_s = 0, m_cm = 0, mt0 = 0, mt1 = 0;
+      const bool dbg = p.dbg != nullptr;
       for (int j = 0; j < nkb; ++j) {
         const int g = j & 1;
+        if (dbg) mt0 = clk();
         mbar_wait(smem_u32(&bar_p[buf]), ppar);
         tc_fence_after();
+        if (dbg) { mt1 = clk(); m_waitp += mt1 - mt0; mt0 = mt1; }
         const uint32_t tP = tmem_base + buf * 128, tO = tmem_base + 384 + g * 64;
         const uint32_t sV = sKV + cs * 2 * AT_TILE128 + AT_TILE128;
 #pragma unroll
         for (int k = 0; k < 128 / 16; ++k)
           umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (j >= 2) || k != 0);
+        if (dbg) { mt1 = clk(); m_pv += mt1 - mt0; mt0 = mt1; }
         umma_commit(smem_u32(&bar_pv[g]));
         umma_commit(smem_u32(&bar_empty[cs]));
+        if (dbg) { mt1 = clk(); m_cm += mt1 - mt0; mt0 = mt1; }
         if (issued < nkb) {  // refill this ring slot with S(j + 3)
+          if (dbg) mt0 = clk();
           mbar_wait(smem_u32(&bar_full[ls]), lph);
           tc_fence_after();
+          if (dbg) { mt1 = clk(); m_waitf += mt1 - mt0; mt0 = mt1; }
           issue_S(buf, ls);
+          if (dbg) { mt1 = clk(); m_s += mt1 - mt0; mt0 = mt1; }
           umma_commit(smem_u32(&bar_s[buf]));
+          if (dbg) { mt1 = clk(); m_cm += mt1 - mt0; mt0 = mt1; }
           if (++ls == F3_STAGES) { ls = 0; lph ^= 1u; }
           ++issued;
         }
@@ -345,6 +363,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (++buf == 3) { buf = 0; ppar ^= 1u; }
       }
       umma_commit(smem_u32(&bar_o));
+      if (dbg) { atomicAdd(p.dbg + 16, m_waitp); atomicAdd(p.dbg + 17, m_waitf); atomicAdd(p.dbg + 18, 1ull);
+                 atomicAdd(p.dbg + 19, m_pv); atomicAdd(p.dbg + 20, m_s); atomicAdd(p.dbg + 21, m_cm); }
     }
   } else {
     const int g = (warp - 2) >> 2;
@@ -356,9 +376,14 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     int buf = g;          // ring slot of block j = g, g + 2, ...
     uint32_t spar = 0;    // parity of bar_s[buf] for that block
     int kown = 0;         // own blocks done
+    unsigned long long d_wait = 0, d_ld = 0, d_cmp = 0, d_st = 0, d_arr = 0, t0 = 0, t1 = 0;
+    const bool dbg = p.dbg != nullptr;
+    const unsigned long long t_begin = dbg ? clk() : 0;
     for (int j = g; j < nkb; j += 2, ++kown) {
+      if (dbg) t0 = clk();
       mbar_wait(smem_u32(&bar_s[buf]), spar);
       tc_fence_after();
+      if (dbg) { t1 = clk(); d_wait += t1 - t0; t0 = t1; }
       const uint32_t tS = tmem_base + buf * 128 + lane_off;
       const int valid = min(128, p.n_k - j * 128);
       uint32_t r[128];
@@ -367,6 +392,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_ld32_nowait(tS + 64, r + 64);
       tmem_ld32_nowait(tS + 96, r + 96);
       tmem_ld_wait();
+      if (dbg) { t1 = clk(); d_ld += t1 - t0; t0 = t1; }
       if (valid < 128) {  // ragged last key block: -inf logits -> P = 0
 #pragma unroll
         for (int i = 0; i < 128; ++i)
@@ -419,14 +445,18 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_st16(tS + cc * 16, pk);  // in place: this thread's row was read out completely above
       }
       l += (l0 + l1) + (l2 + l3);
+      if (dbg) { t1 = clk(); d_cmp += t1 - t0; t0 = t1; }
       tmem_st_wait();
       tc_fence_before();
+      if (dbg) { t1 = clk(); d_st += t1 - t0; t0 = t1; }
       mbar_arrive(smem_u32(&bar_p[buf]));
+      if (dbg) { t1 = clk(); d_arr += t1 - t0; t0 = t1; }
       buf += 2;
       if (buf >= 3) { buf -= 3; spar ^= 1u; }
     }
     // ---- merge the two groups' partial results (split-KV combine), 32 output columns per group
     ml[g][row] = make_float2(m_used, l);
+    const unsigned long long t_loop_end = dbg ? clk() : 0;
     mbar_wait(smem_u32(&bar_o), 0);
     tc_fence_after();
     a3_group_sync();
@@ -448,6 +478,13 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int gq = q0 + row;
     if (gq < p.n_q) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + g * 32, f);
     if (g == 0 && gq < p.n_pad) p.LSE[((long long)b * p.H + h) * p.n_pad + gq] = gq < p.n_q ? m + log2f(lt) : INFINITY;
+    if (dbg && lane == 0 && qd == 0) {
+      const unsigned long long t_end = clk();
+      unsigned long long* d = p.dbg + g * 8;
+      atomicAdd(d + 0, d_wait); atomicAdd(d + 1, d_ld); atomicAdd(d + 2, d_cmp); atomicAdd(d + 3, d_st);
+      atomicAdd(d + 4, d_arr); atomicAdd(d + 5, t_loop_end - t_begin); atomicAdd(d + 6, t_end - t_loop_end);
+      atomicAdd(d + 7, 1ull);
+    }
   }
 
   tc_fence_before();
@@ -1144,6 +1181,12 @@ using namespace b2;
 
 extern "C" int b2_attn_lse_rows(int n_q) { return (n_q + 127) / 128 * 128; }
 
+/* profiling hook (tools/attn_phase_timing.py): 32 uint64 counters accumulated by attn_fwd3_kernel, NULL disables */
+extern "C" int b2_attn_set_debug(void* counters) {
+  b2::g_attn_dbg = reinterpret_cast<unsigned long long*>(counters);
+  return B2_OK;
+}
+
 extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
   int rc = check_common(a, "b2_attn_fwd");
   if (rc) return rc;
@@ -1160,6 +1203,7 @@ extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
   p.H = a->H; p.n_q = a->n_q; p.n_k = a->n_k; p.n_pad = b2_attn_lse_rows(a->n_q);
   p.scale = a->scale; p.c = a->scale * 1.4426950408889634f;
   p.LSE = a->LSE; p.D = nullptr;
+  p.dbg = g_attn_dbg;
   p.out0 = (bf16*)a->O; p.ld0 = a->ldo; p.bs0 = a->o_bs;
   static const bool legacy = getenv("B2_ATTN_LEGACY") != nullptr;
   if (!legacy) {
