@@ -261,7 +261,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
   const uint32_t sKV = smem_base + AT_TILE128;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nkb = (p.n_k + 127) / 128;
 
@@ -289,25 +289,31 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = uniform_u32(tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
+    {
+      if (el) {
       mbar_expect_tx(smem_u32(&bar_q), AT_TILE128);
-      tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
+        tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
+      }
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nkb; ++j) {
         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
         const uint32_t full = smem_u32(&bar_full[s]);
+        if (el) {
         mbar_expect_tx(full, 2 * AT_TILE128);
-        tma_load_4d(sKV + s * 2 * AT_TILE128, &tmK, full, 0, j * 128, h, b);
-        tma_load_4d(sKV + s * 2 * AT_TILE128 + AT_TILE128, &tmV, full, 0, j * 128, h, b);
+          tma_load_4d(sKV + s * 2 * AT_TILE128, &tmK, full, 0, j * 128, h, b);
+          tma_load_4d(sKV + s * 2 * AT_TILE128 + AT_TILE128, &tmV, full, 0, j * 128, h, b);
+        }
         if (++s == F3_STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool el = elect_one();
+    {
       constexpr uint32_t idS = umma_idesc(128, 128, 0, 0);
       constexpr uint32_t idO = umma_idesc(128, AT_D, 0, 1);
       auto issue_S = [&](int buf, int stage) {
@@ -324,8 +330,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (; issued < 3 && issued < nkb; ++issued) {
         mbar_wait(smem_u32(&bar_full[ls]), lph);
         tc_fence_after();
-        issue_S(issued, ls);
-        umma_commit(smem_u32(&bar_s[issued]));
+        if (el) issue_S(issued, ls);
+        if (el) umma_commit(smem_u32(&bar_s[issued]));
         if (++ls == F3_STAGES) { ls = 0; lph ^= 1u; }
       }
       int buf = 0, cs = 0;  // ring slot and KV stage of block j
@@ -340,21 +346,23 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (dbg) { mt1 = clk(); m_waitp += mt1 - mt0; mt0 = mt1; }
         const uint32_t tP = tmem_base + buf * 128, tO = tmem_base + 384 + g * 64;
         const uint32_t sV = sKV + cs * 2 * AT_TILE128 + AT_TILE128;
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < 128 / 16; ++k)
-          umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (j >= 2) || k != 0);
+          for (int k = 0; k < 128 / 16; ++k)
+            umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (j >= 2) || k != 0);
+        }
         if (dbg) { mt1 = clk(); m_pv += mt1 - mt0; mt0 = mt1; }
-        umma_commit(smem_u32(&bar_pv[g]));
-        umma_commit(smem_u32(&bar_empty[cs]));
+        if (el) umma_commit(smem_u32(&bar_pv[g]));
+        if (el) umma_commit(smem_u32(&bar_empty[cs]));
         if (dbg) { mt1 = clk(); m_cm += mt1 - mt0; mt0 = mt1; }
         if (issued < nkb) {  // refill this ring slot with S(j + 3)
           if (dbg) mt0 = clk();
           mbar_wait(smem_u32(&bar_full[ls]), lph);
           tc_fence_after();
           if (dbg) { mt1 = clk(); m_waitf += mt1 - mt0; mt0 = mt1; }
-          issue_S(buf, ls);
+          if (el) issue_S(buf, ls);
           if (dbg) { mt1 = clk(); m_s += mt1 - mt0; mt0 = mt1; }
-          umma_commit(smem_u32(&bar_s[buf]));
+          if (el) umma_commit(smem_u32(&bar_s[buf]));
           if (dbg) { mt1 = clk(); m_cm += mt1 - mt0; mt0 = mt1; }
           if (++ls == F3_STAGES) { ls = 0; lph ^= 1u; }
           ++issued;
@@ -362,8 +370,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (++cs == F3_STAGES) cs = 0;
         if (++buf == 3) { buf = 0; ppar ^= 1u; }
       }
-      umma_commit(smem_u32(&bar_o));
-      if (dbg) { atomicAdd(p.dbg + 16, m_waitp); atomicAdd(p.dbg + 17, m_waitf); atomicAdd(p.dbg + 18, 1ull);
+      if (el) umma_commit(smem_u32(&bar_o));
+      if (dbg && el) { atomicAdd(p.dbg + 16, m_waitp); atomicAdd(p.dbg + 17, m_waitf); atomicAdd(p.dbg + 18, 1ull);
                  atomicAdd(p.dbg + 19, m_pv); atomicAdd(p.dbg + 20, m_s); atomicAdd(p.dbg + 21, m_cm); }
     }
   } else {
@@ -539,7 +547,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base, sdO = smem_base + AT_TILE128, sKV = smem_base + 2 * AT_TILE128;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nkb = (p.n_k + 63) / 64;
 
@@ -563,26 +571,32 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = uniform_u32(tmem_slot);
   const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdS = tmem_base + 128, tdQ = tmem_base + 160;
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
+    {
+      if (el) {
       mbar_expect_tx(smem_u32(&bar_q), 2 * AT_TILE128);
-      tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
-      tma_load_4d(sdO, &tmdO, smem_u32(&bar_q), 0, q0, h, b);
+        tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
+        tma_load_4d(sdO, &tmdO, smem_u32(&bar_q), 0, q0, h, b);
+      }
       for (int j = 0; j < nkb; ++j) {
         const int s = j % BWD_STAGES;
         const uint32_t ph = (j / BWD_STAGES) & 1;
         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
         const uint32_t full = smem_u32(&bar_full[s]);
+        if (el) {
         mbar_expect_tx(full, 2 * AT_TILE64);
-        tma_load_4d(sKV + s * 2 * AT_TILE64, &tmK, full, 0, j * 64, h, b);
-        tma_load_4d(sKV + s * 2 * AT_TILE64 + AT_TILE64, &tmV, full, 0, j * 64, h, b);
+          tma_load_4d(sKV + s * 2 * AT_TILE64, &tmK, full, 0, j * 64, h, b);
+          tma_load_4d(sKV + s * 2 * AT_TILE64 + AT_TILE64, &tmV, full, 0, j * 64, h, b);
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool el = elect_one();
+    {
       constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
       constexpr uint32_t idQ = umma_idesc(128, AT_D, 0, 1);
       mbar_wait(smem_u32(&bar_q), 0);
@@ -598,15 +612,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
           umma_bf16(tdP, umma_desc(sdO + k * 32, 16, 1024), umma_desc(sV + k * 32, 16, 1024), idS, k != 0);
-        umma_commit(smem_u32(&bar_s));
+        if (el) umma_commit(smem_u32(&bar_s));
         mbar_wait(smem_u32(&bar_p), j & 1);
         tc_fence_after();
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < 64 / 16; ++k)
-          umma_bf16_ts(tdQ, tdS + k * 8, umma_desc(sK + k * 2048, 8192, 1024), idQ, (j | k) != 0);
-        umma_commit(smem_u32(&bar_empty[s]));
+          for (int k = 0; k < 64 / 16; ++k)
+            umma_bf16_ts(tdQ, tdS + k * 8, umma_desc(sK + k * 2048, 8192, 1024), idQ, (j | k) != 0);
+        }
+        if (el) umma_commit(smem_u32(&bar_empty[s]));
       }
-      umma_commit(smem_u32(&bar_o));
+      if (el) umma_commit(smem_u32(&bar_o));
     }
   } else {
     const int qd = warp & 3;
@@ -675,7 +691,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = smem_base, sV = smem_base + AT_TILE128, sQdO = smem_base + 2 * AT_TILE128;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nqb = (p.n_q + 63) / 64;
 
@@ -700,26 +716,32 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = uniform_u32(tmem_slot);
   const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdV = tmem_base + 128, tdK = tmem_base + 192;
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
+    {
+      if (el) {
       mbar_expect_tx(smem_u32(&bar_kv), 2 * AT_TILE128);
-      tma_load_4d(sK, &tmK, smem_u32(&bar_kv), 0, k0, h, b);
-      tma_load_4d(sV, &tmV, smem_u32(&bar_kv), 0, k0, h, b);
+        tma_load_4d(sK, &tmK, smem_u32(&bar_kv), 0, k0, h, b);
+        tma_load_4d(sV, &tmV, smem_u32(&bar_kv), 0, k0, h, b);
+      }
       for (int i = 0; i < nqb; ++i) {
         const int s = i % BWD_STAGES;
         const uint32_t ph = (i / BWD_STAGES) & 1;
         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
         const uint32_t full = smem_u32(&bar_full[s]);
+        if (el) {
         mbar_expect_tx(full, 2 * AT_TILE64);
-        tma_load_4d(sQdO + s * 2 * AT_TILE64, &tmQ, full, 0, i * 64, h, b);
-        tma_load_4d(sQdO + s * 2 * AT_TILE64 + AT_TILE64, &tmdO, full, 0, i * 64, h, b);
+          tma_load_4d(sQdO + s * 2 * AT_TILE64, &tmQ, full, 0, i * 64, h, b);
+          tma_load_4d(sQdO + s * 2 * AT_TILE64 + AT_TILE64, &tmdO, full, 0, i * 64, h, b);
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool el = elect_one();
+    {
       constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
       constexpr uint32_t idG = umma_idesc(128, AT_D, 0, 1);
       mbar_wait(smem_u32(&bar_kv), 0);
@@ -736,19 +758,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
           umma_bf16(tdP, umma_desc(sV + k * 32, 16, 1024), umma_desc(sdO + k * 32, 16, 1024), idS, k != 0);
-        umma_commit(smem_u32(&bar_s));
+        if (el) umma_commit(smem_u32(&bar_s));
         mbar_wait(smem_u32(&bar_p), i & 1);
         tc_fence_after();
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < 64 / 16; ++k)
-          umma_bf16_ts(tdV, tS + k * 8, umma_desc(sdO + k * 2048, 8192, 1024), idG, (i | k) != 0);
+          for (int k = 0; k < 64 / 16; ++k)
+            umma_bf16_ts(tdV, tS + k * 8, umma_desc(sdO + k * 2048, 8192, 1024), idG, (i | k) != 0);
+        }
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < 64 / 16; ++k)
-          umma_bf16_ts(tdK, tdP + k * 8, umma_desc(sQ + k * 2048, 8192, 1024), idG, (i | k) != 0);
-        umma_commit(smem_u32(&bar_empty[s]));
+          for (int k = 0; k < 64 / 16; ++k)
+            umma_bf16_ts(tdK, tdP + k * 8, umma_desc(sQ + k * 2048, 8192, 1024), idG, (i | k) != 0);
+        }
+        if (el) umma_commit(smem_u32(&bar_empty[s]));
         if (kDrain) umma_commit(smem_u32(&bar_x));
       }
-      umma_commit(smem_u32(&bar_o));
+      if (el) umma_commit(smem_u32(&bar_o));
     }
   } else {
     const int qd = warp & 3;
@@ -822,7 +848,7 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base, sdO = smem_base + AT_TILE128, sKV = smem_base + 2 * AT_TILE128;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nkb = (p.n_k + 63) / 64;
 
@@ -849,26 +875,32 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = uniform_u32(tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
+    {
+      if (el) {
       mbar_expect_tx(smem_u32(&bar_q), 2 * AT_TILE128);
-      tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
-      tma_load_4d(sdO, &tmdO, smem_u32(&bar_q), 0, q0, h, b);
+        tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
+        tma_load_4d(sdO, &tmdO, smem_u32(&bar_q), 0, q0, h, b);
+      }
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nkb; ++j) {
         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
         const uint32_t full = smem_u32(&bar_full[s]);
+        if (el) {
         mbar_expect_tx(full, 2 * AT_TILE64);
-        tma_load_4d(sKV + s * 2 * AT_TILE64, &tmK, full, 0, j * 64, h, b);
-        tma_load_4d(sKV + s * 2 * AT_TILE64 + AT_TILE64, &tmV, full, 0, j * 64, h, b);
+          tma_load_4d(sKV + s * 2 * AT_TILE64, &tmK, full, 0, j * 64, h, b);
+          tma_load_4d(sKV + s * 2 * AT_TILE64 + AT_TILE64, &tmV, full, 0, j * 64, h, b);
+        }
         if (++s == Q3_STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool el = elect_one();
+    {
       constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
       constexpr uint32_t idQ = umma_idesc(128, AT_D, 0, 1);
       auto issue_SdP = [&](int buf, int stage) {
@@ -887,8 +919,8 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (; issued < 3 && issued < nkb; ++issued) {
         mbar_wait(smem_u32(&bar_full[ls]), lph);
         tc_fence_after();
-        issue_SdP(issued, ls);
-        umma_commit(smem_u32(&bar_s[issued]));
+        if (el) issue_SdP(issued, ls);
+        if (el) umma_commit(smem_u32(&bar_s[issued]));
         if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
       }
       int buf = 0, cs = 0;
@@ -899,22 +931,24 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         const uint32_t tdS = tmem_base + buf * 128;
         const uint32_t sK = sKV + cs * 2 * AT_TILE64;
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < 64 / 16; ++k)
-          umma_bf16_ts(tdQ, tdS + k * 8, umma_desc(sK + k * 2048, 8192, 1024), idQ, (j | k) != 0);
-        umma_commit(smem_u32(&bar_empty[cs]));
+          for (int k = 0; k < 64 / 16; ++k)
+            umma_bf16_ts(tdQ, tdS + k * 8, umma_desc(sK + k * 2048, 8192, 1024), idQ, (j | k) != 0);
+        }
+        if (el) umma_commit(smem_u32(&bar_empty[cs]));
         if (issued < nkb) {
           mbar_wait(smem_u32(&bar_full[ls]), lph);
           tc_fence_after();
-          issue_SdP(buf, ls);
-          umma_commit(smem_u32(&bar_s[buf]));
+          if (el) issue_SdP(buf, ls);
+          if (el) umma_commit(smem_u32(&bar_s[buf]));
           if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
           ++issued;
         }
         if (++cs == Q3_STAGES) cs = 0;
         if (++buf == 3) { buf = 0; ppar ^= 1u; }
       }
-      umma_commit(smem_u32(&bar_o));
+      if (el) umma_commit(smem_u32(&bar_o));
     }
   } else {
     const int g = (warp - 2) >> 2;
@@ -990,7 +1024,7 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = smem_base, sV = smem_base + AT_TILE128, sQdO = smem_base + 2 * AT_TILE128;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nqb = (p.n_q + 63) / 64;
 
@@ -1017,26 +1051,32 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = uniform_u32(tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
+    {
+      if (el) {
       mbar_expect_tx(smem_u32(&bar_kv), 2 * AT_TILE128);
-      tma_load_4d(sK, &tmK, smem_u32(&bar_kv), 0, k0, h, b);
-      tma_load_4d(sV, &tmV, smem_u32(&bar_kv), 0, k0, h, b);
+        tma_load_4d(sK, &tmK, smem_u32(&bar_kv), 0, k0, h, b);
+        tma_load_4d(sV, &tmV, smem_u32(&bar_kv), 0, k0, h, b);
+      }
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nqb; ++i) {
         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
         const uint32_t full = smem_u32(&bar_full[s]);
+        if (el) {
         mbar_expect_tx(full, 2 * AT_TILE64);
-        tma_load_4d(sQdO + s * 2 * AT_TILE64, &tmQ, full, 0, i * 64, h, b);
-        tma_load_4d(sQdO + s * 2 * AT_TILE64 + AT_TILE64, &tmdO, full, 0, i * 64, h, b);
+          tma_load_4d(sQdO + s * 2 * AT_TILE64, &tmQ, full, 0, i * 64, h, b);
+          tma_load_4d(sQdO + s * 2 * AT_TILE64 + AT_TILE64, &tmdO, full, 0, i * 64, h, b);
+        }
         if (++s == Q3_STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool el = elect_one();
+    {
       constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
       constexpr uint32_t idG = umma_idesc(128, AT_D, 0, 1);
       auto issue_SdP = [&](int buf, int stage) {
@@ -1055,8 +1095,8 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       for (; issued < 3 && issued < nqb; ++issued) {
         mbar_wait(smem_u32(&bar_full[ls]), lph);
         tc_fence_after();
-        issue_SdP(issued, ls);
-        umma_commit(smem_u32(&bar_s[issued]));
+        if (el) issue_SdP(issued, ls);
+        if (el) umma_commit(smem_u32(&bar_s[issued]));
         if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
       }
       int buf = 0, cs = 0;
@@ -1067,25 +1107,29 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
         tc_fence_after();
         const uint32_t tP = tmem_base + buf * 128, tdS = tP + 64;
         const uint32_t sQb = sQdO + cs * 2 * AT_TILE64, sdOb = sQb + AT_TILE64;
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < 64 / 16; ++k)
-          umma_bf16_ts(tdV, tP + k * 8, umma_desc(sdOb + k * 2048, 8192, 1024), idG, (i | k) != 0);
+          for (int k = 0; k < 64 / 16; ++k)
+            umma_bf16_ts(tdV, tP + k * 8, umma_desc(sdOb + k * 2048, 8192, 1024), idG, (i | k) != 0);
+        }
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < 64 / 16; ++k)
-          umma_bf16_ts(tdK, tdS + k * 8, umma_desc(sQb + k * 2048, 8192, 1024), idG, (i | k) != 0);
-        umma_commit(smem_u32(&bar_empty[cs]));
+          for (int k = 0; k < 64 / 16; ++k)
+            umma_bf16_ts(tdK, tdS + k * 8, umma_desc(sQb + k * 2048, 8192, 1024), idG, (i | k) != 0);
+        }
+        if (el) umma_commit(smem_u32(&bar_empty[cs]));
         if (issued < nqb) {
           mbar_wait(smem_u32(&bar_full[ls]), lph);
           tc_fence_after();
-          issue_SdP(buf, ls);
-          umma_commit(smem_u32(&bar_s[buf]));
+          if (el) issue_SdP(buf, ls);
+          if (el) umma_commit(smem_u32(&bar_s[buf]));
           if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
           ++issued;
         }
         if (++cs == Q3_STAGES) cs = 0;
         if (++buf == 3) { buf = 0; ppar ^= 1u; }
       }
-      umma_commit(smem_u32(&bar_o));
+      if (el) umma_commit(smem_u32(&bar_o));
     }
   } else {
     const int g = (warp - 2) >> 2;

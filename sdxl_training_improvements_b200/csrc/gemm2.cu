@@ -112,8 +112,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_epi = smem_base + G2_STAGES * G2_STAGE_BYTES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const uint32_t rank = uniform_u32(cluster_ctarank());
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int num_tiles = p.tiles_m * p.tiles_n;
@@ -144,11 +144,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = uniform_u32(tmem_slot);
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs): warp-uniform loop, elected lane issues =====================
+    const bool el = elect_one();
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int cv_cend = p.cv_cpb * 64;
@@ -203,20 +204,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait<true>(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full_local = smem_u32(&bar_full[stage]);
-          if (leader) mbar_expect_tx(full_local, 2 * stage_tx);
+          if (leader && el) mbar_expect_tx(full_local, 2 * stage_tx);
           const uint32_t full = mapa_u32(full_local, 0);
           const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
           const uint32_t sb = sa + G2_A_BYTES;
           const int k0 = kb * G2_BK;
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
           if (p.conv == 1) {
-            tma_load_4d_2sm(sa, &tmA, full, c0, cw0 + p.cv_sign * (kw - 1), ch0 + p.cv_sign * (kh - 1), cb);
-            if (!p.b_mn) {
-              tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
-            } else {
+            if (el) {
+              tma_load_4d_2sm(sa, &tmA, full, c0, cw0 + p.cv_sign * (kw - 1), ch0 + p.cv_sign * (kh - 1), cb);
+              if (!p.b_mn) {
+                tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
+              } else {
 #pragma unroll
-              for (int j = 0; j < 2; ++j)
-                if (j < nblk) tma_load_2d_2sm(sb + j * 8192, &tmB, full, tapoff + n_base + 64 * j, c0);
+                for (int j = 0; j < 2; ++j)
+                  if (j < nblk) tma_load_2d_2sm(sb + j * 8192, &tmB, full, tapoff + n_base + 64 * j, c0);
+              }
             }
             c0 += 64;
             if (c0 == cv_cend) {
@@ -226,16 +229,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             continue;
           }
-          if (!p.a_mn) {
-            tma_load_2d_2sm(sa, &tmA, full, k0, m_base);
-          } else {
-            tma_load_2d_2sm(sa, &tmA, full, m_base, k0);
-            tma_load_2d_2sm(sa + 8192, &tmA, full, m_base + 64, k0);
+          if (el) {
+            if (!p.a_mn) {
+              tma_load_2d_2sm(sa, &tmA, full, k0, m_base);
+            } else {
+              tma_load_2d_2sm(sa, &tmA, full, m_base, k0);
+              tma_load_2d_2sm(sa + 8192, &tmA, full, m_base + 64, k0);
+            }
           }
           if (p.conv == 2) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              if (j < nblk) tma_load_4d_2sm(sb + j * 8192, &tmB, full, tapc[j], pw0 + tdw[j], ph0 + tdh[j], pb);
+              if (j < nblk && el) tma_load_4d_2sm(sb + j * 8192, &tmB, full, tapc[j], pw0 + tdw[j], ph0 + tdh[j], pb);
             if (p.cv_W >= 64) {
               pw0 += 64;
               if (pw0 == p.cv_W) { pw0 = 0; ++ph0; }
@@ -244,18 +249,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             if (ph0 == cv_H) { ph0 = 0; ++pb; }
           } else if (!p.b_mn) {
-            tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
+            if (el) tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
           } else {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              if (j < nblk) tma_load_2d_2sm(sb + j * 8192, &tmB, full, n_base + 64 * j, k0);
+              if (j < nblk && el) tma_load_2d_2sm(sb + j * 8192, &tmB, full, n_base + 64 * j, k0);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, one thread) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA): warp-uniform loop, elected lane issues =====================
+    const bool el = elect_one();
+    if (leader) {
       const uint32_t idesc = umma_idesc(256, p.BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? 8192 : 16, a_kstep = p.a_mn ? 2048 : 32;
       const uint32_t b_lbo = p.b_mn ? 8192 : 16, b_kstep = p.b_mn ? 2048 : 32;
@@ -277,13 +283,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait<true>(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();
           const uint64_t so = (uint64_t)((uint32_t)(stage * G2_STAGE_BYTES) >> 4);
+          if (el) {
 #pragma unroll
-          for (int k = 0; k < G2_BK / 16; ++k)
-            umma_bf16_2sm(tacc, adesc0 + so + k * a_k16, bdesc0 + so + k * b_k16, idesc, ((kb - kb0) | k) != 0);
-          umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);
+            for (int k = 0; k < G2_BK / 16; ++k)
+              umma_bf16_2sm(tacc, adesc0 + so + k * a_k16, bdesc0 + so + k * b_k16, idesc, ((kb - kb0) | k) != 0);
+            umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);
+          }
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_2sm(smem_u32(&bar_acc_full[buf]), 3);
+        if (el) umma_commit_2sm(smem_u32(&bar_acc_full[buf]), 3);
       }
     }
   } else {

@@ -81,6 +81,29 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
+// warp-uniform issue
+//   UTMALDG / UTCHMMA / UTCBAR take their operands from UNIFORM registers.  If the issuing code sits inside a
+//   `lane == 0` branch the compiler must assume the operands diverge and wraps every instruction in a waterfall loop
+//   (ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY, ~60 cycles of a lone thread's time per MMA) — measured: 12 MMAs + 3 commits
+//   per attention key block cost ~1000 cycles of issue time against 512 cycles of tensor work.  The producer / issuer
+//   warps therefore run their loops warp-uniformly (all 32 lanes wait on the barriers) and only the asm statement is
+//   predicated on elect_one(); values that come from special registers or shared memory are laundered through
+//   uniform_u32() so the compiler can keep them in uniform registers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// ---------------------------------------------------------------------------------------------
 // cluster
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
