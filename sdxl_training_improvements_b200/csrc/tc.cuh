@@ -70,8 +70,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
       if (now - t0 > 4000000000ull) {  // 4 s
-        printf("libsdxl_b200: mbarrier wait timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x,
-               blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+        if ((threadIdx.x & 31) == 0)
+          printf("libsdxl_b200: mbarrier wait timeout (grid %d,%d,%d block %d,%d,%d threads %d warp %d bar %u parity %u)\n",
+                 gridDim.x, gridDim.y, gridDim.z, blockIdx.x, blockIdx.y, blockIdx.z, blockDim.x, threadIdx.x >> 5, bar,
+                 parity);
         __trap();
       }
     }

@@ -78,10 +78,10 @@ def test_attention_fwd_bwd(B, H, n_q, n_k, fused, gain):
         assert torch.isfinite(got.float()).all(), name
         e = _rel(_heads(got, B, n, H), ref)
         assert e <= 2e-2, f"{name} rel-L2 {e}"
-    # A/B: the issue-order WAR assumption of the dK/dV kernel vs an explicit pipe drain must agree bit for bit
-    dk2, dv2, dq2 = torch.empty_like(dk.contiguous()), torch.empty_like(dv.contiguous()), torch.empty_like(dq.contiguous())
-    ops.attn_bwd(q, k, v, o, lse, do, dq2, dk2, dv2, B, H, n_q, n_k, scale, flags=1)
-    assert torch.equal(dk2, dk.contiguous()) and torch.equal(dv2, dv.contiguous())
+    # determinism: the kernels have no atomics and a fixed block order -> a second run is bit-identical
+    dq2, dk2, dv2 = torch.empty_like(dq.contiguous()), torch.empty_like(dk.contiguous()), torch.empty_like(dv.contiguous())
+    ops.attn_bwd(q, k, v, o, lse, do, dq2, dk2, dv2, B, H, n_q, n_k, scale)
+    assert torch.equal(dq2, dq.contiguous()) and torch.equal(dk2, dk.contiguous()) and torch.equal(dv2, dv.contiguous())
     torch.cuda.synchronize()
 
 
