@@ -507,7 +507,7 @@ static G2Plan gemm2_plan(int M, int N, int K, int b_mn, int num_clusters, bool m
            ((splits > 1 && needs_zero_fill) ? 3000.0 : 0.0);
   };
   double best_cost = unit_cost(best.bn, 1, num_kb);
-  static const int cand[] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
+  static const int cand[] = {2, 3, 4, 5, 6, 8, 10, 12, 16};  // every split adds one bf16 rounding of the running sum
   for (int bn = 256; bn >= 128; bn -= 64) {
     if (b_mn && (bn & 127)) continue;
     if (bn > 128 && bn - 64 >= N) continue;

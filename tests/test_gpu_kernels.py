@@ -167,7 +167,7 @@ def test_gemm_split_k_gradients(ops, M, N, K):
     ops.linear_dgrad(dy, W, dx, accumulate=False)
     sdx = float(ref_dx.abs().max())
     _close(dx, ref_dx, atol=3e-2 + 2 ** -6 * sdx, what="split-K dgrad")
-    assert float((dx.float() - ref_dx).norm() / ref_dx.norm()) <= 4e-3
+    assert float((dx.float() - ref_dx).norm() / ref_dx.norm()) <= 8e-3
     ops.linear_dgrad(dy, W, dx, accumulate=True)
     _close(dx, 2 * ref_dx, rtol=2 ** -6, atol=6e-2 + 2 ** -5 * sdx, what="split-K dgrad accumulate")
     ref_dw = dy.float().t() @ x.float()
@@ -176,11 +176,12 @@ def test_gemm_split_k_gradients(ops, M, N, K):
     scale = float(ref_dw.abs().max())
     # elementwise bound: each of up to 32 bf16 partials carries 2^-9 of ITS magnitude; aggregate bound: rel-L2
     _close(dW, ref_dw, rtol=2 ** -6, atol=2 ** -6 * scale, what="split-K wgrad")
-    assert float((dW.float() - ref_dw).norm() / ref_dw.norm()) <= 4e-3
+    # s reduce-adds round the running bf16 total s times: rel-L2 ~ sqrt(s) * 2^-9 / sqrt(3), s <= 16
+    assert float((dW.float() - ref_dw).norm() / ref_dw.norm()) <= 8e-3
     dW1 = torch.zeros_like(dW)
     ops.gemm_raw(dy, x, dW1, N, K, M, a_mn=True, b_mn=True, lda=N, ldb=K, ldd=K, allow_split_k=False)
     _close(dW, dW1, rtol=2 ** -6, atol=2 ** -6 * scale, what="split vs unsplit")
-    assert float((dW.float() - dW1.float()).norm() / dW1.float().norm()) <= 4e-3
+    assert float((dW.float() - dW1.float()).norm() / dW1.float().norm()) <= 8e-3
     ops.linear_wgrad(dy, x, dW, accumulate=True)
     _close(dW, 2 * ref_dw, rtol=2 ** -5, atol=2 ** -5 * scale, what="split-K wgrad accumulate")
     torch.cuda.synchronize()
