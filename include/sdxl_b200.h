@@ -196,6 +196,16 @@ int b2_copy2d_any(const void* src, void* dst, int64_t rows, int64_t cols, int64_
 int b2_colsum(const void* dy, void* db, int64_t M, int N, int64_t ld, int accumulate, float* ws /* float[N] */,
               void* stream);                                                                  /* db[n] (+)= sum_m dy[m,n] */
 int b2_accum_f32_to_bf16(const float* src, void* dst, int64_t n, int accumulate, void* stream);
+/* Small-parameter gradients (biases, norm scale / shift; replaces the autograd bias / affine gradient reductions):
+ *   b2_colsum_f32: out[n] += sum_m dy[m,n] with fp32 atomics into a staging buffer (no zero-fill, no conversion);
+ *   b2_flush_small_grads: for every segment (staging offset, gradient offset, length; int64 triples on the device)
+ *   grad_bf16[dst + i] += staging[src + i], then staging is cleared — one launch per backward pass. */
+int b2_colsum_f32(const void* dy, float* out, int64_t M, int N, int64_t ld, void* stream);
+/* out[g, n] (+)= sum over the rows of group g (rows [g*rows_per_group, (g+1)*rows_per_group)) of dy[m, n]; out bf16
+ * [groups, N] dense.  The per-sample gradient of ResnetBlock2D's time-embedding row (conv1 epilogue bias). */
+int b2_colsum_groups(const void* dy, void* out, int groups, int64_t rows_per_group, int N, int64_t ld, int accumulate,
+                     float* ws /* float[groups*N] */, void* stream);
+int b2_flush_small_grads(float* staging, void* grad_bf16, const int64_t* segments, int nseg, void* stream);
 int b2_nchw_to_nhwc(const void* x, int x_fp32, void* y, int B, int C, int HW, int Cpad, void* stream);
 int b2_nhwc_to_nchw(const void* x, void* y, int y_fp32, int B, int C, int HW, int Cpad, void* stream);
 

@@ -77,6 +77,9 @@ SIGNATURES = {
     "b2_copy2d_any": [c_p, c_p, i64, i64, i64, i64, i32, c_p],
     "b2_colsum": [c_p, c_p, i64, i32, i64, i32, c_p, c_p],
     "b2_accum_f32_to_bf16": [c_p, c_p, i64, i32, c_p],
+    "b2_colsum_f32": [c_p, c_p, i64, i32, i64, c_p],
+    "b2_colsum_groups": [c_p, c_p, i32, i64, i32, i64, i32, c_p, c_p],
+    "b2_flush_small_grads": [c_p, c_p, c_p, i32, c_p],
     "b2_nchw_to_nhwc": [c_p, i32, c_p, i32, i32, i32, i32, c_p],
     "b2_nhwc_to_nchw": [c_p, c_p, i32, i32, i32, i32, i32, c_p],
     "b2_timestep_embedding": [c_p, c_p, i32, i32, i64, c_p],

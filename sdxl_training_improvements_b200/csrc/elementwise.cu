@@ -49,9 +49,30 @@ __global__ void softmax_bwd_kernel(const bf16* __restrict__ P, const float* __re
 }
 
 // ---------------------------------------------------------------- GEGLU
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (diffusers GEGLU uses F.gelu, not the tanh form).  erff() costs ~25 instructions and made these
+// kernels ALU-bound (41 / 53 us for 126 / 210 MB); Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, far below one bf16
+// ulp of the product) needs one reciprocal, five FMAs and ONE exponential — exp(-x^2/2) — which is also the Gaussian
+// density the derivative needs:   Phi(x) = (1 + erf(x/sqrt2)) / 2,   gelu' = Phi + x * phi.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));  // exp(-x^2 / 2)
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
+                              0.254829592f);
+  const float erf_abs = fmaf(-poly, e, 1.f);
+  cdf = 0.5f * (1.f + copysignf(erf_abs, x));
+  pdf = 0.3989422804014327f * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float c, d;
+  gelu_parts(x, c, d);
+  return x * c;
+}
 __device__ __forceinline__ float dgelu_erf(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  float c, d;
+  gelu_parts(x, c, d);
+  return fmaf(x, d, c);
 }
 
 __global__ void geglu_fwd_kernel(const bf16* __restrict__ u, bf16* __restrict__ z, long long M, int F) {
@@ -82,8 +103,10 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ u, const bf16* __restr
     unpack8(ld8(dz + m * F + c), d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      dh[j] = d[j] * gelu_erf(g[j]);
-      dg[j] = d[j] * h[j] * dgelu_erf(g[j]);
+      float cdf, pdf;
+      gelu_parts(g[j], cdf, pdf);
+      dh[j] = d[j] * g[j] * cdf;
+      dg[j] = d[j] * h[j] * fmaf(g[j], pdf, cdf);
     }
     st8(du + m * 2 * F + c, pack8(dh));
     st8(du + m * 2 * F + F + c, pack8(dg));
@@ -152,6 +175,8 @@ __global__ void copy2d_any_kernel(const bf16* __restrict__ src, bf16* __restrict
 __global__ void colsum_kernel(const bf16* __restrict__ dy, float* ws, long long M, int N, long long ld,
                               long long rows_per_cta) {
   __shared__ float sm[32][65];
+  dy += (long long)blockIdx.z * M * ld;  // row groups (per-sample sums): group z = rows [z*M, (z+1)*M), output row z
+  ws += (long long)blockIdx.z * N;
   const int cv = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int c0 = blockIdx.x * 64 + cv * 8;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
@@ -179,6 +204,24 @@ __global__ void colsum_kernel(const bf16* __restrict__ dy, float* ws, long long 
     for (int r = 0; r < 32; ++r) t += sm[r][threadIdx.x];
     const int gc = blockIdx.x * 64 + threadIdx.x;
     if (gc < N) atomicAdd(&ws[gc], t);
+  }
+}
+
+// Small-parameter gradient staging (biases, norm scales / shifts): every producer kernel accumulates into ONE fp32 buffer
+// with atomics during the backward pass; this kernel folds each segment into the flat bf16 gradient buffer (+=, which is
+// what gradient accumulation needs) and clears the staging area for the next micro-step.  Replaces ~1,650 tiny launches
+// per step (a zero-fill + an fp32->bf16 accumulate per tensor).
+__global__ void flush_small_grads_kernel(float* __restrict__ src, bf16* __restrict__ dst, const long long* __restrict__ seg,
+                                         int nseg) {
+  for (int sgi = blockIdx.x; sgi < nseg; sgi += gridDim.x) {
+    const long long so = seg[3 * sgi], d0 = seg[3 * sgi + 1], n = seg[3 * sgi + 2];
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = src[so + i];
+      if (v != 0.f) {
+        dst[d0 + i] = __float2bfloat16(__bfloat162float(dst[d0 + i]) + v);
+        src[so + i] = 0.f;
+      }
+    }
   }
 }
 
@@ -311,6 +354,40 @@ extern "C" int b2_colsum(const void* dy, void* db, int64_t M, int N, int64_t ld,
   if (rc) return rc;
   accum_f32_to_bf16_kernel<<<ew_blocks(N, 256), 256, 0, st>>>(ws, (bf16*)db, N, accumulate);
   return check_launch("colsum_finish");
+}
+extern "C" int b2_colsum_groups(const void* dy, void* out, int groups, int64_t rows_per_group, int N, int64_t ld,
+                                int accumulate, float* ws, void* stream) {
+  B2_REQUIRE(dy && out && ws && groups > 0 && groups <= 65535 && rows_per_group > 0 && N > 0, "b2_colsum_groups: bad args");
+  B2_REQUIRE(ld % 8 == 0 && !((uintptr_t)dy & 15), "b2_colsum_groups: needs 16-byte aligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)N * groups, st);
+  const int colblocks = (N + 63) / 64;
+  long long rows_per_cta = (rows_per_group * colblocks * groups + 2LL * num_sms() - 1) / (2LL * num_sms());
+  if (rows_per_cta < 256) rows_per_cta = 256;
+  const int rchunks = (int)((rows_per_group + rows_per_cta - 1) / rows_per_cta);
+  colsum_kernel<<<dim3(colblocks, rchunks, groups), 256, 0, st>>>((const bf16*)dy, ws, rows_per_group, N, ld, rows_per_cta);
+  int rc = check_launch("colsum_groups");
+  if (rc) return rc;
+  accum_f32_to_bf16_kernel<<<ew_blocks((long long)N * groups, 256), 256, 0, st>>>(ws, (bf16*)out, (long long)N * groups,
+                                                                                 accumulate);
+  return check_launch("colsum_groups_finish");
+}
+extern "C" int b2_colsum_f32(const void* dy, float* out, int64_t M, int N, int64_t ld, void* stream) {
+  B2_REQUIRE(dy && out && M > 0 && N > 0, "b2_colsum_f32: bad args");
+  B2_REQUIRE(ld % 8 == 0 && !((uintptr_t)dy & 15), "b2_colsum_f32: needs 16-byte aligned rows");
+  const int colblocks = (N + 63) / 64;
+  long long rows_per_cta = (M * colblocks + 2LL * num_sms() - 1) / (2LL * num_sms());
+  if (rows_per_cta < 256) rows_per_cta = 256;
+  const int rchunks = (int)((M + rows_per_cta - 1) / rows_per_cta);
+  colsum_kernel<<<dim3(colblocks, rchunks), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, out, M, N, ld, rows_per_cta);
+  return check_launch("colsum_f32");
+}
+extern "C" int b2_flush_small_grads(float* staging, void* grad_bf16, const int64_t* segments, int nseg, void* stream) {
+  B2_REQUIRE(staging && grad_bf16 && segments && nseg > 0, "b2_flush_small_grads: bad args");
+  int blocks = nseg < 4 * num_sms() ? nseg : 4 * num_sms();
+  flush_small_grads_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(staging, (bf16*)grad_bf16,
+                                                                     (const long long*)segments, nseg);
+  return check_launch("flush_small_grads");
 }
 extern "C" int b2_nchw_to_nhwc(const void* x, int x_fp32, void* y, int B, int C, int HW, int Cpad, void* stream) {
   B2_REQUIRE(x && y && Cpad >= C, "b2_nchw_to_nhwc: bad args");

@@ -291,6 +291,25 @@ def colsum(dy, db, accumulate=True):
     return db
 
 
+def colsum_groups(dy, out, groups, rows_per_group, accumulate=False):
+    """out[g, :] (+)= column sums of rows [g*rows_per_group, (g+1)*rows_per_group) of dy; out bf16 [groups, N]."""
+    N = dy.shape[1]
+    ws = torch.empty(groups * N, device=dy.device, dtype=torch.float32)
+    _lib.check(_lib.load().b2_colsum_groups(_p(dy), _p(out), int(groups), int(rows_per_group), N, dy.stride(0),
+                                           int(accumulate), _p(ws), _stream()), "colsum_groups")
+    return out
+
+
+def colsum_f32(dy, out32):
+    """out32[n] += sum_m dy[m, n]  (fp32 staging slice; see ParamStore.small32)."""
+    M, N = dy.shape
+    _lib.check(_lib.load().b2_colsum_f32(_p(dy), _p(out32), M, N, dy.stride(0), _stream()), "colsum_f32")
+
+
+def flush_small_grads(staging, grad, segments, nseg):
+    _lib.check(_lib.load().b2_flush_small_grads(_p(staging), _p(grad), _p(segments), int(nseg), _stream()), "flush_small_grads")
+
+
 def accum_f32_to_bf16(src, dst, accumulate=True):
     _lib.check(_lib.load().b2_accum_f32_to_bf16(_p(src), _p(dst), src.numel(), int(accumulate), _stream()), "accum")
     return dst

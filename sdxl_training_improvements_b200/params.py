@@ -132,6 +132,22 @@ class ParamStore:
         self.numel = sum(int(torch.Size(s).numel()) for _, s in self.specs)
         self.flat = torch.zeros(self.total, dtype=torch.bfloat16, device=device)
         self.grad = torch.zeros(self.total, dtype=torch.bfloat16, device=device)
+        # fp32 staging for the gradients of the small (1-D) parameters — biases and norm scale / shift: kernels accumulate
+        # into it with atomics, `flush_small_grads()` folds it into `grad` once per backward pass.  Same order as the
+        # specs, so a norm's (weight, bias) pair is one contiguous [2C] slice.
+        self.small_off: Dict[str, int] = {}
+        so = 0
+        segs = []
+        for name, shape in self.specs:
+            if len(shape) == 1:
+                self.small_off[name] = so
+                segs += [so, self.offsets[name], int(shape[0])]
+                so += (int(shape[0]) + 3) // 4 * 4
+        self.small_total = so
+        self.small32 = torch.zeros(max(so, 4), dtype=torch.float32, device=device)
+        self._small_segs_host = torch.tensor(segs, dtype=torch.int64)
+        self.small_segs = self._small_segs_host.to(device)
+        self.n_small = len(segs) // 3
         self.params: "OrderedDict[str, torch.nn.Parameter]" = OrderedDict()
         self._build_views()
 
@@ -154,6 +170,8 @@ class ParamStore:
     def to(self, device):
         self.flat = self.flat.to(device)
         self.grad = self.grad.to(device)
+        self.small32 = self.small32.to(device)
+        self.small_segs = self._small_segs_host.to(device)
         self._build_views()
         return self
 
@@ -171,6 +189,15 @@ class ParamStore:
         off = self.offsets[name]
         n = int(torch.Size(dict(self.specs)[name]).numel()) if False else self._numel[name]
         return self.flat[off:off + n]
+
+    def gs(self, name: str, n: int = 0) -> torch.Tensor:
+        """fp32 staging slice of a small parameter's gradient (n > 0: span `n` floats, e.g. a norm's weight+bias pair)."""
+        off = self.small_off[name]
+        return self.small32[off:off + (n or self._numel[name])]
+
+    def flush_small_grads(self):
+        from . import ops
+        ops.flush_small_grads(self.small32, self.grad, self.small_segs, self.n_small)
 
     def gv(self, name: str) -> torch.Tensor:
         off = self.offsets[name]

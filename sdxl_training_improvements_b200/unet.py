@@ -97,9 +97,11 @@ class UNetEngine:
         self.ws("dcol", maxcol, bf16)
 
     # ------------------------------------------------------------------ primitive layers
-    def _pgrad_norm(self, dgb: torch.Tensor, wname: str, bname: str, Cc: int):
-        ops.accum_f32_to_bf16(dgb[:Cc], self.store.gv(wname), True)
-        ops.accum_f32_to_bf16(dgb[Cc:], self.store.gv(bname), True)
+    def _norm_dgb(self, wname: str, bname: str, Cc: int) -> torch.Tensor:
+        """fp32 [2C] staging slice the norm backward kernels accumulate (dgamma | dbeta) into."""
+        st = self.store
+        assert st.small_off[bname] == st.small_off[wname] + Cc, "norm weight / bias must be adjacent in the staging buffer"
+        return st.gs(wname, 2 * Cc)
 
     def linear(self, x: Act, wname: str, N: int, K: int, bname: Optional[str] = None, residual: Optional[Act] = None,
                need_dx: bool = True, res_ld0: Optional[torch.Tensor] = None) -> Act:
@@ -118,7 +120,7 @@ class UNetEngine:
             dy = out.g
             ops.linear_wgrad(dy, x.d, st.g(wname, N, K), accumulate=True)
             if bname:
-                ops.colsum(dy, st.gv(bname), accumulate=True)
+                ops.colsum_f32(dy, st.gs(bname))
             if need_dx:
                 buf, acc = _gslot(x)
                 ops.linear_dgrad(dy, Wt, buf, acc)
@@ -142,10 +144,8 @@ class UNetEngine:
         out = Act(ops.gn_apply(x.d, mean, rstd, gamma, beta, B, HW, Cc, G, silu))
 
         def bwd():
-            dgb = torch.zeros(2 * Cc, device=x.d.device, dtype=torch.float32)
             buf, acc = _gslot(x)
-            ops.gn_bwd(x.d, out.g, mean, rstd, gamma, beta, B, HW, Cc, G, silu, dgb, buf, acc)
-            self._pgrad_norm(dgb, wname, bname, Cc)
+            ops.gn_bwd(x.d, out.g, mean, rstd, gamma, beta, B, HW, Cc, G, silu, self._norm_dgb(wname, bname, Cc), buf, acc)
 
         self.tape.append(bwd)
         return out
@@ -157,10 +157,8 @@ class UNetEngine:
         out = Act(y)
 
         def bwd():
-            dgb = torch.zeros(2 * Cc, device=x.d.device, dtype=torch.float32)
             buf, acc = _gslot(x)
-            ops.ln_bwd(x.d, out.g, gamma, mean, rstd, dgb, buf, acc)
-            self._pgrad_norm(dgb, wname, bname, Cc)
+            ops.ln_bwd(x.d, out.g, gamma, mean, rstd, self._norm_dgb(wname, bname, Cc), buf, acc)
 
         self.tape.append(bwd)
         return out
@@ -210,11 +208,9 @@ class UNetEngine:
                     acc = False
                 else:
                     acc = True
-                hw = Ho * Wo
-                for b in range(B):
-                    ops.colsum(dy[b * hw:(b + 1) * hw], rowbias.g[b], accumulate=acc)
+                ops.colsum_groups(dy, rowbias.g, B, Ho * Wo, accumulate=acc)
             elif bias_t is None:
-                ops.colsum(dy, st.gv(bname), accumulate=True)
+                ops.colsum_f32(dy, st.gs(bname))
             if need_dx:
                 buf, acc = _gslot(x)
                 if implicit:
@@ -266,7 +262,7 @@ class UNetEngine:
         h1 = self.conv3x3(a1, B, H, W, Cin, Cout, f"{pfx}.conv1.weight", f"{pfx}.conv1.bias", rowbias=tproj)
 
         def conv1_bias_grad():  # d conv1.bias = sum over samples of d tproj
-            ops.colsum(tproj.g, st.gv(f"{pfx}.conv1.bias"), accumulate=True)
+            ops.colsum_f32(tproj.g, st.gs(f"{pfx}.conv1.bias"))
 
         # runs after conv1's backward (which fills tproj.g) and before the time_emb_proj linear's backward
         self.tape.insert(len(self.tape) - 1, conv1_bias_grad)
@@ -472,6 +468,7 @@ class UNetEngine:
         for fn in reversed(tape):
             fn()
         tape.clear()
+        self.store.flush_small_grads()  # biases / norm affine: fp32 staging -> flat bf16 gradient buffer (+=)
 
 
 class _UNetFunction(torch.autograd.Function):

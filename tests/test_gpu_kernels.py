@@ -411,3 +411,29 @@ def test_adamw_and_sumsq(ops):
         opt.step()
     _close(master, ref_p.detach(), rtol=1e-5, atol=1e-6, what="adamw master")
     assert torch.equal(p, master.to(bf16))
+
+
+def test_small_grad_staging_and_group_colsum(ops):
+    """fp32 staging path of the bias / norm-affine gradients and the per-sample (grouped) column sum."""
+    dy = _rand(3 * 200, 320, seed=50)
+    out = torch.zeros(3, 320, device="cuda", dtype=bf16)
+    ops.colsum_groups(dy, out, 3, 200, accumulate=False)
+    ref = dy.float().view(3, 200, 320).sum(1)
+    _close(out, ref, rtol=1e-2, atol=5e-2, what="colsum_groups")
+    ops.colsum_groups(dy, out, 3, 200, accumulate=True)
+    _close(out, 2 * ref, rtol=2e-2, atol=1e-1, what="colsum_groups accumulate")
+    st = torch.zeros(1000, device="cuda", dtype=torch.float32)
+    ops.colsum_f32(dy, st[40:360])
+    ops.colsum_f32(dy, st[40:360])
+    _close(st[40:360], 2 * dy.float().sum(0), rtol=1e-5, atol=1e-3, what="colsum_f32 accumulates")
+    assert float(st[:40].abs().sum()) == 0 and float(st[360:].abs().sum()) == 0
+    grad = _rand(5000, seed=51)
+    g0 = grad.clone()
+    segs = torch.tensor([40, 1000, 320, 600, 16, 8], device="cuda", dtype=torch.int64)  # (src, dst, n) triples
+    st[600:608] = 3.0
+    ops.flush_small_grads(st, grad, segs, 2)
+    exp = g0.float().clone()
+    exp[1000:1320] += 2 * dy.float().sum(0)
+    exp[16:24] += 3.0
+    _close(grad, exp, rtol=2 ** -7, atol=2e-2, what="flush_small_grads")
+    assert float(st.abs().sum()) == 0.0, "staging must be cleared by the flush"
