@@ -10,7 +10,8 @@
 // helpers compute in fp32 and round with SR(x) = (bits(x) + rand16) & 0xFFFF0000.
 //
 // Traffic: reads p, g, m, v, shift and writes p, m, v, shift = 18 B / parameter (46 GB for the SDXL UNet), HBM-bound.
-// Random bits: Philox4x32-10, 64 bits per element (4 roundings x 16 bits), counter = element-pair index, key = seed,
+// Random bits: Philox4x32-7 (the 7-round variant is Crush-resistant; the kernel is ALU-co-bound, every round is ~10 integer
+// instructions per element pair), 64 bits per element (4 roundings x 16 bits), counter = element-pair index, key = seed,
 // stream = optimizer step — reproducible and independent of the launch geometry.
 #include "common.cuh"
 
@@ -19,7 +20,7 @@ namespace b2 {
 struct pu4 { uint32_t x, y, z, w; };
 __device__ __forceinline__ pu4 philox_opt(pu4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 7; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = pu4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
@@ -88,37 +89,52 @@ adamw_bf16_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __rest
     a.step_size = (float)(-a.lr * sqrt(1.0 - pow(a.b2d, (double)step)));
   }
   const long long nv = n >> 3;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += (long long)gridDim.x * blockDim.x) {
-    float fp[8], fg[8], fm[8], fv[8], fs[8];
-    unpack8(ld8(p + q * 8), fp);
-    unpack8(ld8(g + q * 8), fg);
-    unpack8(ld8(m + q * 8), fm);
-    unpack8(ld8(v + q * 8), fv);
-    unpack8(ld8(sh + q * 8), fs);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // two 16-byte vectors per array in flight per thread (10 independent loads): the loop is latency-bound otherwise
+  for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < nv; q0 += 2 * stride) {
+    bf16x8 vp[2], vg[2], vm[2], vv[2], vs[2];
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      pu4 r;
-      if (a.rng_mode == 0) {
-        const uint64_t ctr = (uint64_t)q * 4 + h;
-        r = philox_opt(pu4{(uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)step, (uint32_t)(step >> 32)}, k0, k1);
-      } else if (a.rng_mode == 3) {
-        const long long e = q * 8 + 2 * h;
-        r.x = (uint32_t)test_rand16[e] | ((uint32_t)test_rand16[n + e] << 16);
-        r.y = (uint32_t)test_rand16[2 * n + e] | ((uint32_t)test_rand16[3 * n + e] << 16);
-        r.z = (uint32_t)test_rand16[e + 1] | ((uint32_t)test_rand16[n + e + 1] << 16);
-        r.w = (uint32_t)test_rand16[2 * n + e + 1] | ((uint32_t)test_rand16[3 * n + e + 1] << 16);
-      } else {
-        const uint32_t f = a.rng_mode == 1 ? 0u : 0xffffffffu;
-        r = pu4{f, f, f, f};
+    for (int u = 0; u < 2; ++u) {
+      const long long q = q0 + u * stride;
+      if (q < nv) {
+        vp[u] = ld8(p + q * 8); vg[u] = ld8(g + q * 8); vm[u] = ld8(m + q * 8); vv[u] = ld8(v + q * 8); vs[u] = ld8(sh + q * 8);
       }
-      adam_bf16_elem(fp[2 * h], fg[2 * h], fm[2 * h], fv[2 * h], fs[2 * h], a, clip, r.x, r.y);
-      adam_bf16_elem(fp[2 * h + 1], fg[2 * h + 1], fm[2 * h + 1], fv[2 * h + 1], fs[2 * h + 1], a, clip, r.z, r.w);
     }
-    // values are exact bf16 (low 16 bits zero): packing is a truncation, not a second rounding
-    st8(p + q * 8, pack8(fp));
-    st8(m + q * 8, pack8(fm));
-    st8(v + q * 8, pack8(fv));
-    st8(sh + q * 8, pack8(fs));
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long q = q0 + u * stride;
+      if (q >= nv) break;
+      float fp[8], fg[8], fm[8], fv[8], fs[8];
+      unpack8(vp[u], fp);
+      unpack8(vg[u], fg);
+      unpack8(vm[u], fm);
+      unpack8(vv[u], fv);
+      unpack8(vs[u], fs);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        pu4 r;
+        if (a.rng_mode == 0) {
+          const uint64_t ctr = (uint64_t)q * 4 + h;
+          r = philox_opt(pu4{(uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)step, (uint32_t)(step >> 32)}, k0, k1);
+        } else if (a.rng_mode == 3) {
+          const long long e = q * 8 + 2 * h;
+          r.x = (uint32_t)test_rand16[e] | ((uint32_t)test_rand16[n + e] << 16);
+          r.y = (uint32_t)test_rand16[2 * n + e] | ((uint32_t)test_rand16[3 * n + e] << 16);
+          r.z = (uint32_t)test_rand16[e + 1] | ((uint32_t)test_rand16[n + e + 1] << 16);
+          r.w = (uint32_t)test_rand16[2 * n + e + 1] | ((uint32_t)test_rand16[3 * n + e + 1] << 16);
+        } else {
+          const uint32_t f = a.rng_mode == 1 ? 0u : 0xffffffffu;
+          r = pu4{f, f, f, f};
+        }
+        adam_bf16_elem(fp[2 * h], fg[2 * h], fm[2 * h], fv[2 * h], fs[2 * h], a, clip, r.x, r.y);
+        adam_bf16_elem(fp[2 * h + 1], fg[2 * h + 1], fm[2 * h + 1], fv[2 * h + 1], fs[2 * h + 1], a, clip, r.z, r.w);
+      }
+      // values are exact bf16 (low 16 bits zero): packing is a truncation, not a second rounding
+      st8(p + q * 8, pack8(fp));
+      st8(m + q * 8, pack8(fm));
+      st8(v + q * 8, pack8(fv));
+      st8(sh + q * 8, pack8(fs));
+    }
   }
   // tail (n % 8 elements), one thread
   if (blockIdx.x == 0 && threadIdx.x == 0) {
