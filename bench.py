@@ -200,6 +200,54 @@ def _cpu_baseline(seconds_budget=30.0, threads=None):
                          f"model build {build_s:.0f} s untimed"}, one
 
 
+def _torch_eager_gpu_baseline(B, H, W, steps=2):
+    """The reference's own GPU path on this box: the oracle module tree (= diffusers' UNet2DConditionModel restated) in
+    PyTorch eager bf16 on cuda:0 -> cuDNN convs, cuBLASLt linears, SDPA attention, autograd backward, + MSE loss.  No
+    optimizer step is timed here (the reference's AdamWBF16 is ~20 eager kernels per tensor), so this flatters it."""
+    from oracle.unet_sdxl import OracleUNet
+    try:
+        with torch.device("meta"):
+            m = OracleUNet()
+        m = m.to(torch.bfloat16).to_empty(device="cuda")
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.dim() >= 2:
+                    p.uniform_(-0.02, 0.02)
+                else:
+                    p.fill_(0.5)
+        x = torch.randn(B, 4, H, W, device="cuda", dtype=torch.bfloat16)
+        ctx = torch.randn(B, 77, 2048, device="cuda", dtype=torch.bfloat16)
+        pooled = torch.randn(B, 1280, device="cuda", dtype=torch.bfloat16)
+        tid = torch.tensor([[8.0 * W, 8.0 * H, 0, 0, 8.0 * W, 8.0 * H]], device="cuda").repeat(B, 1)
+        t = torch.randint(0, 1000, (B,), device="cuda")
+        tgt = torch.randn(B, 4, H, W, device="cuda", dtype=torch.bfloat16)
+
+        def step():
+            out = m(x, t, ctx, added_cond_kwargs={"text_embeds": pooled, "time_ids": tid}).sample
+            torch.nn.functional.mse_loss(out, tgt).backward()
+
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res = {"value": round(B / (ms * 1e-3), 3), "unit": "images/s", "ms_per_step": round(ms, 1),
+               "what": f"oracle UNet (diffusers module tree) in PyTorch eager bf16 on the same GPU, fwd+bwd+MSE, B={B}, "
+                       "no optimizer step"}
+    except Exception as e:  # noqa: BLE001  (an OOM here must not lose the main measurement)
+        res = {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
+    finally:
+        m = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -248,6 +296,9 @@ def run_ours(args):
     peaks = _peaks()
     B, H, W = 4, 128, 128
     cfg = _config_ns(args.method)
+    eager = None
+    if world == 1 and not args.no_eager_baseline:
+        eager = _torch_eager_gpu_baseline(B, H, W)
     unet = B200UNet(device=f"cuda:{local}")
     _init_weights_(unet, seed=1234)  # identical on every rank (replicated parameters)
     if args.optimizer == "adamw_bf16":  # the reference's default (src/config.yaml: optimizer_type adamw_bf16)
@@ -356,7 +407,8 @@ def run_ours(args):
                        "d2h_bytes_per_step": 4 + 6 * 8, "ms_per_step": round(ms_e2e, 2),
                        "api": "B200DDPMTrainer._execute_training_step(batch) with pinned host tensors"
                               + (" (cuda_graph=True)" if use_graph else "")},
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb}
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
+               "torch_eager_gpu": eager}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -370,6 +422,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--method", default="ddpm", choices=["ddpm", "flow_matching"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU oracle timing")
     ap.add_argument("--optimizer", default="adamw_bf16", choices=["adamw_bf16", "adamw_fp32"])
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of CUDA graphs")
     args = ap.parse_args()

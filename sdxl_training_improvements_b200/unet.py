@@ -579,6 +579,51 @@ class B200UNet:
             json.dump({"_class_name": "UNet2DConditionModel", **{k: (list(v) if isinstance(v, tuple) else v)
                                                                 for k, v in self.config.items()}}, f, indent=1)
 
+    @classmethod
+    def from_pretrained(cls, path, device="cuda", subfolder: Optional[str] = None, **kw):
+        """Load a diffusers-format UNet directory (what `StableDiffusionXL.save_pretrained` writes per component,
+        src/models/sdxl.py:246-288, and what `StableDiffusionXLPipeline.from_pretrained(...).unet` reads,
+        src/models/sdxl.py:25-40): `config.json` + `diffusion_pytorch_model.safetensors` (single file or sharded with
+        `diffusion_pytorch_model.safetensors.index.json`) or `.bin`.  Weights are diffusers' logical layout (conv OIHW,
+        Linear [out, in]); ParamStore re-lays them out (channels-last conv taps, adjacent q/k/v) on the way in."""
+        import json
+        import os
+        root = os.path.join(path, subfolder) if subfolder else path
+        cfg = dict(SDXL_BASE)
+        cj = os.path.join(root, "config.json")
+        if os.path.exists(cj):
+            with open(cj) as f:
+                disk = json.load(f)
+            if "num_heads" not in disk and "attention_head_dim" in disk:  # diffusers names the head COUNT this way
+                disk["num_heads"] = disk["attention_head_dim"]
+            if "transformer_layers_per_block" in disk and "down_block_types" in disk:
+                tl = disk["transformer_layers_per_block"]
+                tl = [tl] * len(disk["down_block_types"]) if isinstance(tl, int) else list(tl)
+                disk["transformer_layers_per_block"] = [t if "CrossAttn" in b else 0
+                                                        for t, b in zip(tl, disk["down_block_types"])]
+            for k in cfg:
+                if k in disk:
+                    cfg[k] = tuple(disk[k]) if isinstance(disk[k], list) else disk[k]
+        net = cls(cfg, device=device)
+        st_single = os.path.join(root, "diffusion_pytorch_model.safetensors")
+        st_index = st_single + ".index.json"
+        sd = {}
+        if os.path.exists(st_single):
+            from safetensors.torch import load_file
+            sd = load_file(st_single)
+        elif os.path.exists(st_index):
+            from safetensors.torch import load_file
+            with open(st_index) as f:
+                shards = sorted(set(json.load(f)["weight_map"].values()))
+            for sh in shards:
+                sd.update(load_file(os.path.join(root, sh)))
+        elif os.path.exists(os.path.join(root, "diffusion_pytorch_model.bin")):
+            sd = torch.load(os.path.join(root, "diffusion_pytorch_model.bin"), map_location="cpu")
+        else:
+            raise FileNotFoundError(f"no diffusion_pytorch_model.(safetensors|bin) under {root}")
+        net.load_state_dict(sd, strict=True)
+        return net
+
     # --- forward ---
     def __call__(self, sample, timestep, encoder_hidden_states=None, added_cond_kwargs=None, **kw):
         if added_cond_kwargs is None:
