@@ -185,7 +185,20 @@ __global__ void colsum_kernel(const bf16* __restrict__ dy, float* ws, long long 
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (c0 + 8 <= N) {
-    for (long long r = r0 + rl; r < r1; r += 32) {
+    // four independent 16-byte loads in flight per thread: with one, the kernel is bound by DRAM latency x trip count
+    long long r = r0 + rl;
+    for (; r + 96 < r1; r += 128) {
+      const bf16x8 v0 = ld8(dy + r * ld + c0), v1 = ld8(dy + (r + 32) * ld + c0), v2 = ld8(dy + (r + 64) * ld + c0),
+                   v3 = ld8(dy + (r + 96) * ld + c0);
+      float f0[8], f1[8], f2[8], f3[8];
+      unpack8(v0, f0);
+      unpack8(v1, f1);
+      unpack8(v2, f2);
+      unpack8(v3, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+    }
+    for (; r < r1; r += 32) {
       float f[8];
       unpack8(ld8(dy + r * ld + c0), f);
 #pragma unroll
@@ -362,8 +375,8 @@ extern "C" int b2_colsum_groups(const void* dy, void* out, int groups, int64_t r
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)N * groups, st);
   const int colblocks = (N + 63) / 64;
-  long long rows_per_cta = (rows_per_group * colblocks * groups + 2LL * num_sms() - 1) / (2LL * num_sms());
-  if (rows_per_cta < 256) rows_per_cta = 256;
+  long long rows_per_cta = (rows_per_group * colblocks * groups + 4LL * num_sms() - 1) / (4LL * num_sms());
+  rows_per_cta = (rows_per_cta + 127) / 128 * 128;
   const int rchunks = (int)((rows_per_group + rows_per_cta - 1) / rows_per_cta);
   colsum_kernel<<<dim3(colblocks, rchunks, groups), 256, 0, st>>>((const bf16*)dy, ws, rows_per_group, N, ld, rows_per_cta);
   int rc = check_launch("colsum_groups");
@@ -376,8 +389,8 @@ extern "C" int b2_colsum_f32(const void* dy, float* out, int64_t M, int N, int64
   B2_REQUIRE(dy && out && M > 0 && N > 0, "b2_colsum_f32: bad args");
   B2_REQUIRE(ld % 8 == 0 && !((uintptr_t)dy & 15), "b2_colsum_f32: needs 16-byte aligned rows");
   const int colblocks = (N + 63) / 64;
-  long long rows_per_cta = (M * colblocks + 2LL * num_sms() - 1) / (2LL * num_sms());
-  if (rows_per_cta < 256) rows_per_cta = 256;
+  long long rows_per_cta = (M * colblocks + 4LL * num_sms() - 1) / (4LL * num_sms());
+  rows_per_cta = (rows_per_cta + 127) / 128 * 128;  // whole 4-deep load groups
   const int rchunks = (int)((M + rows_per_cta - 1) / rows_per_cta);
   colsum_kernel<<<dim3(colblocks, rchunks), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, out, M, N, ld, rows_per_cta);
   return check_launch("colsum_f32");

@@ -559,6 +559,10 @@ static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
     p.kb_per = (p.K + G2_BK - 1) / G2_BK;
   }
   if (p.splits > 1) p.has_res = 0;  // the reduce-add epilogue is the accumulation
+  static const bool log_calls = getenv("B2_GEMM_LOG") != nullptr;
+  if (log_calls)
+    fprintf(stderr, "B2GEMM %s M=%d N=%d K=%d a_mn=%d b_mn=%d conv=%d BN=%d splits=%d bias=%d res=%d\n", what, p.M, p.N, p.K,
+            p.a_mn, p.b_mn, p.conv, p.BN, p.splits, p.bias != nullptr, p.has_res);
   const long long tiles = (long long)p.tiles_m * p.tiles_n * p.splits;
   const int clusters = (int)(tiles < num_clusters ? tiles : num_clusters);
   gemm2_kernel<<<dim3(2 * clusters), G2_THREADS, G2_SMEM, st>>>(ta, tb, td, tr, p);
@@ -621,10 +625,6 @@ int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc) {
   if (plan.splits > 1 && !a->accumulate) {
     if ((rc = gemm2_zero_fill(a->D, a->ldd, a->M, a->N, st))) { *out_rc = rc; return 1; }
   }
-  static const bool log_calls = getenv("B2_GEMM_LOG") != nullptr;
-  if (log_calls)
-    fprintf(stderr, "B2GEMM M=%d N=%d K=%d a_mn=%d b_mn=%d BN=%d splits=%d bias=%d res=%d acc=%d\n", a->M, a->N, a->K, p.a_mn,
-            p.b_mn, bn, plan.splits, a->bias != nullptr, a->residual != nullptr, a->accumulate);
   *out_rc = gemm2_launch(ta, tb, td, tr, p, st, "b2_gemm(pair)");
   return 1;
 }
