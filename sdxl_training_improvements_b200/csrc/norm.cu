@@ -300,6 +300,112 @@ __global__ void ln_bwd_dx_kernel(const bf16* __restrict__ x, const bf16* __restr
   }
 }
 
+// Register-resident LayerNorm rows: one warp per row, each lane keeps its NV 16-byte vectors of the row (C <= 256 * NV)
+// in registers, so x (and dy) are read from memory exactly once; the generic kernels above re-read the row per pass.
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_fwd_reg_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ gamma,
+                  const bf16* __restrict__ beta, float* __restrict__ mean, float* __restrict__ rstd, int M, int C,
+                  float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  const int nvec = C >> 3;
+  const bf16* xr = x + (size_t)row * C;
+  float f[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      unpack8(ld8(xr + v * 8), f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[i][j];
+    }
+  }
+  s = warp_sum(s);
+  const float mu = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mu;
+        q += d * d;
+      }
+    }
+  q = warp_sum(q);
+  const float rs = rsqrtf(q / (float)C + eps);
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+  bf16* yr = y + (size_t)row * C;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float g[8], b[8];
+      unpack8(ld8(gamma + v * 8), g);
+      unpack8(ld8(beta + v * 8), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[i][j] = (f[i][j] - mu) * rs * g[j] + b[j];
+      st8(yr + v * 8, pack8(f[i]));
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_bwd_dx_reg_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                     const bf16* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, int M,
+                     int C, int accumulate) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  const int nvec = C >> 3;
+  const bf16* xr = x + (size_t)row * C;
+  const bf16* dr = dy + (size_t)row * C;
+  const float mu = mean[row], rs = rstd[row];
+  float xh[NV][8], dg[NV][8];
+  float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float d[8], g[8];
+      unpack8(ld8(xr + v * 8), xh[i]);
+      unpack8(ld8(dr + v * 8), d);
+      unpack8(ld8(gamma + v * 8), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[i][j] = (xh[i][j] - mu) * rs;
+        dg[i][j] = d[j] * g[j];
+        c1 += dg[i][j];
+        c2 += dg[i][j] * xh[i][j];
+      }
+    }
+  }
+  c1 = warp_sum(c1) / (float)C;
+  c2 = warp_sum(c2) / (float)C;
+  bf16* oxr = dx + (size_t)row * C;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float o[8];
+      if (accumulate) unpack8(ld8(oxr + v * 8), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float r_ = rs * (dg[i][j] - c1 - xh[i][j] * c2);
+        o[j] = accumulate ? o[j] + r_ : r_;
+      }
+      st8(oxr + v * 8, pack8(o));
+    }
+  }
+}
+
 // dgamma[c] += sum_m dy*xhat, dbeta[c] += sum_m dy.  CTA = 64 columns x a chunk of rows; 8 column-vectors x 32 rows.
 __global__ void ln_bwd_dgb_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ mean,
                                   const float* __restrict__ rstd, float* dgb, int M, int C, int rows_per_cta) {
@@ -398,8 +504,19 @@ extern "C" int b2_ln_fwd(const void* x, void* y, const void* gamma, const void* 
                          int C, float eps, void* stream) {
   B2_REQUIRE(x && y && gamma && beta && mean && rstd, "b2_ln_fwd: null pointer");
   B2_REQUIRE(C % 8 == 0, "b2_ln_fwd: C %% 8 != 0");
-  ln_fwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, (const bf16*)gamma,
-                                                               (const bf16*)beta, mean, rstd, M, C, eps);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nv = (C / 8 + 31) / 32;
+#define B2_LN_FWD(NV)                                                                                              \
+  ln_fwd_reg_kernel<NV><<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, (bf16*)y, (const bf16*)gamma, (const bf16*)beta, \
+                                                     mean, rstd, M, C, eps)
+  if (nv <= 2) B2_LN_FWD(2);
+  else if (nv <= 3) B2_LN_FWD(3);
+  else if (nv <= 5) B2_LN_FWD(5);
+  else if (nv <= 8) B2_LN_FWD(8);
+  else
+    ln_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, (bf16*)y, (const bf16*)gamma, (const bf16*)beta, mean, rstd,
+                                               M, C, eps);
+#undef B2_LN_FWD
   return check_launch("ln_fwd");
 }
 
@@ -408,8 +525,17 @@ extern "C" int b2_ln_bwd(const void* x, const void* dy, void* dx, const void* ga
   B2_REQUIRE(x && dy && dx && gamma && mean && rstd && dgb, "b2_ln_bwd: null pointer");
   B2_REQUIRE(C % 8 == 0, "b2_ln_bwd: C %% 8 != 0");
   cudaStream_t st = (cudaStream_t)stream;
-  ln_bwd_dx_kernel<<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, (const bf16*)gamma, mean,
-                                                rstd, M, C, accumulate_dx);
+  const int nv = (C / 8 + 31) / 32;
+#define B2_LN_BWD(NV)                                                                                                 \
+  ln_bwd_dx_reg_kernel<NV><<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, (const bf16*)gamma, \
+                                                        mean, rstd, M, C, accumulate_dx)
+  if (nv <= 2) B2_LN_BWD(2);
+  else if (nv <= 3) B2_LN_BWD(3);
+  else if (nv <= 5) B2_LN_BWD(5);
+  else
+    ln_bwd_dx_kernel<<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, (const bf16*)gamma, mean,
+                                                  rstd, M, C, accumulate_dx);
+#undef B2_LN_BWD
   int rc = check_launch("ln_bwd_dx");
   if (rc) return rc;
   const int colblocks = (C + 63) / 64;
