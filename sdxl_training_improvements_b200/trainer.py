@@ -287,7 +287,8 @@ def _prep_batch(batch: Dict[str, Any], device) -> Dict[str, torch.Tensor]:
 def _tag_weight_mean(batch) -> Optional[float]:
     """ddpm_trainer.py:348-368: mean over samples of the mean tag weight, if every sample has weights."""
     md = batch.get("metadata")
-    if isinstance(md, (list, tuple)) and md and all(isinstance(m, dict) and "tag_info" in m for m in md):
+    if isinstance(md, (list, tuple)) and md and all(isinstance(m, dict) and isinstance(m.get("tag_info"), dict)
+                                                     and "tags" in m["tag_info"] for m in md):
         ws = []
         for m in md:
             iw = [td["weight"] for tags in m["tag_info"]["tags"].values() for td in tags]
