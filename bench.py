@@ -294,8 +294,10 @@ def run_ours(args):
     from sdxl_training_improvements_b200.unet import B200UNet
 
     peaks = _peaks()
-    B, H, W = 4, 128, 128
+    B, H, W = 4, args.latent_h, args.latent_w
+    A = max(1, args.accum)  # micro-steps per optimizer step (config 5: grad-accum 4)
     cfg = _config_ns(args.method)
+    cfg.training.gradient_accumulation_steps = A
     eager = None
     if world == 1 and not args.no_eager_baseline:
         eager = _torch_eager_gpu_baseline(B, H, W)
@@ -316,8 +318,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up through the public plugin API (also JITs nothing: all kernels are prebuilt) ----
+    def api_step():
+        for a in range(A):
+            loss, metrics = trainer._execute_training_step(batch, accumulate=A > 1, is_last_accumulation_step=a == A - 1)
+        return loss, metrics
+
     for _ in range(max(args.warmup, 3)):
-        trainer._execute_training_step(batch)
+        api_step()
     barrier()
 
     # ---- (1) device-resident timing: `value` ----
@@ -327,12 +334,12 @@ def run_ours(args):
     sched = trainer.noise_scheduler if args.method == "ddpm" else None
     gen = torch.Generator().manual_seed(5 + rank)
     if args.method == "ddpm":
-        ts = [sched.sample_timesteps(B, generator=gen) for _ in range(K)]
+        ts = [sched.sample_timesteps(B, generator=gen) for _ in range(K * A)]
         t_embed = [t.float().cuda() for t in ts]
         sig = [sched.timestep_to_sigma(t).float().cuda() for t in ts]
     else:
         from sdxl_training_improvements_b200.trainer import sample_logit_normal
-        ts = [sample_logit_normal((B,), generator=gen) for _ in range(K)]
+        ts = [sample_logit_normal((B,), generator=gen) for _ in range(K * A)]
         t_embed = [t.float().cuda() for t in ts]
         sig = t_embed
     core = trainer.core
@@ -346,15 +353,18 @@ def run_ours(args):
     e0.record()
     for i in range(K):
         if use_graph:  # one graph launch per micro-step, one per optimizer step; inputs already resident in HBM
-            gm.load(dev_batch["latents"], dev_batch["ctx"], dev_batch["pooled"], dev_batch["time_ids"], t_embed[i], sig[i])
-            gm.replay()
+            for a in range(A):
+                gm.load(dev_batch["latents"], dev_batch["ctx"], dev_batch["pooled"], dev_batch["time_ids"],
+                        t_embed[i * A + a], sig[i * A + a], None, 1.0 / A)
+                gm.replay()
             if world > 1:
                 allreduce_gradients(unet)
             og.replay()
         else:
-            core.step_no_autograd(latents=dev_batch["latents"], ctx=dev_batch["ctx"], pooled=dev_batch["pooled"],
-                                  time_ids=dev_batch["time_ids"], t_embed=t_embed[i], sig_or_t=sig[i], weight=None,
-                                  loss_scale=1.0)
+            for a in range(A):
+                core.step_no_autograd(grad_scale=1.0 / A, latents=dev_batch["latents"], ctx=dev_batch["ctx"],
+                                      pooled=dev_batch["pooled"], time_ids=dev_batch["time_ids"], t_embed=t_embed[i * A + a],
+                                      sig_or_t=sig[i * A + a], weight=None, loss_scale=1.0)
             if world > 1:
                 allreduce_gradients(unet)
             opt.fused_step(max_norm=1.0, grad_scale=1.0 / world)
@@ -363,7 +373,7 @@ def run_ours(args):
     barrier()
     launches = _lib.launch_count() - launches0
     if use_graph:
-        launches = K * (gm.launches_per_replay + og.launches_per_replay)
+        launches = K * (A * gm.launches_per_replay + og.launches_per_replay)
     ms_dev = e0.elapsed_time(e1) / K
 
     # ---- (2) end-to-end through the plugin API with host buffers: `e2e` ----
@@ -372,7 +382,7 @@ def run_ours(args):
     e2.record()
     last_loss = None
     for i in range(K):
-        loss, metrics = trainer._execute_training_step(batch)
+        loss, metrics = api_step()
         last_loss = metrics["loss"]  # python float: the D2H read of the step's result already happened
     e3.record()
     barrier()
@@ -385,9 +395,9 @@ def run_ours(args):
         ms_dev, ms_e2e = float(t[0]), float(t[1])
 
     if rank == 0:
-        step_flops = train_step_flops(None, H, W) * B
-        value = world * B / (ms_dev * 1e-3)
-        e2e_v = world * B / (ms_e2e * 1e-3)
+        step_flops = train_step_flops(None, H, W) * B * A
+        value = world * B * A / (ms_dev * 1e-3)
+        e2e_v = world * B * A / (ms_e2e * 1e-3)
         roof = _time_gemm_roofline(ops, peaks)
         roof["step_tflops_per_gpu"] = round(step_flops / (ms_dev * 1e-3) / 1e12, 1)
         roof["step_frac_of_sustained_peak"] = round(step_flops / (ms_dev * 1e-3) / 1e12 / peaks["sustained"], 4)
@@ -397,14 +407,15 @@ def run_ours(args):
         out = {"metric": METRIC, "value": round(value, 4), "unit": "images/s", "n_gpus": world, "steps": K,
                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev, 2), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-               "config": {"workload": f"SDXL-base UNet, {args.method} v_prediction, bs=4/GPU, 1024^2 (latent 128x128), "
+               "config": {"workload": f"SDXL-base UNet, {args.method} v_prediction, bs=4/GPU, {8 * W}x{8 * H} (latent {H}x{W}), "
+                                      + (f"grad-accum {A}, " if A > 1 else "") +
                                       f"bf16, full fwd+bwd+loss+clip+{args.optimizer} (configs[1])",
                           "cuda_graph": use_graph,
-                          "global_batch": B * world, "parallelism": f"dp{world}",
+                          "global_batch": B * world * A, "parallelism": f"dp{world}",
                           "l2": "working set >> L2: 5.1 GB of weights + ~40 GB activations streamed every step",
                           "last_loss": last_loss},
-               "e2e": {"value": round(e2e_v, 4), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
-                       "d2h_bytes_per_step": 4 + 6 * 8, "ms_per_step": round(ms_e2e, 2),
+               "e2e": {"value": round(e2e_v, 4), "unit": "images/s", "h2d_bytes_per_step": int(h2d) * A,
+                       "d2h_bytes_per_step": (4 + 6 * 8) * A, "ms_per_step": round(ms_e2e, 2),
                        "api": "B200DDPMTrainer._execute_training_step(batch) with pinned host tensors"
                               + (" (cuda_graph=True)" if use_graph else "")},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
@@ -421,6 +432,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--method", default="ddpm", choices=["ddpm", "flow_matching"])
+    ap.add_argument("--latent-h", type=int, default=128, help="latent height (image / 8); default 128 = 1024 px")
+    ap.add_argument("--latent-w", type=int, default=128)
+    ap.add_argument("--accum", type=int, default=1, help="gradient-accumulation micro-steps per optimizer step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU oracle timing")
     ap.add_argument("--optimizer", default="adamw_bf16", choices=["adamw_bf16", "adamw_fp32"])
