@@ -30,6 +30,10 @@ constexpr int G2_A_BYTES = 128 * G2_BK * 2;        // 16 KiB: this CTA's 128 row
 constexpr int G2_STAGE_BYTES = 2 * G2_A_BYTES;     // A + up to 128 rows of B
 constexpr int G2_EPI_BYTES = 128 * 64 * 2;         // one 128 x 64 bf16 staging tile
 constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 2 * G2_EPI_BYTES + 1024;
+constexpr int G2_WIDE_BN = 320;
+constexpr int G2_WIDE_STAGES = 5;
+constexpr int G2_WIDE_STAGE_BYTES = G2_A_BYTES + (G2_WIDE_BN / 2) * G2_BK * 2;  // 16 KiB A + 20 KiB B half
+static_assert(G2_WIDE_STAGES * G2_WIDE_STAGE_BYTES + 2 * G2_EPI_BYTES + 1024 <= G2_SMEM, "wide mode must fit the same smem budget");
 constexpr int G2_TMEM_COLS = 512;
 
 struct Gemm2P {
@@ -60,6 +64,12 @@ struct Gemm2P {
   // its epilogue adds the bf16 partial into D with a TMA reduce (cp.reduce.async.bulk.tensor .add), so units of one
   // tile may run concurrently on different clusters.  D must hold the value to accumulate onto (zeros if none).
   int splits, kb_per;
+  // wide mode (BN = 320): one 256 x 320 tile per CTA pair issued as two N = 160 UMMAs per k-step into a single-buffered
+  // 320-column accumulator.  Used when it turns "80 tiles on 74 clusters" (N = 1280 at M = 4096: two rounds, the second
+  // 8 % full) into 64 tiles in ONE round; each CTA stages its B half as two 80-row boxes so that accumulator columns
+  // stay in natural order.
+  int wide;
+  int stages, stage_bytes;
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
@@ -111,7 +121,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_epi = smem_base + G2_STAGES * G2_STAGE_BYTES;
+  const uint32_t smem_epi = smem_base + p.stages * p.stage_bytes;
   const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const uint32_t rank = uniform_u32(cluster_ctarank());
   const bool leader = rank == 0;
@@ -160,6 +170,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int mb = t % p.tiles_m, nb = t / p.tiles_m;
         const int m_base = mb * 256 + (int)rank * 128;
         const int n_base = nb * p.BN + (int)rank * halfn;
+        const int n_wide = nb * p.BN + (int)rank * 80;  // wide mode: rows [n_wide, +80) and [n_wide + 160, +80)
         // Implicit-conv address state.  Everything below is strength-reduced to counters: this loop runs on ONE
         // thread and must issue a k-block's TMAs in well under the k-block's MMA time (256..512 cycles); runtime
         // integer divisions here (~40 dependent instructions each) made the first version producer-bound.
@@ -206,15 +217,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t full_local = smem_u32(&bar_full[stage]);
           if (leader && el) mbar_expect_tx(full_local, 2 * stage_tx);
           const uint32_t full = mapa_u32(full_local, 0);
-          const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
           const uint32_t sb = sa + G2_A_BYTES;
           const int k0 = kb * G2_BK;
-          if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           if (p.conv == 1) {
             if (el) {
               tma_load_4d_2sm(sa, &tmA, full, c0, cw0 + p.cv_sign * (kw - 1), ch0 + p.cv_sign * (kh - 1), cb);
               if (!p.b_mn) {
-                tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
+                if (p.wide) {
+                  tma_load_2d_2sm(sb, &tmB, full, k0, n_wide);
+                  tma_load_2d_2sm(sb + 10240, &tmB, full, k0, n_wide + 160);
+                } else {
+                  tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
+                }
               } else {
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
@@ -249,7 +265,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             if (ph0 == cv_H) { ph0 = 0; ++pb; }
           } else if (!p.b_mn) {
-            if (el) tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
+            if (el) {
+              if (p.wide) {
+                tma_load_2d_2sm(sb, &tmB, full, k0, n_wide);
+                tma_load_2d_2sm(sb + 10240, &tmB, full, k0, n_wide + 160);
+              } else {
+                tma_load_2d_2sm(sb, &tmB, full, k0, n_base);
+              }
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
@@ -262,7 +285,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================== MMA issuer (leader CTA): warp-uniform loop, elected lane issues =====================
     const bool el = elect_one();
     if (leader) {
-      const uint32_t idesc = umma_idesc(256, p.BN, p.a_mn, p.b_mn);
+      const uint32_t idesc = umma_idesc(256, p.wide ? 160 : p.BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? 8192 : 16, a_kstep = p.a_mn ? 2048 : 32;
       const uint32_t b_lbo = p.b_mn ? 8192 : 16, b_kstep = p.b_mn ? 2048 : 32;
       // descriptors differ between stages / k-steps only in their 14-bit start-address field: one add each
@@ -282,14 +305,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait<true>(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();
-          const uint64_t so = (uint64_t)((uint32_t)(stage * G2_STAGE_BYTES) >> 4);
+          const uint64_t so = (uint64_t)((uint32_t)(stage * p.stage_bytes) >> 4);
           if (el) {
+            if (p.wide) {
 #pragma unroll
-            for (int k = 0; k < G2_BK / 16; ++k)
-              umma_bf16_2sm(tacc, adesc0 + so + k * a_k16, bdesc0 + so + k * b_k16, idesc, ((kb - kb0) | k) != 0);
+              for (int k = 0; k < G2_BK / 16; ++k) {
+                const uint32_t acc = ((kb - kb0) | k) != 0;
+                umma_bf16_2sm(tacc, adesc0 + so + k * a_k16, bdesc0 + so + k * b_k16, idesc, acc);
+                umma_bf16_2sm(tacc + 160, adesc0 + so + k * a_k16, bdesc0 + so + k * b_k16 + (10240 >> 4), idesc, acc);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < G2_BK / 16; ++k)
+                umma_bf16_2sm(tacc, adesc0 + so + k * a_k16, bdesc0 + so + k * b_k16, idesc, ((kb - kb0) | k) != 0);
+            }
             umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);
           }
-          if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         if (el) umma_commit_2sm(smem_u32(&bar_acc_full[buf]), 3);
       }
@@ -489,6 +521,17 @@ int gemm2_pick_bn(int M, int N, int K, int b_mn, int num_clusters) {
   return best;
 }
 
+// 256 x 320 single-round tiles: K-major B only, N a multiple of 320, every tile gets its own cluster, and the best
+// <= 256-wide plan needs at least two rounds.
+static bool gemm2_use_wide(int M, int N, int b_mn, int bn_narrow, int num_clusters) {
+  static const bool off = getenv("B2_GEMM_NOWIDE") != nullptr;
+  if (off || b_mn || N % G2_WIDE_BN) return false;
+  const long long tiles_m = (M + 255) / 256;
+  if (tiles_m * (N / G2_WIDE_BN) > num_clusters) return false;
+  const long long narrow_tiles = tiles_m * ((N + bn_narrow - 1) / bn_narrow);
+  return narrow_tiles > num_clusters;
+}
+
 struct G2Plan { int bn, splits, kb_per; };
 
 // Tile width + K split for a gradient GEMM.  Model: a unit costs kb_per * tile_cost(bn) + a fixed hand-over bubble;
@@ -558,6 +601,9 @@ static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
     p.splits = 1;
     p.kb_per = (p.K + G2_BK - 1) / G2_BK;
   }
+  p.wide = p.BN == G2_WIDE_BN ? 1 : 0;
+  p.stages = p.wide ? G2_WIDE_STAGES : G2_STAGES;
+  p.stage_bytes = p.wide ? G2_WIDE_STAGE_BYTES : G2_STAGE_BYTES;
   if (p.splits > 1) p.has_res = 0;  // the reduce-add epilogue is the accumulation
   static const bool log_calls = getenv("B2_GEMM_LOG") != nullptr;
   if (log_calls)
@@ -585,8 +631,9 @@ int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc) {
   const int num_clusters = num_sms() / 2;
   const bool may_split = a->allow_split_k && !a->bias && !a->residual && a->alpha == 1.f;
   const G2Plan plan = gemm2_plan(a->M, a->N, a->K, a->b_mn, num_clusters, may_split, !a->accumulate);
-  const int bn = plan.bn;
-  if (bn < 32 || bn > 256 || (bn & 15) || (a->b_mn && (bn & 127))) {
+  int bn = plan.bn;
+  if (plan.splits == 1 && gemm2_use_wide(a->M, a->N, a->b_mn, bn, num_clusters)) bn = G2_WIDE_BN;
+  if (bn != G2_WIDE_BN && (bn < 32 || bn > 256 || (bn & 15) || (a->b_mn && (bn & 127)))) {
     set_error("b2_gemm: bad BN %d", bn);
     *out_rc = B2_ERR_ARG;
     return 1;
@@ -599,7 +646,7 @@ int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc) {
     rc = make_map_2d(&ta, a->A, a->M, a->K, a->lda, 64, 64, "A(mn)");
   if (rc) { *out_rc = rc; return 1; }
   if (!a->b_mn)
-    rc = make_map_2d(&tb, a->B, a->K, a->N, a->ldb, 64, bn / 2, "B");
+    rc = make_map_2d(&tb, a->B, a->K, a->N, a->ldb, 64, bn == G2_WIDE_BN ? 80 : bn / 2, "B");
   else
     rc = make_map_2d(&tb, a->B, a->N, a->K, a->ldb, 64, 64, "B(mn)");
   if (rc) { *out_rc = rc; return 1; }
@@ -700,8 +747,9 @@ extern "C" int b2_conv3x3(const b2_conv3x3_args* a, void* stream) {
     p.M = (int)pixels; p.N = Cout; p.K = 9 * Cin;
     p.a_mn = 0; p.b_mn = 0; p.conv = 1; p.cv_sign = 1; p.cv_cpb = Cin / 64;
     p.BN = gemm2_pick_bn(p.M, p.N, p.K, 0, num_clusters);
+    if (gemm2_use_wide(p.M, p.N, 0, p.BN, num_clusters)) p.BN = G2_WIDE_BN;
     if ((rc = make_map_conv(&ta, a->x, B, H, W, Cin, ldx, 128, "conv x"))) return rc;
-    if ((rc = make_map_2d(&tb, a->w, 9ull * Cin, Cout, ldw, 64, p.BN / 2, "conv w"))) return rc;
+    if ((rc = make_map_2d(&tb, a->w, 9ull * Cin, Cout, ldw, 64, p.BN == G2_WIDE_BN ? 80 : p.BN / 2, "conv w"))) return rc;
     if ((rc = make_map_2d(&td, a->y, Cout, pixels, ldy, 64, 128, "conv y"))) return rc;
     if (a->residual) {
       const long long ldr = a->ldr > 0 ? a->ldr : Cout;

@@ -47,6 +47,8 @@ GEMM_SHAPES = [
     (308, 640, 2048),     # cross-attn K/V projection (B*77 rows)
     (1024, 64, 1024),     # N = 64 tile
     (16384, 8, 2880),     # conv_out (Cout padded to 8)
+    (4000, 1280, 192),    # wide 256x320 single-round tiles, ragged M, short K (3 k-blocks < ring depth)
+    (4096, 1280, 5120),   # wide tiles, long K (ff2 forward)
 ]
 
 
