@@ -85,22 +85,22 @@ def test_flow_timestep_and_state_dict_surface():
     assert sum(p.numel() for p in net.parameters()) == sum(p.numel() for p in ref.parameters())
 
 
-def test_fullsize_sdxl_unet_forward_backward_vs_oracle_cuda_eager():
-    """T4 at the REAL size (2.57 B parameters, SDXL-base config, latent 64x64, B=1): the kernel UNet vs the oracle module
-    tree in PyTorch eager bf16 on the same GPU, identical weights / inputs.  Both sides compute in bf16, so the bars are
-    the bf16 noise floor measured by tools/fullsize_check.py (forward 0.5 %, aggregate gradient 0.5 %, worst tensor 2 %):
-    forward rel-L2 <= 2e-2, aggregate parameter-gradient rel-L2 <= 1.5e-2, every tensor with a non-negligible gradient
-    <= 6e-2.  Exercises what the tiny config cannot: split-K plans, 1280-channel implicit convs, n = 4096 / 1024
-    attention with 10 / 20 heads, 77-key cross-attention kernels, the 10-deep transformer stacks."""
+def test_fullsize_sdxl_unet_forward_backward_vs_oracle():
+    """T4 at the REAL size (2.57 B parameters, SDXL-base config, latent 64x64, B=1), identical weights / inputs:
+      * truth      = the oracle module tree in fp32 (CUDA),
+      * yardstick  = the same oracle in PyTorch eager bf16 (what the reference's diffusers path computes on a GPU),
+      * candidate  = the kernel UNet (bf16 activations, fp32 accumulation).
+    Bars: forward rel-L2 vs fp32 <= 2e-2; aggregate parameter-gradient rel-L2 vs fp32 <= max(1.5e-2, 2 x yardstick's);
+    every tensor with a non-negligible gradient <= max(6e-2, 2.5 x the yardstick's error on that tensor) — random-init
+    attention is peaky in the deep blocks and bf16 noise on dS is amplified there for ANY bf16 implementation.
+    Exercises what the tiny config cannot: split-K plans, wide tiles, 1280-channel implicit convs, 10 / 20-head attention,
+    77-key cross-attention kernels, the 10-deep transformer stacks."""
     import bench
     from oracle.unet_sdxl import OracleUNet
     from sdxl_training_improvements_b200.unet import B200UNet
     net = B200UNet(device="cuda")
     bench._init_weights_(net, 1234)
-    with torch.device("meta"):
-        ref = OracleUNet()
-    ref = ref.to_empty(device="cuda").to(bf16)
-    ref.load_state_dict({k: v.to(bf16) for k, v in net.state_dict().items()})
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     B, H, W = 1, 64, 64
     g = torch.Generator(device="cuda").manual_seed(3)
     x = (torch.randn(B, 4, H, W, device="cuda", generator=g) * 3).to(bf16)
@@ -111,23 +111,42 @@ def test_fullsize_sdxl_unet_forward_backward_vs_oracle_cuda_eager():
     wgt = torch.randn(B, 4, H, W, device="cuda", generator=g)
     ko = net(x, t, ctx, added_cond_kwargs={"text_embeds": pooled, "time_ids": tid}).sample
     (ko.float() * wgt).sum().backward()
-    ro = ref(x, t, ctx, added_cond_kwargs={"text_embeds": pooled, "time_ids": tid}).sample
-    (ro.float() * wgt).sum().backward()
-    assert torch.isfinite(ko.float()).all()
-    e = _rel(ko.detach(), ro.detach())
-    assert e <= 2e-2, f"full-size forward rel-L2 {e}"
-    rp = dict(ref.named_parameters())
-    num = den = 0.0
-    rels = []
-    for k, p in net.named_parameters():
-        gk, go = p.grad.float(), rp[k].grad.float()
-        num += float((gk - go).norm() ** 2)
-        den += float(go.norm() ** 2)
-        rels.append((k, _rel(gk, go), float(go.norm())))
-    agg = (num / den) ** 0.5
-    assert agg <= 1.5e-2, f"aggregate gradient rel-L2 {agg}"
-    floor = 1e-7 * den ** 0.5
-    worst = max((r for r in rels if r[2] > floor), key=lambda r: r[1])
-    assert worst[1] <= 6e-2, f"worst parameter gradient {worst}"
-    del net, ref
+    gk = {k: p.grad.float().clone() for k, p in net.named_parameters()}
+    ko = ko.detach().float()
+    del net
     torch.cuda.empty_cache()
+
+    def run_oracle(dtype):
+        with torch.device("meta"):
+            ref = OracleUNet()
+        ref = ref.to_empty(device="cuda").to(dtype)
+        ref.load_state_dict({k: v.to(dtype) for k, v in sd.items()})
+        out = ref(x.to(dtype), t, ctx.to(dtype), added_cond_kwargs={"text_embeds": pooled.to(dtype), "time_ids": tid}).sample
+        (out.float() * wgt).sum().backward()
+        grads = {k: p.grad.float().clone() for k, p in ref.named_parameters()}
+        out = out.detach().float()
+        del ref
+        torch.cuda.empty_cache()
+        return out, grads
+
+    o32, g32 = run_oracle(torch.float32)
+    o16, g16 = run_oracle(bf16)
+    assert torch.isfinite(ko).all()
+    ef, eo = _rel(ko, o32), _rel(o16, o32)
+    assert ef <= 2e-2, f"full-size forward rel-L2 {ef} (eager bf16: {eo})"
+    nk = no = den = 0.0
+    bad = []
+    for k in gk:
+        d = float(g32[k].norm() ** 2)
+        den += d
+        nk += float((gk[k] - g32[k]).norm() ** 2)
+        no += float((g16[k] - g32[k]).norm() ** 2)
+    for k in gk:
+        if float(g32[k].norm()) <= 1e-7 * den ** 0.5:
+            continue
+        rk, ro_ = _rel(gk[k], g32[k]), _rel(g16[k], g32[k])
+        if rk > max(6e-2, 2.5 * ro_):
+            bad.append((k, rk, ro_))
+    agg_k, agg_o = (nk / den) ** 0.5, (no / den) ** 0.5
+    assert agg_k <= max(1.5e-2, 2 * agg_o), f"aggregate gradient rel-L2 {agg_k} (eager bf16: {agg_o})"
+    assert not bad, f"{len(bad)} tensors worse than the bf16 yardstick allows: {sorted(bad, key=lambda r: -r[1])[:5]}"
