@@ -154,8 +154,8 @@ int b2_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int n
  *   so the fused QKV projection output [B*n, 3C] is consumed in place (ld = 3C, bs = n*3C, K = Q + C, V = Q + 2C).
  *   TMA constraints (checked): bases 16-byte aligned, ld / bs multiples of 8 elements.
  *   LSE: float [B, H, n_pad], n_pad = b2_attn_lse_rows(n_q) (= n_q rounded up to 128), log2 domain, written by fwd,
- *   read by bwd.  D: float [B, H, n_pad] scratch written by bwd.  flags bit 0: debug (drain the MMA pipe between
- *   query blocks in the dK/dV kernel instead of relying on issue-order execution).
+ *   read by bwd.  D: float [B, H, n_pad] scratch written by bwd.  flags: reserved (0).
+ *   n_k <= 96 (cross-attention, 77 text tokens) takes a query-tile-persistent forward kernel.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct b2_attn_args {
   const void* Q;

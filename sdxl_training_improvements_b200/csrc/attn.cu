@@ -2,15 +2,15 @@
 // Replaces F.scaled_dot_product_attention inside diffusers' AttnProcessor2_0 (self-attention, n keys; cross-attention,
 // 77 keys) and its autograd backward — SURVEY.md §8 a5.5 / a5.6.  No n x n tensor ever touches HBM.
 //
-// Three kernels with one shape: TMA-staged bf16 tiles in SWIZZLE_128B smem -> tcgen05.mma (SS) into TMEM -> the
-// four "row" warps read their TMEM lane with tcgen05.ld, do the exp2 / rescale math in registers, write the bf16
-// result back to TMEM with tcgen05.st -> tcgen05.mma (TS: A operand from TMEM) accumulates the output tile in TMEM.
-//   fwd    : CTA = 128 queries x (all keys in blocks of 128);  S -> P -> O += P V, online softmax with lazy rescale.
-//   bwd_dq : CTA = 128 queries x (keys in blocks of 64);        S, dP -> dS -> dQ += dS K.
-//   bwd_dkv: CTA = 128 keys x (queries in blocks of 64);        S^T, dP^T -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = row warps
-// (warp w owns TMEM lanes 32*(w%4)..+31).  256 TMEM columns and <= 82 KB smem per CTA -> two CTAs per SM, which is
-// what overlaps one CTA's exp2 phase with the other CTA's MMA phase.
+// Kernels (all: TMA-staged bf16 tiles in SWIZZLE_128B smem -> tcgen05.mma (SS) into TMEM -> softmax warps read their TMEM
+// lane with tcgen05.ld, do the exp2 / rescale math in registers, write the bf16 result back IN PLACE with tcgen05.st ->
+// tcgen05.mma (TS: A operand from TMEM) accumulates the output tile in TMEM):
+//   attn_fwd3   : CTA = 128 queries x key blocks of 128; ring of three S accumulators, two softmax groups on alternate blocks
+//   attn_xfwd   : cross-attention (<= 96 keys): persistent CTA per SM over (sample, head, query-tile) work items
+//   attn_bwd_dq3: CTA = 128 queries x key blocks of 64;   S, dP -> dS -> dQ += dS K
+//   attn_bwd_dkv3: CTA = 128 keys x query blocks of 64;   S^T, dP^T -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 / 6..9 = the two
+// softmax groups (warp w owns TMEM lanes 32*(w%4)..+31).  One CTA per SM (512 TMEM columns).
 //
 // LSE is kept in the log2 domain: L2[i] = m_i + log2(sum_j 2^(s_ij*c - m_i)), c = scale*log2(e); P_ij = 2^(s_ij*c - L2[i]).
 // LSE / D are laid out [B, H, n_pad] with n_pad = ceil(n_q/128)*128; pad rows hold L2 = +inf (P = 0) and D = 0.
@@ -28,7 +28,6 @@ __device__ __forceinline__ unsigned long long clk() {
   return t;
 }
 
-constexpr int AT_THREADS = 192;
 constexpr int AT_D = 64;                        // head dim
 constexpr int AT_TILE128 = 128 * AT_D * 2;      // 16 KiB: 128 rows x 64 bf16
 constexpr int AT_TILE64 = 64 * AT_D * 2;        // 8 KiB
@@ -55,170 +54,6 @@ __device__ __forceinline__ void store_row64(bf16* dst, const uint32_t* r0, const
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[j]) * mul;
     st8(dst + g * 8, pack8(f));
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------------------------
-constexpr int FWD_STAGES = 2;
-constexpr int FWD_SMEM = AT_TILE128 + FWD_STAGES * 2 * AT_TILE128 + 1024;
-
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnP p) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_full[FWD_STAGES], bar_empty[FWD_STAGES], bar_s, bar_p, bar_o;
-  __shared__ uint32_t tmem_slot;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;
-  const uint32_t sKV = smem_base + AT_TILE128;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nkb = (p.n_k + 127) / 128;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(smem_u32(&bar_q), 1);
-#pragma unroll
-    for (int s = 0; s < FWD_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
-    }
-    mbar_init(smem_u32(&bar_s), 1);
-    mbar_init(smem_u32(&bar_p), 128);
-    mbar_init(smem_u32(&bar_o), 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), AT_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-  const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(smem_u32(&bar_q), AT_TILE128);
-      tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
-      for (int j = 0; j < nkb; ++j) {
-        const int s = j % FWD_STAGES;
-        const uint32_t ph = (j / FWD_STAGES) & 1;
-        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-        const uint32_t full = smem_u32(&bar_full[s]);
-        mbar_expect_tx(full, 2 * AT_TILE128);
-        tma_load_4d(sKV + s * 2 * AT_TILE128, &tmK, full, 0, j * 128, h, b);
-        tma_load_4d(sKV + s * 2 * AT_TILE128 + AT_TILE128, &tmV, full, 0, j * 128, h, b);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idS = umma_idesc(128, 128, 0, 0);
-      constexpr uint32_t idO = umma_idesc(128, AT_D, 0, 1);
-      mbar_wait(smem_u32(&bar_q), 0);
-      for (int j = 0; j < nkb; ++j) {
-        const int s = j % FWD_STAGES;
-        const uint32_t ph = (j / FWD_STAGES) & 1;
-        mbar_wait(smem_u32(&bar_full[s]), ph);
-        tc_fence_after();
-        const uint32_t sK = sKV + s * 2 * AT_TILE128, sV = sK + AT_TILE128;
-#pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
-        umma_commit(smem_u32(&bar_s));
-        mbar_wait(smem_u32(&bar_p), j & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k)
-          umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (j | k) != 0);
-        umma_commit(smem_u32(&bar_empty[s]));
-      }
-      umma_commit(smem_u32(&bar_o));
-    }
-  } else {
-    const int qd = warp & 3;
-    const int row = qd * 32 + lane;
-    const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    float m_used = 0.f, l = 0.f;
-    for (int j = 0; j < nkb; ++j) {
-      mbar_wait(smem_u32(&bar_s), j & 1);
-      tc_fence_after();
-      const int valid = min(128, p.n_k - j * 128);
-      // pass 1: row max of the raw logits
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_off + cc * 32, r);
-        if (valid >= 128) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cc * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
-      }
-      mx *= p.c;
-      float factor = 1.f;
-      if (j == 0) {
-        m_used = mx;
-      } else if (mx > m_used + 8.f) {  // lazy rescale: stale max is fine while 2^(s - m) <= 2^8
-        factor = fast_exp2(m_used - mx);
-        m_used = mx;
-      }
-      if (j > 0 && __any_sync(AT_FULL, factor != 1.f)) {
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t r[32];
-          tmem_ld32(tO + lane_off + cc * 32, r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
-          tmem_st32(tO + lane_off + cc * 32, r);
-        }
-        l *= factor;
-      }
-      // pass 2: P = 2^(s*c - m), row sum, bf16 P -> TMEM (A operand of the PV MMA)
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32], pk[16];
-        tmem_ld32(tS + lane_off + cc * 32, r);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.c, -m_used));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.c, -m_used));
-          if (valid < 128) {
-            if (cc * 32 + 2 * i >= valid) p0 = 0.f;
-            if (cc * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-          }
-          l += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        tmem_st16(tP + lane_off + cc * 16, pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bar_p));
-    }
-    mbar_wait(smem_u32(&bar_o), 0);
-    tc_fence_after();
-    uint32_t r0[32], r1[32];
-    tmem_ld32_nowait(tO + lane_off, r0);
-    tmem_ld32_nowait(tO + lane_off + 32, r1);
-    tmem_ld_wait();
-    const int gq = q0 + row;
-    const float inv = 1.f / l;
-    if (gq < p.n_q) store_row64(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D, r0, r1, inv);
-    if (gq < p.n_pad) p.LSE[((long long)b * p.H + h) * p.n_pad + gq] = gq < p.n_q ? m_used + log2f(l) : INFINITY;
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
   }
 }
 
@@ -290,6 +125,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(tmem_slot);
+  pdl_wait();  // set-up above overlaps the previous kernel's tail (PDL); its outputs are visible from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
@@ -533,308 +370,6 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, const bf16* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward, dQ: CTA = 128 queries, loops over key blocks of 64
-//   TMEM: S [0,64)  dP [64,128)  dS(bf16) [128,160)  dQ [160,224)
-// ---------------------------------------------------------------------------------------------
-constexpr int BWD_STAGES = 3;
-constexpr int BWD_SMEM = 2 * AT_TILE128 + BWD_STAGES * 2 * AT_TILE64 + 1024;
-
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnP p) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_full[BWD_STAGES], bar_empty[BWD_STAGES], bar_s, bar_p, bar_o;
-  __shared__ uint32_t tmem_slot;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base, sdO = smem_base + AT_TILE128, sKV = smem_base + 2 * AT_TILE128;
-  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nkb = (p.n_k + 63) / 64;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmdO);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(smem_u32(&bar_q), 1);
-#pragma unroll
-    for (int s = 0; s < BWD_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
-    }
-    mbar_init(smem_u32(&bar_s), 1);
-    mbar_init(smem_u32(&bar_p), 128);
-    mbar_init(smem_u32(&bar_o), 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), AT_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = uniform_u32(tmem_slot);
-  const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdS = tmem_base + 128, tdQ = tmem_base + 160;
-
-  if (warp == 0) {
-    const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
-    {
-      if (el) {
-      mbar_expect_tx(smem_u32(&bar_q), 2 * AT_TILE128);
-        tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
-        tma_load_4d(sdO, &tmdO, smem_u32(&bar_q), 0, q0, h, b);
-      }
-      for (int j = 0; j < nkb; ++j) {
-        const int s = j % BWD_STAGES;
-        const uint32_t ph = (j / BWD_STAGES) & 1;
-        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-        const uint32_t full = smem_u32(&bar_full[s]);
-        if (el) {
-        mbar_expect_tx(full, 2 * AT_TILE64);
-          tma_load_4d(sKV + s * 2 * AT_TILE64, &tmK, full, 0, j * 64, h, b);
-          tma_load_4d(sKV + s * 2 * AT_TILE64 + AT_TILE64, &tmV, full, 0, j * 64, h, b);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    const bool el = elect_one();
-    {
-      constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
-      constexpr uint32_t idQ = umma_idesc(128, AT_D, 0, 1);
-      mbar_wait(smem_u32(&bar_q), 0);
-      for (int j = 0; j < nkb; ++j) {
-        const int s = j % BWD_STAGES;
-        const uint32_t ph = (j / BWD_STAGES) & 1;
-        mbar_wait(smem_u32(&bar_full[s]), ph);
-        tc_fence_after();
-        const uint32_t sK = sKV + s * 2 * AT_TILE64, sV = sK + AT_TILE64;
-#pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
-#pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tdP, umma_desc(sdO + k * 32, 16, 1024), umma_desc(sV + k * 32, 16, 1024), idS, k != 0);
-        if (el) umma_commit(smem_u32(&bar_s));
-        mbar_wait(smem_u32(&bar_p), j & 1);
-        tc_fence_after();
-        if (el) {
-#pragma unroll
-          for (int k = 0; k < 64 / 16; ++k)
-            umma_bf16_ts(tdQ, tdS + k * 8, umma_desc(sK + k * 2048, 8192, 1024), idQ, (j | k) != 0);
-        }
-        if (el) umma_commit(smem_u32(&bar_empty[s]));
-      }
-      if (el) umma_commit(smem_u32(&bar_o));
-    }
-  } else {
-    const int qd = warp & 3;
-    const int row = qd * 32 + lane;
-    const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    const int gq = q0 + row;
-    const long long sidx = ((long long)b * p.H + h) * p.n_pad + gq;
-    const float L2 = p.LSE[sidx];   // +inf on pad rows -> P = 0
-    const float Dr = p.D[sidx];
-    for (int j = 0; j < nkb; ++j) {
-      mbar_wait(smem_u32(&bar_s), j & 1);
-      tc_fence_after();
-      const int valid = min(64, p.n_k - j * 64);
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t rs[32], rd[32], pk[16];
-        tmem_ld32_nowait(tS + lane_off + cc * 32, rs);
-        tmem_ld32_nowait(tdP + lane_off + cc * 32, rd);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(rs[2 * i]), p.c, -L2));
-          float p1 = fast_exp2(fmaf(__uint_as_float(rs[2 * i + 1]), p.c, -L2));
-          if (valid < 64) {
-            if (cc * 32 + 2 * i >= valid) p0 = 0.f;
-            if (cc * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-          }
-          pk[i] = pack_bf16x2(p0 * (__uint_as_float(rd[2 * i]) - Dr), p1 * (__uint_as_float(rd[2 * i + 1]) - Dr));
-        }
-        tmem_st16(tdS + lane_off + cc * 16, pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bar_p));
-    }
-    mbar_wait(smem_u32(&bar_o), 0);
-    tc_fence_after();
-    uint32_t r0[32], r1[32];
-    tmem_ld32_nowait(tdQ + lane_off, r0);
-    tmem_ld32_nowait(tdQ + lane_off + 32, r1);
-    tmem_ld_wait();
-    if (gq < p.n_q) store_row64(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D, r0, r1, p.scale);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// backward, dK / dV: CTA = 128 keys, loops over query blocks of 64
-//   TMEM: S^T -> P^T(bf16, in place) [0,64)   dP^T -> dS^T(bf16, in place) [64,128)   dV [128,192)   dK [192,256)
-//   The next S^T / dP^T MMAs overwrite columns the previous dV / dK MMAs read as their A operand; tcgen05.mma
-//   instructions of one thread execute in issue order, so the pipe itself orders that WAR.  kDrain = true inserts an
-//   explicit completion wait instead (debug / A-B check).
-// ---------------------------------------------------------------------------------------------
-template <bool kDrain>
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO, const AttnP p) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_kv, bar_full[BWD_STAGES], bar_empty[BWD_STAGES], bar_s, bar_p, bar_o, bar_x;
-  __shared__ uint32_t tmem_slot;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sK = smem_base, sV = smem_base + AT_TILE128, sQdO = smem_base + 2 * AT_TILE128;
-  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nqb = (p.n_q + 63) / 64;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmdO);
-    mbar_init(smem_u32(&bar_kv), 1);
-#pragma unroll
-    for (int s = 0; s < BWD_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
-    }
-    mbar_init(smem_u32(&bar_s), 1);
-    mbar_init(smem_u32(&bar_p), 128);
-    mbar_init(smem_u32(&bar_o), 1);
-    mbar_init(smem_u32(&bar_x), 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), AT_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = uniform_u32(tmem_slot);
-  const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdV = tmem_base + 128, tdK = tmem_base + 192;
-
-  if (warp == 0) {
-    const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
-    {
-      if (el) {
-      mbar_expect_tx(smem_u32(&bar_kv), 2 * AT_TILE128);
-        tma_load_4d(sK, &tmK, smem_u32(&bar_kv), 0, k0, h, b);
-        tma_load_4d(sV, &tmV, smem_u32(&bar_kv), 0, k0, h, b);
-      }
-      for (int i = 0; i < nqb; ++i) {
-        const int s = i % BWD_STAGES;
-        const uint32_t ph = (i / BWD_STAGES) & 1;
-        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-        const uint32_t full = smem_u32(&bar_full[s]);
-        if (el) {
-        mbar_expect_tx(full, 2 * AT_TILE64);
-          tma_load_4d(sQdO + s * 2 * AT_TILE64, &tmQ, full, 0, i * 64, h, b);
-          tma_load_4d(sQdO + s * 2 * AT_TILE64 + AT_TILE64, &tmdO, full, 0, i * 64, h, b);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    const bool el = elect_one();
-    {
-      constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
-      constexpr uint32_t idG = umma_idesc(128, AT_D, 0, 1);
-      mbar_wait(smem_u32(&bar_kv), 0);
-      for (int i = 0; i < nqb; ++i) {
-        const int s = i % BWD_STAGES;
-        const uint32_t ph = (i / BWD_STAGES) & 1;
-        mbar_wait(smem_u32(&bar_full[s]), ph);
-        if (kDrain && i > 0) mbar_wait(smem_u32(&bar_x), (i - 1) & 1);
-        tc_fence_after();
-        const uint32_t sQ = sQdO + s * 2 * AT_TILE64, sdO = sQ + AT_TILE64;
-#pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sK + k * 32, 16, 1024), umma_desc(sQ + k * 32, 16, 1024), idS, k != 0);
-#pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tdP, umma_desc(sV + k * 32, 16, 1024), umma_desc(sdO + k * 32, 16, 1024), idS, k != 0);
-        if (el) umma_commit(smem_u32(&bar_s));
-        mbar_wait(smem_u32(&bar_p), i & 1);
-        tc_fence_after();
-        if (el) {
-#pragma unroll
-          for (int k = 0; k < 64 / 16; ++k)
-            umma_bf16_ts(tdV, tS + k * 8, umma_desc(sdO + k * 2048, 8192, 1024), idG, (i | k) != 0);
-        }
-        if (el) {
-#pragma unroll
-          for (int k = 0; k < 64 / 16; ++k)
-            umma_bf16_ts(tdK, tdP + k * 8, umma_desc(sQ + k * 2048, 8192, 1024), idG, (i | k) != 0);
-        }
-        if (el) umma_commit(smem_u32(&bar_empty[s]));
-        if (kDrain) umma_commit(smem_u32(&bar_x));
-      }
-      if (el) umma_commit(smem_u32(&bar_o));
-    }
-  } else {
-    const int qd = warp & 3;
-    const int row = qd * 32 + lane;
-    const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    const float* Lp = p.LSE + ((long long)b * p.H + h) * p.n_pad;
-    const float* Dp = p.D + ((long long)b * p.H + h) * p.n_pad;
-    for (int i = 0; i < nqb; ++i) {
-      mbar_wait(smem_u32(&bar_s), i & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t rs[32], rd[32], pp[16], pd[16];
-        tmem_ld32_nowait(tS + lane_off + cc * 32, rs);
-        tmem_ld32_nowait(tdP + lane_off + cc * 32, rd);
-        const float4* L4 = reinterpret_cast<const float4*>(Lp + i * 64 + cc * 32);
-        const float4* D4 = reinterpret_cast<const float4*>(Dp + i * 64 + cc * 32);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 lv = __ldg(L4 + g), dv = __ldg(D4 + g);
-          const float p0 = fast_exp2(fmaf(__uint_as_float(rs[4 * g + 0]), p.c, -lv.x));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(rs[4 * g + 1]), p.c, -lv.y));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(rs[4 * g + 2]), p.c, -lv.z));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(rs[4 * g + 3]), p.c, -lv.w));
-          pp[2 * g] = pack_bf16x2(p0, p1);
-          pp[2 * g + 1] = pack_bf16x2(p2, p3);
-          pd[2 * g] = pack_bf16x2(p0 * (__uint_as_float(rd[4 * g + 0]) - dv.x), p1 * (__uint_as_float(rd[4 * g + 1]) - dv.y));
-          pd[2 * g + 1] = pack_bf16x2(p2 * (__uint_as_float(rd[4 * g + 2]) - dv.z), p3 * (__uint_as_float(rd[4 * g + 3]) - dv.w));
-        }
-        tmem_st16(tS + lane_off + cc * 16, pp);
-        tmem_st16(tdP + lane_off + cc * 16, pd);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bar_p));
-    }
-    mbar_wait(smem_u32(&bar_o), 0);
-    tc_fence_after();
-    const int gk = k0 + row;
-    uint32_t r0[32], r1[32];
-    tmem_ld32_nowait(tdV + lane_off, r0);
-    tmem_ld32_nowait(tdV + lane_off + 32, r1);
-    tmem_ld_wait();
-    if (gk < p.n_k) store_row64(p.out1 + (long long)b * p.bs1 + (long long)gk * p.ld1 + h * AT_D, r0, r1, 1.f);
-    tmem_ld32_nowait(tdK + lane_off, r0);
-    tmem_ld32_nowait(tdK + lane_off + 32, r1);
-    tmem_ld_wait();
-    if (gk < p.n_k) store_row64(p.out0 + (long long)b * p.bs0 + (long long)gk * p.ld0 + h * AT_D, r0, r1, p.scale);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Cross-attention kernels (n_k <= 96 keys: SDXL's 77 text tokens = ONE key block).
 //   With a single key block the v3 kernels spend their time in per-CTA set-up (640 CTAs x {TMEM alloc, barrier init, one
 //   128x128 tile}): 29 us per layer call for 1.6 GFLOP / 22.6 MB (HBM floor 3.5 us).  Here the loop dimension is the
@@ -888,6 +423,8 @@ attn_xfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(tmem_slot);
+  pdl_wait();  // set-up above overlaps the previous kernel's tail (PDL); its outputs are visible from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     const bool el = elect_one();
@@ -1075,6 +612,8 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(tmem_slot);
+  pdl_wait();  // set-up above overlaps the previous kernel's tail (PDL); its outputs are visible from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
@@ -1251,6 +790,8 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(tmem_slot);
+  pdl_wait();  // set-up above overlaps the previous kernel's tail (PDL); its outputs are visible from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
@@ -1433,24 +974,17 @@ extern "C" int b2_attn_set_debug(void* counters) {
 extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
   int rc = check_common(a, "b2_attn_fwd");
   if (rc) return rc;
-  CUtensorMap tq, tk, tv;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tq;
   if ((rc = make_map_bf16_4d(&tq, a->Q, AT_D, a->n_q, a->H, a->B, a->ldq, AT_D, a->q_bs, 64, 128, "attn Q"))) return rc;
-  if ((rc = make_map_bf16_4d(&tk, a->K, AT_D, a->n_k, a->H, a->B, a->ldk, AT_D, a->k_bs, 64, 128, "attn K"))) return rc;
-  if ((rc = make_map_bf16_4d(&tv, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 128, "attn V"))) return rc;
-  static bool configured = false;
-  if (!configured) {
-    if ((rc = set_smem(attn_fwd_kernel, FWD_SMEM, "b2_attn_fwd"))) return rc;
-    configured = true;
-  }
   AttnP p{};
   p.H = a->H; p.n_q = a->n_q; p.n_k = a->n_k; p.n_pad = b2_attn_lse_rows(a->n_q);
   p.scale = a->scale; p.c = a->scale * 1.4426950408889634f;
   p.LSE = a->LSE; p.D = nullptr;
   p.dbg = g_attn_dbg;
   p.out0 = (bf16*)a->O; p.ld0 = a->ldo; p.bs0 = a->o_bs;
-  static const bool legacy = getenv("B2_ATTN_LEGACY") != nullptr;
   static const bool no_cross = getenv("B2_ATTN_NO_CROSS") != nullptr;
-  if (!legacy && !no_cross && a->n_k <= X_KV_ROWS) {  // cross-attention: query-tile-persistent kernel
+  if (!no_cross && a->n_k <= X_KV_ROWS) {  // cross-attention: query-tile-persistent kernel
     static bool configured_x = false;
     if (!configured_x) {
       if ((rc = set_smem(attn_xfwd_kernel, X_SMEM, "b2_attn_fwd"))) return rc;
@@ -1463,21 +997,18 @@ extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
     const long long total = (long long)nqt * a->H * a->B;
     B2_REQUIRE(total < (1ll << 31), "b2_attn_fwd: too many tiles");
     const int grid = (int)(total < num_sms() ? total : num_sms());
-    attn_xfwd_kernel<<<grid, A3_THREADS, X_SMEM, (cudaStream_t)stream>>>(tq, tkx, tvx, p, nqt, (int)total);
+    (void)launch_pdl(attn_xfwd_kernel, dim3(grid), dim3(A3_THREADS), (size_t)X_SMEM, st, tq, tkx, tvx, p, nqt, (int)total);
     return check_launch("b2_attn_fwd(cross)");
   }
-  if (!legacy) {
-    static bool configured2 = false;
-    if (!configured2) {
-      if ((rc = set_smem(attn_fwd3_kernel, F3_SMEM, "b2_attn_fwd"))) return rc;
-      configured2 = true;
-    }
-    dim3 grid3((a->n_q + 127) / 128, a->H, a->B);
-    attn_fwd3_kernel<<<grid3, A3_THREADS, F3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
-    return check_launch("b2_attn_fwd");
+  CUtensorMap tk, tv;
+  if ((rc = make_map_bf16_4d(&tk, a->K, AT_D, a->n_k, a->H, a->B, a->ldk, AT_D, a->k_bs, 64, 128, "attn K"))) return rc;
+  if ((rc = make_map_bf16_4d(&tv, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 128, "attn V"))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    if ((rc = set_smem(attn_fwd3_kernel, F3_SMEM, "b2_attn_fwd"))) return rc;
+    configured = true;
   }
-  dim3 grid((a->n_q + 127) / 128, a->H, a->B);
-  attn_fwd_kernel<<<grid, AT_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  (void)launch_pdl(attn_fwd3_kernel, dim3((a->n_q + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)F3_SMEM, st, tq, tk, tv, p);
   return check_launch("b2_attn_fwd");
 }
 
@@ -1495,69 +1026,32 @@ extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
   }
   static bool configured = false;
   if (!configured) {
-    if ((rc = set_smem(attn_bwd_dq_kernel, BWD_SMEM, "b2_attn_bwd"))) return rc;
-    if ((rc = set_smem(attn_bwd_dkv_kernel<false>, BWD_SMEM, "b2_attn_bwd"))) return rc;
-    if ((rc = set_smem(attn_bwd_dkv_kernel<true>, BWD_SMEM, "b2_attn_bwd"))) return rc;
+    if ((rc = set_smem(attn_bwd_dq3_kernel, Q3_SMEM, "b2_attn_bwd"))) return rc;
+    if ((rc = set_smem(attn_bwd_dkv3_kernel, Q3_SMEM, "b2_attn_bwd"))) return rc;
     configured = true;
   }
   AttnP p{};
   p.H = a->H; p.n_q = a->n_q; p.n_k = a->n_k; p.n_pad = n_pad;
   p.scale = a->scale; p.c = a->scale * 1.4426950408889634f;
   p.LSE = a->LSE; p.D = a->D;
-  static const bool legacy = getenv("B2_ATTN_LEGACY") != nullptr;
-  if (!legacy && !(a->flags & 1)) {
-    static bool configured2 = false;
-    if (!configured2) {
-      if ((rc = set_smem(attn_bwd_dq3_kernel, Q3_SMEM, "b2_attn_bwd"))) return rc;
-      if ((rc = set_smem(attn_bwd_dkv3_kernel, Q3_SMEM, "b2_attn_bwd"))) return rc;
-      configured2 = true;
-    }
-    CUtensorMap tq128, tdo128, tk64, tv64, tk128, tv128, tq64, tdo64;
-    if ((rc = make_map_bf16_4d(&tq128, a->Q, AT_D, a->n_q, a->H, a->B, a->ldq, AT_D, a->q_bs, 64, 128, "attn Q"))) return rc;
-    if ((rc = make_map_bf16_4d(&tdo128, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 128, "attn dO"))) return rc;
-    if ((rc = make_map_bf16_4d(&tk64, a->K, AT_D, a->n_k, a->H, a->B, a->ldk, AT_D, a->k_bs, 64, 64, "attn K64"))) return rc;
-    if ((rc = make_map_bf16_4d(&tv64, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 64, "attn V64"))) return rc;
-    if ((rc = make_map_bf16_4d(&tk128, a->K, AT_D, a->n_k, a->H, a->B, a->ldk, AT_D, a->k_bs, 64, 128, "attn K"))) return rc;
-    if ((rc = make_map_bf16_4d(&tv128, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 128, "attn V"))) return rc;
-    if ((rc = make_map_bf16_4d(&tq64, a->Q, AT_D, a->n_q, a->H, a->B, a->ldq, AT_D, a->q_bs, 64, 64, "attn Q64"))) return rc;
-    if ((rc = make_map_bf16_4d(&tdo64, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 64, "attn dO64"))) return rc;
-    AttnP pq = p;
-    pq.out0 = (bf16*)a->dQ; pq.ld0 = a->lddq; pq.bs0 = a->dq_bs;
-    attn_bwd_dq3_kernel<<<dim3((a->n_q + 127) / 128, a->H, a->B), A3_THREADS, Q3_SMEM, st>>>(tq128, tdo128, tk64, tv64, pq);
-    if ((rc = check_launch("b2_attn_bwd dq3"))) return rc;
-    AttnP pk = p;
-    pk.out0 = (bf16*)a->dK; pk.ld0 = a->lddk; pk.bs0 = a->dk_bs;
-    pk.out1 = (bf16*)a->dV; pk.ld1 = a->lddv; pk.bs1 = a->dv_bs;
-    attn_bwd_dkv3_kernel<<<dim3((a->n_k + 127) / 128, a->H, a->B), A3_THREADS, Q3_SMEM, st>>>(tk128, tv128, tq64, tdo64, pk);
-    return check_launch("b2_attn_bwd dkv3");
-  }
-  {
-    CUtensorMap tq, tdo, tk, tv;
-    if ((rc = make_map_bf16_4d(&tq, a->Q, AT_D, a->n_q, a->H, a->B, a->ldq, AT_D, a->q_bs, 64, 128, "attn Q"))) return rc;
-    if ((rc = make_map_bf16_4d(&tdo, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 128, "attn dO"))) return rc;
-    if ((rc = make_map_bf16_4d(&tk, a->K, AT_D, a->n_k, a->H, a->B, a->ldk, AT_D, a->k_bs, 64, 64, "attn K64"))) return rc;
-    if ((rc = make_map_bf16_4d(&tv, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 64, "attn V64"))) return rc;
-    AttnP pq = p;
-    pq.out0 = (bf16*)a->dQ; pq.ld0 = a->lddq; pq.bs0 = a->dq_bs;
-    dim3 grid((a->n_q + 127) / 128, a->H, a->B);
-    attn_bwd_dq_kernel<<<grid, AT_THREADS, BWD_SMEM, st>>>(tq, tdo, tk, tv, pq);
-    if ((rc = check_launch("b2_attn_bwd dq"))) return rc;
-  }
-  {
-    CUtensorMap tk, tv, tq, tdo;
-    if ((rc = make_map_bf16_4d(&tk, a->K, AT_D, a->n_k, a->H, a->B, a->ldk, AT_D, a->k_bs, 64, 128, "attn K"))) return rc;
-    if ((rc = make_map_bf16_4d(&tv, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 128, "attn V"))) return rc;
-    if ((rc = make_map_bf16_4d(&tq, a->Q, AT_D, a->n_q, a->H, a->B, a->ldq, AT_D, a->q_bs, 64, 64, "attn Q64"))) return rc;
-    if ((rc = make_map_bf16_4d(&tdo, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 64, "attn dO64"))) return rc;
-    AttnP pk = p;
-    pk.out0 = (bf16*)a->dK; pk.ld0 = a->lddk; pk.bs0 = a->dk_bs;
-    pk.out1 = (bf16*)a->dV; pk.ld1 = a->lddv; pk.bs1 = a->dv_bs;
-    dim3 grid((a->n_k + 127) / 128, a->H, a->B);
-    if (a->flags & 1)
-      attn_bwd_dkv_kernel<true><<<grid, AT_THREADS, BWD_SMEM, st>>>(tk, tv, tq, tdo, pk);
-    else
-      attn_bwd_dkv_kernel<false><<<grid, AT_THREADS, BWD_SMEM, st>>>(tk, tv, tq, tdo, pk);
-    if ((rc = check_launch("b2_attn_bwd dkv"))) return rc;
-  }
-  return B2_OK;
+  CUtensorMap tq128, tdo128, tk64, tv64, tk128, tv128, tq64, tdo64;
+  if ((rc = make_map_bf16_4d(&tq128, a->Q, AT_D, a->n_q, a->H, a->B, a->ldq, AT_D, a->q_bs, 64, 128, "attn Q"))) return rc;
+  if ((rc = make_map_bf16_4d(&tdo128, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 128, "attn dO"))) return rc;
+  if ((rc = make_map_bf16_4d(&tk64, a->K, AT_D, a->n_k, a->H, a->B, a->ldk, AT_D, a->k_bs, 64, 64, "attn K64"))) return rc;
+  if ((rc = make_map_bf16_4d(&tv64, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 64, "attn V64"))) return rc;
+  if ((rc = make_map_bf16_4d(&tk128, a->K, AT_D, a->n_k, a->H, a->B, a->ldk, AT_D, a->k_bs, 64, 128, "attn K"))) return rc;
+  if ((rc = make_map_bf16_4d(&tv128, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 128, "attn V"))) return rc;
+  if ((rc = make_map_bf16_4d(&tq64, a->Q, AT_D, a->n_q, a->H, a->B, a->ldq, AT_D, a->q_bs, 64, 64, "attn Q64"))) return rc;
+  if ((rc = make_map_bf16_4d(&tdo64, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 64, "attn dO64"))) return rc;
+  AttnP pq = p;
+  pq.out0 = (bf16*)a->dQ; pq.ld0 = a->lddq; pq.bs0 = a->dq_bs;
+  (void)launch_pdl(attn_bwd_dq3_kernel, dim3((a->n_q + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)Q3_SMEM, st, tq128,
+                   tdo128, tk64, tv64, pq);
+  if ((rc = check_launch("b2_attn_bwd dq3"))) return rc;
+  AttnP pk = p;
+  pk.out0 = (bf16*)a->dK; pk.ld0 = a->lddk; pk.bs0 = a->dk_bs;
+  pk.out1 = (bf16*)a->dV; pk.ld1 = a->lddv; pk.bs1 = a->dv_bs;
+  (void)launch_pdl(attn_bwd_dkv3_kernel, dim3((a->n_k + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)Q3_SMEM, st, tk128,
+                   tv128, tq64, tdo64, pk);
+  return check_launch("b2_attn_bwd dkv3");
 }

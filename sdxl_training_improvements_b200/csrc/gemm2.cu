@@ -155,6 +155,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(tmem_slot);
+  pdl_wait();               // everything above overlapped the previous kernel's tail; from here on we touch its outputs
+  pdl_launch_dependents();  // let the next kernel begin ITS set-up as our CTAs retire
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs): warp-uniform loop, elected lane issues =====================
@@ -611,7 +613,11 @@ static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
             p.a_mn, p.b_mn, p.conv, p.BN, p.splits, p.bias != nullptr, p.has_res);
   const long long tiles = (long long)p.tiles_m * p.tiles_n * p.splits;
   const int clusters = (int)(tiles < num_clusters ? tiles : num_clusters);
-  gemm2_kernel<<<dim3(2 * clusters), G2_THREADS, G2_SMEM, st>>>(ta, tb, td, tr, p);
+  cudaError_t le = launch_pdl(gemm2_kernel, dim3(2 * clusters), dim3(G2_THREADS), (size_t)G2_SMEM, st, ta, tb, td, tr, p);
+  if (le != cudaSuccess) {
+    set_error("%s: launch: %s", what, cudaGetErrorString(le));
+    return B2_ERR_CUDA;
+  }
   return check_launch(what);
 }
 

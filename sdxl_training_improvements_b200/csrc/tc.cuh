@@ -2,6 +2,7 @@
 // UMMA shared-memory + instruction descriptors, and the host-side cuTensorMapEncodeTiled helper.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -104,6 +105,33 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL)
+//   The tcgen05 kernels have ~1.5-2.5 us of set-up (barrier init, TMEM allocation, tensor-map prefetch, cluster sync)
+//   that touches no global data.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, kernel i+1 may start
+//   that set-up while kernel i drains; pdl_wait() (griddepcontrol.wait) then blocks until kernel i has completed and its
+//   writes are visible — it MUST precede the first global read or write.  Every kernel launched through launch_pdl()
+//   calls pdl_wait(); kernels launched the normal way are fully stream-ordered as before, so mixing is safe.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool off = getenv("B2_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------
 // cluster
