@@ -760,6 +760,9 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_kv, bar_full[Q3_STAGES], bar_empty[Q3_STAGES], bar_s[3], bar_p[3], bar_o;
   __shared__ uint32_t tmem_slot;
+  // LSE / D of each stage's 64 queries, staged by the producer with a bulk copy: reading them with __ldg from the softmax
+  // warps cost ~2000 cycles per block (32 L2-latency loads the compiler cannot hoist past 128 live accumulator registers)
+  __shared__ __align__(16) float ld_s[Q3_STAGES][128];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = smem_base, sV = smem_base + AT_TILE128, sQdO = smem_base + 2 * AT_TILE128;
   const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -876,30 +879,34 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    const float* Lp = p.LSE + ((long long)b * p.H + h) * p.n_pad;
-    const float* Dp = p.D + ((long long)b * p.H + h) * p.n_pad;
-    int buf = g;
-    uint32_t spar = 0;
+    int buf = g, stg = g;   // ring slot and TMA stage of this group's current block
+    uint32_t spar = 0, fpar = 0;
+    unsigned long long d_wait = 0, d_ld = 0, d_cmp = 0, d_st = 0, t0 = 0, t1 = 0;
+    const bool dbg = p.dbg != nullptr;
     for (int i = g; i < nqb; i += 2) {
+      if (dbg) t0 = clk();
       mbar_wait(smem_u32(&bar_s[buf]), spar);
       tc_fence_after();
+      if (dbg) { t1 = clk(); d_wait += t1 - t0; t0 = t1; }
       const uint32_t tS = tmem_base + buf * 128 + lane_off, tdP = tS + 64;
       uint32_t rs[64], rd[64];
       tmem_ld32_nowait(tS, rs);
       tmem_ld32_nowait(tS + 32, rs + 32);
       tmem_ld32_nowait(tdP, rd);
       tmem_ld32_nowait(tdP + 32, rd + 32);
-      // n_pad is a multiple of 128 and the last 64-query block starts below n_q <= n_pad: always in bounds; pad rows
-      // hold LSE = +inf (P = 0) and D = 0
-      const float4* L4 = reinterpret_cast<const float4*>(Lp + i * 64);
-      const float4* D4 = reinterpret_cast<const float4*>(Dp + i * 64);
+      // pad rows hold LSE = +inf (P = 0) and D = 0; the stage's full barrier (observed by the MMA thread before it issued
+      // S^T) covers these bytes too, and bar_s was committed after that
+      mbar_wait(smem_u32(&bar_full[stg]), fpar);  // already complete: makes the bulk-copied bytes visible to this thread
+      const float4* L4 = reinterpret_cast<const float4*>(&ld_s[stg][0]);
+      const float4* D4 = reinterpret_cast<const float4*>(&ld_s[stg][64]);
       tmem_ld_wait();
+      if (dbg) { t1 = clk(); d_ld += t1 - t0; t0 = t1; }
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t pp[16], pd[16];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 lv = __ldg(L4 + cc * 8 + q), dv = __ldg(D4 + cc * 8 + q);
+          const float4 lv = L4[cc * 8 + q], dv = D4[cc * 8 + q];
           const int o = cc * 32 + 4 * q;
           const float p0 = fast_exp2(fmaf(__uint_as_float(rs[o + 0]), p.c, -lv.x));
           const float p1 = fast_exp2(fmaf(__uint_as_float(rs[o + 1]), p.c, -lv.y));
@@ -913,11 +920,20 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
         tmem_st16(tS + cc * 16, pp);
         tmem_st16(tdP + cc * 16, pd);
       }
+      if (dbg) { t1 = clk(); d_cmp += t1 - t0; t0 = t1; }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_p[buf]));
+      if (dbg) { t1 = clk(); d_st += t1 - t0; t0 = t1; }
       buf += 2;
       if (buf >= 3) { buf -= 3; spar ^= 1u; }
+      stg += 2;
+      if (stg >= Q3_STAGES) { stg -= Q3_STAGES; fpar ^= 1u; }
+    }
+    if (dbg && lane == 0 && qd == 0) {
+      unsigned long long* d = p.dbg + 24 + g * 4;
+      atomicAdd(d + 0, d_wait); atomicAdd(d + 1, d_ld); atomicAdd(d + 2, d_cmp); atomicAdd(d + 3, d_st);
+      if (g == 0) atomicAdd(p.dbg + 23, 1ull);
     }
     mbar_wait(smem_u32(&bar_o), 0);
     tc_fence_after();
@@ -1034,6 +1050,7 @@ extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
   p.H = a->H; p.n_q = a->n_q; p.n_k = a->n_k; p.n_pad = n_pad;
   p.scale = a->scale; p.c = a->scale * 1.4426950408889634f;
   p.LSE = a->LSE; p.D = a->D;
+  p.dbg = g_attn_dbg;
   CUtensorMap tq128, tdo128, tk64, tv64, tk128, tv128, tq64, tdo64;
   if ((rc = make_map_bf16_4d(&tq128, a->Q, AT_D, a->n_q, a->H, a->B, a->ldq, AT_D, a->q_bs, 64, 128, "attn Q"))) return rc;
   if ((rc = make_map_bf16_4d(&tdo128, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 128, "attn dO"))) return rc;

@@ -18,6 +18,24 @@ for (B, H, n) in ((4, 20, 1024), (4, 10, 4096)):
     torch.cuda.synchronize()
     _lib.load().b2_attn_set_debug(None)
     c = ctr.tolist()
+    # backward dK/dV kernel phases
+    do = torch.randn(B * n, Cc, device="cuda").to(bf16)
+    dqkv = torch.empty_like(qkv)
+    o, lse = ops.attn_fwd(q, k, v, B, H, n, n, 0.125)
+    ops.attn_bwd(q, k, v, o, lse, do, dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:], B, H, n, n, 0.125)
+    torch.cuda.synchronize()
+    ctr2 = torch.zeros(32, device="cuda", dtype=torch.int64)
+    _lib.load().b2_attn_set_debug(ctr2.data_ptr())
+    ops.attn_bwd(q, k, v, o, lse, do, dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:], B, H, n, n, 0.125)
+    torch.cuda.synchronize()
+    _lib.load().b2_attn_set_debug(None)
+    c2 = ctr2.tolist()
+    nqb = n // 64
+    for g in (0, 1):
+        d = c2[24 + g * 4: 28 + g * 4]
+        cnt = max(1, c2[23]); blocks = (nqb - g + 1) // 2
+        print(f"n={n} dkv3 group {g}: per own 64-query block cycles: wait_S {d[0] / cnt / blocks:.0f}, tmem_ld {d[1] / cnt / blocks:.0f}, "
+              f"compute {d[2] / cnt / blocks:.0f}, st+arrive {d[3] / cnt / blocks:.0f}")
     nkb = n // 128
     for g in (0, 1):
         d = c[g * 8:(g + 1) * 8]
