@@ -810,9 +810,12 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
         const uint32_t full = smem_u32(&bar_full[s]);
         if (el) {
-        mbar_expect_tx(full, 2 * AT_TILE64);
+          mbar_expect_tx(full, 2 * AT_TILE64 + 512);
           tma_load_4d(sQdO + s * 2 * AT_TILE64, &tmQ, full, 0, i * 64, h, b);
           tma_load_4d(sQdO + s * 2 * AT_TILE64 + AT_TILE64, &tmdO, full, 0, i * 64, h, b);
+          const long long off = ((long long)b * p.H + h) * p.n_pad + (long long)i * 64;
+          bulk_load_1d(smem_u32(&ld_s[s][0]), p.LSE + off, 256, full);
+          bulk_load_1d(smem_u32(&ld_s[s][64]), p.D + off, 256, full);
         }
         if (++s == Q3_STAGES) { s = 0; ph ^= 1u; }
       }
