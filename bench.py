@@ -200,7 +200,7 @@ def _cpu_baseline(seconds_budget=30.0, threads=None):
                          f"model build {build_s:.0f} s untimed"}, one
 
 
-def _torch_eager_gpu_baseline(B, H, W, steps=2):
+def _torch_eager_gpu_baseline(B, H, W, steps=3):
     """The reference's own GPU path on this box: the oracle module tree (= diffusers' UNet2DConditionModel restated) in
     PyTorch eager bf16 on cuda:0 -> cuDNN convs, cuBLASLt linears, SDPA attention, autograd backward, + MSE loss.  No
     optimizer step is timed here (the reference's AdamWBF16 is ~20 eager kernels per tensor), so this flatters it."""
@@ -227,17 +227,21 @@ def _torch_eager_gpu_baseline(B, H, W, steps=2):
             torch.nn.functional.mse_loss(out, tgt).backward()
 
         step()
+        step()  # two warm-ups: cuDNN / cuBLASLt heuristics and the caching allocator settle on the second pass
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        best = None
+        for _ in range(max(2, steps)):  # best of N: this is a baseline, give it every benefit
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             step()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1)
+            best = t if best is None else min(best, t)
+        ms = best
         res = {"value": round(B / (ms * 1e-3), 3), "unit": "images/s", "ms_per_step": round(ms, 1),
                "what": f"oracle UNet (diffusers module tree) in PyTorch eager bf16 on the same GPU, fwd+bwd+MSE, B={B}, "
-                       "no optimizer step"}
+                       "no optimizer step, best of 3 after 2 warm-ups"}
     except Exception as e:  # noqa: BLE001  (an OOM here must not lose the main measurement)
         res = {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
     finally:
