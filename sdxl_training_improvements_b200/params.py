@@ -122,7 +122,22 @@ class ParamStore:
         self.specs = unet_param_specs(cfg)
         self.offsets: Dict[str, int] = {}
         off = 0
-        for name, shape in self.specs:
+        # Placement order != state-dict order for one family: the cross-attention K / V projection weights of every block
+        # with the same width are laid out back to back ([to_k; to_v] per block), so that ALL of them form one
+        # [L * 2C, cross_dim] matrix — the text embeddings are step-invariant, so the 140 projections run as one GEMM per
+        # width at the start of the forward pass and their weight gradients as one GEMM at the end of the backward pass.
+        kv = [(n_, s_) for n_, s_ in self.specs if n_.endswith(".attn2.to_k.weight") or n_.endswith(".attn2.to_v.weight")]
+        rest = [(n_, s_) for n_, s_ in self.specs if not (n_.endswith(".attn2.to_k.weight") or n_.endswith(".attn2.to_v.weight"))]
+        self.kv_groups: Dict[int, List[str]] = {}     # width C -> block prefixes ("....attn2") in placement order
+        for n_, s_ in kv:
+            if n_.endswith(".to_k.weight"):
+                self.kv_groups.setdefault(int(s_[0]), []).append(n_[:-len(".to_k.weight")])
+        placed = list(rest)
+        for C_ in sorted(self.kv_groups):
+            for pfx in self.kv_groups[C_]:
+                shp = dict(kv)
+                placed += [(pfx + ".to_k.weight", shp[pfx + ".to_k.weight"]), (pfx + ".to_v.weight", shp[pfx + ".to_v.weight"])]
+        for name, shape in placed:
             n = 1
             for d in shape:
                 n *= d
@@ -208,6 +223,17 @@ class ParamStore:
         if not hasattr(self, "_numel_cache"):
             self._numel_cache = {n: int(torch.Size(s).numel()) for n, s in self.specs}
         return self._numel_cache
+
+    def kv_group_view(self, C: int, grad: bool = False) -> torch.Tensor:
+        """[L * 2C, cross_dim] view over the stacked cross-attention K/V projection weights (or their gradients)."""
+        pfxs = self.kv_groups[C]
+        cdim = self.cfg["cross_attention_dim"]
+        first = pfxs[0] + ".to_k.weight"
+        for a, b in zip(pfxs, pfxs[1:]):
+            assert self.offsets[b + ".to_k.weight"] == self.offsets[a + ".to_k.weight"] + 2 * C * cdim
+        off = self.offsets[first]
+        buf = self.grad if grad else self.flat
+        return buf[off:off + len(pfxs) * 2 * C * cdim].view(len(pfxs) * 2 * C, cdim)
 
     def adjacent(self, *names) -> bool:
         """True if the given params are stored back to back (fused-weight views are valid)."""

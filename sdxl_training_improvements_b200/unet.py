@@ -287,11 +287,9 @@ class UNetEngine:
             q_t, k_t, v_t = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
         else:
             nk = n_ctx
-            cdim = self.cfg["cross_attention_dim"]
             Wq = st.w(f"{pfx}.to_q.weight", Cc, Cc)
-            Wkv = st.w(f"{pfx}.to_k.weight", 2 * Cc, cdim)
             q = ops.linear_fwd(xn.d, Wq)
-            kv = ops.linear_fwd(ctx, Wkv)  # [B*77, 2C]
+            kv, dkv = self._kv_slices[pfx]  # [B*77, 2C] views of the grouped projection (computed once per forward)
             q_t, k_t, v_t = q, kv[:, :Cc], kv[:, Cc:]
         O, lse = ops.attn_fwd(q_t, k_t, v_t, B, heads, n, nk, scale)
         Oa = Act(O)
@@ -304,8 +302,7 @@ class UNetEngine:
                 dq_t, dk_t, dv_t = dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:]
             else:
                 dq = torch.empty_like(q)
-                dkv = torch.empty_like(kv)
-                dq_t, dk_t, dv_t = dq, dkv[:, :Cc], dkv[:, Cc:]
+                dq_t, dk_t, dv_t = dq, dkv[:, :Cc], dkv[:, Cc:]  # slice of the grouped dKV buffer (written, not accumulated)
             ops.attn_bwd(q_t, k_t, v_t, O, lse, dO, dq_t, dk_t, dv_t, B, heads, n, nk, scale)
             buf, acc = _gslot(xn)
             if is_self:
@@ -314,7 +311,7 @@ class UNetEngine:
             else:
                 ops.linear_wgrad(dq, xn.d, st.g(f"{pfx}.to_q.weight", Cc, Cc), accumulate=True)
                 ops.linear_dgrad(dq, Wq, buf, acc)
-                ops.linear_wgrad(dkv, ctx, st.g(f"{pfx}.to_k.weight", 2 * Cc, cdim), accumulate=True)
+                # the K/V projection weight gradients of all blocks run as ONE GEMM per width (see _project_context)
 
         # attention-core backward must run after to_out's backward (already on the tape) -> append
         self.tape.append(bwd)
@@ -343,6 +340,29 @@ class UNetEngine:
         for k in range(depth):
             h = self.transformer_block(h, B, H * W, Cc, f"{pfx}.transformer_blocks.{k}", ctx, n_ctx)
         return self.linear(h, f"{pfx}.proj_out.weight", Cc, Cc, f"{pfx}.proj_out.bias", residual=x)
+
+    def _project_context(self, ctx: torch.Tensor):
+        """Cross-attention K / V of EVERY transformer block in one GEMM per width: the text embeddings do not change
+        through the network, and ParamStore stacks the [to_k; to_v] weights of all blocks of a width into one
+        [L * 2C, 2048] matrix.  140 GEMMs with M = B*77 = 308 rows (and their 70 weight-gradient GEMMs with K = 308)
+        become 2 + 2 launches.  Backward: each block's attention kernel writes its dK / dV slice of `dkv_all`; the
+        closure recorded here runs LAST in the reverse replay and accumulates all weight gradients at once."""
+        st = self.store
+        self._kv_slices = {}
+        groups = []
+        for Cc, pfxs in st.kv_groups.items():
+            W = st.kv_group_view(Cc)
+            kv_all = ops.linear_fwd(ctx, W)                      # [B*77, L*2C]
+            dkv_all = torch.empty_like(kv_all)
+            for l, pfx in enumerate(pfxs):
+                self._kv_slices[pfx] = (kv_all[:, l * 2 * Cc:(l + 1) * 2 * Cc], dkv_all[:, l * 2 * Cc:(l + 1) * 2 * Cc])
+            groups.append((Cc, dkv_all))
+
+        def bwd():
+            for Cc, dkv_all in groups:
+                ops.linear_wgrad(dkv_all, ctx, st.kv_group_view(Cc, grad=True), accumulate=True)
+
+        self.tape.append(bwd)
 
     def embeddings(self, t_f32: torch.Tensor, pooled: torch.Tensor, time_ids_f32: torch.Tensor, B) -> Act:
         """time_embedding(sinus(t)) + add_embedding([pooled, sinus(time_ids)]) -> SiLU (shared by all resnets)."""
@@ -382,6 +402,7 @@ class UNetEngine:
         assert cin <= 8 and cfg["out_channels"] <= 8
         dev = x_nhwc8.device
 
+        self._project_context(ctx)  # first on the tape -> its weight-gradient GEMMs run last in the backward pass
         emb_silu = self.embeddings(t_f32, pooled, time_ids_f32, B)
 
         # conv_in: weight repacked to Cin padded to 8 (K = 72)
