@@ -265,6 +265,36 @@ int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shift, int64_t
                   const uint64_t* seed_offset, int as_written, int rng_mode, const int32_t* test_rand16, void* stream);
 int b2_axpy_bf16(void* y, const void* x, int64_t n, float alpha, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVSwitch peer memory.
+ * replaces: DistributedDataParallel's bucketed NCCL all-reduce of the UNet gradients
+ *   (src/core/distributed.py:142-163 `convert_model_to_ddp`; the reducer fires during `loss.backward()`,
+ *   ddpm_trainer.py:271).  Sum over ranks of pieces ("chunks") of the flat bf16 gradient buffer, started as soon
+ *   as the backward pass has finished writing a chunk and running beside the rest of it WITHOUT occupying SMs:
+ *   reduce-scatter and all-gather are copy-engine transfers between IPC-mapped peer buffers, ordering across
+ *   processes is by flag words (st.release.sys from a one-warp kernel; cuStreamWaitValue32 on the waiting side),
+ *   and the only arithmetic is one shared-memory-free reduce kernel over the owner's shard.  Every rank ends
+ *   with bit-identical sums (fp32 accumulation, one rounding).  csrc/dpx.cu.
+ *   b2_dpx_ipc_export / _import: cudaIpc handle (64 bytes) + byte offset of `dev_ptr` inside its allocation.
+ *   b2_dpx_alloc_flags: this rank's zeroed flag page (library-owned cudaMalloc; export it with _ipc_export).
+ *   b2_dpx_create: grad_ptrs / flag_ptrs are [world] device pointers valid IN THIS PROCESS (own entry = local
+ *       buffer, the others IPC-mapped); staging = (world-1) slots of staging_slot_elems bf16.
+ *   b2_dpx_exchange: enqueue the exchange of chunk `chunk` (< b2_dpx_max_chunks()) after everything already
+ *       enqueued on main_stream; shard_off / shard_len / staging_off ([n_ranges], elements, multiples of 8)
+ *       describe THIS rank's shard of each piece.  `seq` must increase by one per optimizer step.
+ *   b2_dpx_finish: main_stream waits until all chunks exchanged with `seq` are complete in the local buffer.
+ * ------------------------------------------------------------------------------------------------ */
+int b2_dpx_ipc_export(const void* dev_ptr, unsigned char* handle_out /* 64 bytes */, int64_t* offset_out);
+int b2_dpx_ipc_import(const unsigned char* handle /* 64 bytes */, int64_t offset, void** dev_ptr_out);
+int b2_dpx_alloc_flags(void** flags_out);
+int b2_dpx_max_chunks(void);
+int b2_dpx_create(int rank, int world, void* const* grad_ptrs, void* const* flag_ptrs, void* staging,
+                  int64_t staging_slot_elems, int n_copy_streams /* 0: default */, void** handle_out);
+int b2_dpx_exchange(void* handle, int chunk, uint32_t seq, int n_ranges, const int64_t* shard_off,
+                    const int64_t* shard_len, const int64_t* staging_off, void* main_stream);
+int b2_dpx_finish(void* handle, uint32_t seq, void* main_stream);
+int b2_dpx_destroy(void* handle);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,14 @@ SIGNATURES = {
     "b2_sumsq": [c_p, i64, c_p, c_p],
     "b2_adamw_bf16": [c_p, c_p, c_p, c_p, c_p, i64, f64, f64, f64, f64, i32, c_p, f32, f32, c_p, i32, i32, c_p, c_p],
     "b2_axpy_bf16": [c_p, c_p, i64, f32, c_p],
+    "b2_dpx_ipc_export": [c_p, c_p, C.POINTER(i64)],
+    "b2_dpx_ipc_import": [c_p, i64, C.POINTER(c_p)],
+    "b2_dpx_alloc_flags": [C.POINTER(c_p)],
+    "b2_dpx_max_chunks": [],
+    "b2_dpx_create": [i32, i32, C.POINTER(c_p), C.POINTER(c_p), c_p, i64, i32, C.POINTER(c_p)],
+    "b2_dpx_exchange": [c_p, i32, C.c_uint32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), c_p],
+    "b2_dpx_finish": [c_p, C.c_uint32, c_p],
+    "b2_dpx_destroy": [c_p],
     "b2_adamw": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, c_p, f32, f32, c_p, c_p],
 }
 _RESTYPES = {"b2_last_error": C.c_char_p, "b2_launch_count": C.c_longlong}

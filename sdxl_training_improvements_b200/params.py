@@ -164,6 +164,10 @@ class ParamStore:
         self.small_segs = self._small_segs_host.to(device)
         self.n_small = len(segs) // 3
         self.params: "OrderedDict[str, torch.nn.Parameter]" = OrderedDict()
+        # (tape position, "flat" | "small", offset, length) of every gradient view handed to a backward kernel while
+        # logging is on — dp.plan_chunks() derives from it when each piece of the gradient buffer is final
+        self.touch_log = None
+        self._touch_pos = 0
         self._build_views()
 
     @staticmethod
@@ -196,8 +200,13 @@ class ParamStore:
         off = self.offsets[name]
         return self.flat[off:off + rows * cols].view(rows, cols)
 
+    def _touch(self, kind: str, off: int, n: int):
+        if self.touch_log is not None:
+            self.touch_log.append((self._touch_pos, kind, off, n))
+
     def g(self, name: str, rows: int, cols: int) -> torch.Tensor:
         off = self.offsets[name]
+        self._touch("flat", off, rows * cols)
         return self.grad[off:off + rows * cols].view(rows, cols)
 
     def v(self, name: str) -> torch.Tensor:
@@ -208,6 +217,7 @@ class ParamStore:
     def gs(self, name: str, n: int = 0) -> torch.Tensor:
         """fp32 staging slice of a small parameter's gradient (n > 0: span `n` floats, e.g. a norm's weight+bias pair)."""
         off = self.small_off[name]
+        self._touch("small", off, n or self._numel[name])
         return self.small32[off:off + (n or self._numel[name])]
 
     def flush_small_grads(self):
@@ -216,6 +226,7 @@ class ParamStore:
 
     def gv(self, name: str) -> torch.Tensor:
         off = self.offsets[name]
+        self._touch("flat", off, self._numel[name])
         return self.grad[off:off + self._numel[name]]
 
     @property
@@ -232,6 +243,8 @@ class ParamStore:
         for a, b in zip(pfxs, pfxs[1:]):
             assert self.offsets[b + ".to_k.weight"] == self.offsets[a + ".to_k.weight"] + 2 * C * cdim
         off = self.offsets[first]
+        if grad:
+            self._touch("flat", off, len(pfxs) * 2 * C * cdim)
         buf = self.grad if grad else self.flat
         return buf[off:off + len(pfxs) * 2 * C * cdim].view(len(pfxs) * 2 * C, cdim)
 

@@ -93,7 +93,7 @@ class _FusedLoss(torch.autograd.Function):
         tape, dpred = ctx.saved
         ctx.saved = None
         ops.scale_bf16(dpred, grad_out.reshape(1).float().contiguous(), 1.0)
-        ctx.core.unet.engine.backward(dpred, tape)
+        ctx.core._backward(dpred, tape)
         return None, None, None
 
 
@@ -127,6 +127,39 @@ class FusedLossCore:
         self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         self._saved = None
         self.last: Dict[str, torch.Tensor] = {}
+        # data parallel (dp.PeerGradExchange or None): when `dp_last` is set — the trainer announces the last accumulation
+        # micro-step of an optimizer step — the backward pass hands each finished chunk of the gradient buffer to the
+        # exchange while the rest of it is still running
+        self.dp = None
+        self.dp_last = False
+
+    def _backward(self, dpred, tape):
+        x = self.dp
+        eng, st = self.unet.engine, self.unet.store
+        if x is None:
+            eng.backward(dpred, tape)
+            return
+        n_tape = len(tape[0])
+        if x.plan is None or x.plan.n_tape != n_tape:
+            # first pass: log which tape position last writes each gradient, derive the chunk plan (a pure function of
+            # the log, hence identical on every rank), exchange the whole buffer in one piece this time
+            from .dp import plan_chunks
+            st.touch_log = []
+            eng.backward(dpred, tape)
+            log, st.touch_log = st.touch_log, None
+            x.set_plan(plan_chunks(st, log, n_tape))
+            if self.dp_last:
+                x.exchange_all()
+            return
+        if not self.dp_last:
+            eng.backward(dpred, tape)
+            return
+
+        def on_cut(k):
+            x.flush_chunk(st, k)
+            x.exchange_chunk(k)
+
+        eng.backward(dpred, tape, cuts=x.plan.cuts, on_cut=on_cut)
 
     def _forward(self, latents, ctx, pooled, time_ids, t_embed, sig_or_t, weight, loss_scale, noise=None):
         """latents fp32 NCHW holding bf16-representable values; returns 0-d fp32 loss (device)."""
@@ -166,7 +199,7 @@ class FusedLossCore:
             ops.scale_bf16(dpred, grad_scale_dev, 1.0)
         elif grad_scale != 1.0:
             ops.scale_bf16(dpred, None, grad_scale)
-        self.unet.engine.backward(dpred, tape)
+        self._backward(dpred, tape)
         return loss
 
 
@@ -191,6 +224,7 @@ class GraphedMicroStep:
         self.weight = torch.ones(B, device=dev, dtype=torch.float32)
         self.grad_scale = torch.ones(1, device=dev, dtype=torch.float32)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graphs: Optional[list] = None  # data parallel: one graph per exchange chunk
         self.loss: Optional[torch.Tensor] = None
         self.launches_per_replay = 0
 
@@ -201,20 +235,53 @@ class GraphedMicroStep:
 
     def capture(self):
         """Call at an optimizer-step boundary: the warm-up passes accumulate into the gradient buffer, which is zeroed
-        again afterwards."""
+        again afterwards.  Data parallel (core.dp set): the micro-step is captured as one graph PER CHUNK of the exchange
+        plan — segment k ends when chunk k of the gradient buffer is final — sharing one memory pool and replayed in
+        order; `replay(last=True)` starts the exchange of chunk k between segment k and k+1."""
         from . import _lib
+        core = self.core
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
+        was_last, core.dp_last = core.dp_last, False
         with torch.cuda.stream(side):
-            for _ in range(2):  # lazy one-time setup (function attributes, grow-only workspaces) must not be captured
+            for _ in range(2):  # lazy one-time setup (function attributes, grow-only workspaces, the dp chunk plan)
                 self._run()
         cur.wait_stream(side)
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._run()
+        x = core.dp
+        if x is None:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._run()
+        else:
+            eng, st = core.unet.engine, core.unet.store
+            cuts = x.plan.cuts
+            self.graphs = []
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.loss = core._forward(latents=self.latents, ctx=self.ctx, pooled=self.pooled, time_ids=self.time_ids,
+                                          t_embed=self.t_embed, sig_or_t=self.sig_or_t, weight=self.weight, loss_scale=1.0)
+                tape, dpred = core._saved
+                core._saved = None
+                ops.scale_bf16(dpred, self.grad_scale, 1.0)
+                assert len(tape[0]) == x.plan.n_tape
+                order = eng.backward_begin(dpred, tape)
+                eng.backward_span(order, 0, cuts[0] + 1)
+                x.flush_chunk(st, 0)
+            self.graphs.append(g)
+            lo = cuts[0] + 1
+            for k in range(1, len(cuts)):
+                gk = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gk, pool=g.pool()):
+                    eng.backward_span(order, lo, cuts[k] + 1)
+                    x.flush_chunk(st, k)
+                lo = cuts[k] + 1
+                self.graphs.append(gk)
+            assert lo == len(order)
+            order.clear()
+        core.dp_last = was_last
         self.launches_per_replay = _lib.launch_count() - n0
         self.core.unet.store.grad.zero_()
         torch.cuda.synchronize()
@@ -233,8 +300,16 @@ class GraphedMicroStep:
             self.weight.copy_(weight, non_blocking=True)
         self.grad_scale.fill_(float(grad_scale))
 
-    def replay(self) -> torch.Tensor:
-        self.graph.replay()
+    def replay(self, last: bool = False) -> torch.Tensor:
+        """`last`: this is the last accumulation micro-step of an optimizer step -> exchange each chunk as it completes."""
+        if self.graphs is None:
+            self.graph.replay()
+            return self.loss
+        x = self.core.dp
+        for k, g in enumerate(self.graphs):
+            g.replay()
+            if last:
+                x.exchange_chunk(k)
         return self.loss
 
 
@@ -334,11 +409,16 @@ class _StepBase:
     # --- accumulate / clip / step protocol (example_method.py:124-148, 191-206; flow_matching_trainer.py:172-189) ---
     def _execute_training_step(self, batch, accumulate: bool = False, is_last_accumulation_step: bool = True):
         self._pending_grad_scale = 1.0 / self.gradient_accumulation_steps if accumulate else 1.0
-        out = self.compute_loss(batch) if not isinstance(self, B200FlowMatchingTrainer) else self.compute_loss(self.model, batch)
-        loss = out["loss"]
-        if accumulate:
-            loss = loss / self.gradient_accumulation_steps
-        loss.backward()
+        # the backward pass of the last micro-step hands finished gradient chunks to the data-parallel exchange
+        self.core.dp_last = (not accumulate) or is_last_accumulation_step
+        try:
+            out = self.compute_loss(batch) if not isinstance(self, B200FlowMatchingTrainer) else self.compute_loss(self.model, batch)
+            loss = out["loss"]
+            if accumulate:
+                loss = loss / self.gradient_accumulation_steps
+            loss.backward()
+        finally:
+            self.core.dp_last = False
         if not accumulate or is_last_accumulation_step:
             self.optimizer_step()
         return out["loss"].detach(), out["metrics"]
@@ -360,13 +440,26 @@ class _StepBase:
             gm.capture()
             self._micro_graphs[key] = gm
         gm.load(t["latents"], t["ctx"], t["pooled"], t["time_ids"], t_embed, sig_or_t, weight, self._pending_grad_scale)
-        loss = gm.replay()
+        loss = gm.replay(last=self.core.dp_last)
         self.core.last = {"numel": t["latents"].numel()}
         return _PrecomputedBackward.apply(loss.reshape(()), self.core._anchor)
 
+    def _init_dp(self):
+        """Data parallel: gradients are exchanged over NVSwitch peer memory beside the backward pass (dp.py); if that
+        cannot be set up on every rank, by ONE NCCL all-reduce of the flat buffer before the optimizer step."""
+        if self.world_size > 1:
+            from .dp import try_create_exchange
+            self.core.dp = try_create_exchange(self.unet.store.grad)
+
     def optimizer_step(self):
         if self.world_size > 1:
-            allreduce_gradients(self.unet)
+            x = self.core.dp
+            if x is not None:
+                if not x.issued:  # nobody announced the last micro-step: exchange the whole buffer now, no overlap
+                    x.exchange_all()
+                x.finish()
+            else:
+                allreduce_gradients(self.unet)
         if self.cuda_graph and hasattr(self.optimizer, "fused_step"):
             if self._opt_graph is None:
                 self._opt_graph = GraphedOptimizerStep(self.optimizer, self.clip_grad_norm, 1.0 / self.world_size).capture()
@@ -415,6 +508,7 @@ class B200DDPMTrainer(_StepBase):
         self.min_snr_gamma = getattr(m, "min_snr_gamma", None)
         self.core = FusedLossCore(self.unet, "ddpm", self.prediction_type, self.noise_scheduler.use_ztsnr,
                                   seed=int(kwargs.get("seed", 0)))
+        self._init_dp()
 
     def training_step(self, batch: Dict[str, Any], noise: Optional[torch.Tensor] = None,
                       timesteps: Optional[torch.Tensor] = None) -> Dict[str, Any]:
@@ -461,6 +555,7 @@ class B200FlowMatchingTrainer(_StepBase):
     def __init__(self, model, optimizer, train_dataloader=None, device=None, wandb_logger=None, config=None, **kwargs):
         super().__init__(model, optimizer, train_dataloader, device, wandb_logger, config, **kwargs)
         self.core = FusedLossCore(self.unet, "flow_matching", seed=int(kwargs.get("seed", 0)))
+        self._init_dp()
 
     def compute_loss(self, model, batch: Dict[str, Any], generator: Optional[torch.Generator] = None,
                      x0: Optional[torch.Tensor] = None, t: Optional[torch.Tensor] = None) -> Dict[str, Any]:

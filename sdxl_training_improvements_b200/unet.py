@@ -482,14 +482,38 @@ class UNetEngine:
         self.tape, self._out = [], None
         return t
 
-    def backward(self, dpred_nhwc8: torch.Tensor, saved=None):
-        """Replay a tape: fills ParamStore.grad (+=).  dpred: [B*H*W, 8] bf16 (pad channels must be zero)."""
+    def backward(self, dpred_nhwc8: torch.Tensor, saved=None, cuts=None, on_cut=None):
+        """Replay a tape: fills ParamStore.grad (+=).  dpred: [B*H*W, 8] bf16 (pad channels must be zero).
+        `cuts` (ascending replay positions, the last one = end of tape) + `on_cut(k)`: data-parallel hook — called right
+        after position cuts[k] has run, when chunk k of the gradient buffer is final (dp.plan_chunks); the hook flushes
+        that chunk's small-parameter gradients and starts its exchange."""
+        order = self.backward_begin(dpred_nhwc8, saved)
+        if cuts is None:
+            self.backward_span(order, 0, len(order))
+            self.store.flush_small_grads()  # biases / norm affine: fp32 staging -> flat bf16 gradient buffer (+=)
+        else:
+            lo = 0
+            for k, c in enumerate(cuts):
+                self.backward_span(order, lo, c + 1)
+                lo = c + 1
+                on_cut(k)
+            assert lo == len(order), "the last cut must be the end of the tape"
+        order.clear()
+
+    def backward_begin(self, dpred_nhwc8: torch.Tensor, saved=None) -> List[Callable[[], None]]:
+        """Closures of one forward pass in replay (reverse) order; run them with backward_span()."""
         tape, out = saved if saved is not None else self.detach_tape()
         out.g = dpred_nhwc8
-        for fn in reversed(tape):
-            fn()
+        order = list(reversed(tape))
         tape.clear()
-        self.store.flush_small_grads()  # biases / norm affine: fp32 staging -> flat bf16 gradient buffer (+=)
+        return order
+
+    def backward_span(self, order, lo: int, hi: int):
+        st = self.store
+        for i in range(lo, hi):
+            st._touch_pos = i
+            order[i]()
+            order[i] = None  # release the closure's activations as soon as it has run
 
 
 class _UNetFunction(torch.autograd.Function):
