@@ -393,6 +393,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e = float(t[0]), float(t[1])
 
+    if rank == 0 and core.dp is not None and core.dp.plan is not None:
+        print(core.dp.plan.describe(), file=sys.stderr, flush=True)
     if rank == 0:
         step_flops = train_step_flops(None, H, W) * B * A
         value = world * B * A / (ms_dev * 1e-3)

@@ -43,6 +43,14 @@ class ChunkPlan:
     def n_chunks(self) -> int:
         return len(self.cuts)
 
+    def describe(self) -> str:
+        rows = []
+        for k, (c, rg) in enumerate(zip(self.cuts, self.ranges)):
+            n = sum(ln for _, ln in rg)
+            rows.append(f"chunk {k}: final after tape[{c}] of {self.n_tape}, {n * 2 / 1e6:9.1f} MB in {len(rg)} piece(s), "
+                        f"{len(self.small_segs[k]) // 3} small params")
+        return "\n".join(rows)
+
 
 def _layout(store):
     """[(offset, padded length, name)] of the flat buffer in address order; padding belongs to the preceding parameter."""
@@ -84,6 +92,9 @@ def plan_chunks(store, log, n_tape: int, target_chunks: int = 10, min_elems: int
     chunk, final at the end of the backward pass."""
     lay = _layout(store)
     last = last_touch_positions(store, log)
+    never = [name for _, _, name in lay if last[name] < 0]
+    if never:  # a gradient the log did not see could be exchanged before it is written: refuse to plan
+        raise RuntimeError(f"plan_chunks: no gradient write observed for {len(never)} parameter(s), e.g. {never[:3]}")
     total = sum(n for _, n, _ in lay)
     target = max(total // max(target_chunks, 1), min_elems, 1)
     by_pos: Dict[int, int] = {}

@@ -175,7 +175,7 @@ class UNetEngine:
         implicit = (stride == 1 and not up and Wk is None and Npad is None
                     and ops.conv3x3_implicit_ok(B, H, W, Cin, Cout))
         Wk = st.w(wname, Cout, K) if Wk is None else Wk
-        gWk = st.g(wname, Cout, K) if gWk is None else gWk
+        gWk_given = gWk
         res = residual.d if residual is not None else None
         if implicit:
             # implicit GEMM: TMA gathers the shifted pixel blocks straight from the NHWC activation (no col buffer)
@@ -196,6 +196,8 @@ class UNetEngine:
 
         def bwd():
             dy = out.g
+            # the gradient view is taken HERE, not in forward: ParamStore logs when each gradient is written (dp.py)
+            gWk = st.g(wname, Cout, K) if gWk_given is None else gWk_given
             if implicit:
                 ops.conv3x3_wgrad(dy, x.d, gWk, B, H, W, Cin, Cout, accumulate=True)
             else:
@@ -287,6 +289,9 @@ class UNetEngine:
             q_t, k_t, v_t = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
         else:
             nk = n_ctx
+            kv_bwd = self._kv_wgrad.pop(Cc, None)
+            if kv_bwd is not None:
+                self.tape.append(kv_bwd)
             Wq = st.w(f"{pfx}.to_q.weight", Cc, Cc)
             q = ops.linear_fwd(xn.d, Wq)
             kv, dkv = self._kv_slices[pfx]  # [B*77, 2C] views of the grouped projection (computed once per forward)
@@ -346,23 +351,24 @@ class UNetEngine:
         through the network, and ParamStore stacks the [to_k; to_v] weights of all blocks of a width into one
         [L * 2C, 2048] matrix.  140 GEMMs with M = B*77 = 308 rows (and their 70 weight-gradient GEMMs with K = 308)
         become 2 + 2 launches.  Backward: each block's attention kernel writes its dK / dV slice of `dkv_all`; the
-        closure recorded here runs LAST in the reverse replay and accumulates all weight gradients at once."""
+        closure built here accumulates all weight gradients of a width at once."""
         st = self.store
         self._kv_slices = {}
-        groups = []
+        self._kv_wgrad = {}
         for Cc, pfxs in st.kv_groups.items():
             W = st.kv_group_view(Cc)
             kv_all = ops.linear_fwd(ctx, W)                      # [B*77, L*2C]
             dkv_all = torch.empty_like(kv_all)
             for l, pfx in enumerate(pfxs):
                 self._kv_slices[pfx] = (kv_all[:, l * 2 * Cc:(l + 1) * 2 * Cc], dkv_all[:, l * 2 * Cc:(l + 1) * 2 * Cc])
-            groups.append((Cc, dkv_all))
 
-        def bwd():
-            for Cc, dkv_all in groups:
+            def bwd(Cc=Cc, dkv_all=dkv_all):
                 ops.linear_wgrad(dkv_all, ctx, st.kv_group_view(Cc, grad=True), accumulate=True)
 
-        self.tape.append(bwd)
+            # recorded on the tape by the FIRST cross-attention of this width in the forward pass (see attention()), so
+            # that in the reverse replay it runs right after the last block that writes into dkv_all — not at the very end
+            # of the backward pass: the stacked K/V gradients (0.73 GB) then join an early data-parallel exchange chunk
+            self._kv_wgrad[Cc] = bwd
 
     def embeddings(self, t_f32: torch.Tensor, pooled: torch.Tensor, time_ids_f32: torch.Tensor, B) -> Act:
         """time_embedding(sinus(t)) + add_embedding([pooled, sinus(time_ids)]) -> SiLU (shared by all resnets)."""
