@@ -275,24 +275,35 @@ int b2_axpy_bf16(void* y, const void* x, int64_t n, float alpha, void* stream);
  *   processes is by flag words (st.release.sys from a one-warp kernel; cuStreamWaitValue32 on the waiting side),
  *   and the only arithmetic is one shared-memory-free reduce kernel over the owner's shard.  Every rank ends
  *   with bit-identical sums (fp32 accumulation, one rounding).  csrc/dpx.cu.
+ *   Three transports, same protocol (b2_dpx_create `mode`): 0 "ce_pull" (reduce-scatter = copy-engine reads from the
+ *   peers), 1 "ce_push" (reduce-scatter = copy-engine writes into the owner's staging slots; NVLink carries posted
+ *   writes only), 2 "sm" (one shared-memory-free kernel of short 128-thread CTAs that co-reside with the persistent
+ *   GEMM / attention CTAs: 16-byte loads of the shard from every peer, fp32 sum, 16-byte stores to every peer; <= 8
+ *   ranks, no staging).
  *   b2_dpx_ipc_export / _import: cudaIpc handle (64 bytes) + byte offset of `dev_ptr` inside its allocation.
  *   b2_dpx_alloc_flags: this rank's zeroed flag page (library-owned cudaMalloc; export it with _ipc_export).
- *   b2_dpx_create: grad_ptrs / flag_ptrs are [world] device pointers valid IN THIS PROCESS (own entry = local
- *       buffer, the others IPC-mapped); staging = (world-1) slots of staging_slot_elems bf16.
+ *   b2_dpx_create: grad_ptrs / flag_ptrs / staging_ptrs are [world] device pointers valid IN THIS PROCESS (own entry =
+ *       local buffer, the others IPC-mapped; peer staging pointers are used by mode 1 only); every staging buffer is
+ *       (world-1) slots of staging_slot_elems bf16.
  *   b2_dpx_exchange: enqueue the exchange of chunk `chunk` (< b2_dpx_max_chunks()) after everything already
- *       enqueued on main_stream; shard_off / shard_len / staging_off ([n_ranges], elements, multiples of 8)
- *       describe THIS rank's shard of each piece.  `seq` must increase by one per optimizer step.
+ *       enqueued on main_stream.  The chunk is n_ranges pieces [range_off, range_off + range_len) of the buffer
+ *       (elements, multiples of 8); each piece is cut into `world` shards of ceil(len / world) rounded up to 8, rank r
+ *       reduces shard r.  staging_base: element offset of the chunk's region inside a staging slot (regions of
+ *       chunks exchanged in the same step must not overlap).  `seq` must increase by one per optimizer step.
  *   b2_dpx_finish: main_stream waits until all chunks exchanged with `seq` are complete in the local buffer.
+ *   b2_dpx_memcpy_async: raw async copy between local / IPC-mapped pointers (copy-engine probe).
  * ------------------------------------------------------------------------------------------------ */
 int b2_dpx_ipc_export(const void* dev_ptr, unsigned char* handle_out /* 64 bytes */, int64_t* offset_out);
 int b2_dpx_ipc_import(const unsigned char* handle /* 64 bytes */, int64_t offset, void** dev_ptr_out);
 int b2_dpx_alloc_flags(void** flags_out);
 int b2_dpx_max_chunks(void);
-int b2_dpx_create(int rank, int world, void* const* grad_ptrs, void* const* flag_ptrs, void* staging,
-                  int64_t staging_slot_elems, int n_copy_streams /* 0: default */, void** handle_out);
-int b2_dpx_exchange(void* handle, int chunk, uint32_t seq, int n_ranges, const int64_t* shard_off,
-                    const int64_t* shard_len, const int64_t* staging_off, void* main_stream);
+int b2_dpx_create(int rank, int world, int mode, void* const* grad_ptrs, void* const* flag_ptrs,
+                  void* const* staging_ptrs, int64_t staging_slot_elems, int n_copy_streams /* 0: default */,
+                  void** handle_out);
+int b2_dpx_exchange(void* handle, int chunk, uint32_t seq, int n_ranges, const int64_t* range_off,
+                    const int64_t* range_len, int64_t staging_base, void* main_stream);
 int b2_dpx_finish(void* handle, uint32_t seq, void* main_stream);
+int b2_dpx_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
 int b2_dpx_destroy(void* handle);
 
 #ifdef __cplusplus

@@ -97,8 +97,9 @@ SIGNATURES = {
     "b2_dpx_ipc_import": [c_p, i64, C.POINTER(c_p)],
     "b2_dpx_alloc_flags": [C.POINTER(c_p)],
     "b2_dpx_max_chunks": [],
-    "b2_dpx_create": [i32, i32, C.POINTER(c_p), C.POINTER(c_p), c_p, i64, i32, C.POINTER(c_p)],
-    "b2_dpx_exchange": [c_p, i32, C.c_uint32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), c_p],
+    "b2_dpx_create": [i32, i32, i32, C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_p), i64, i32, C.POINTER(c_p)],
+    "b2_dpx_exchange": [c_p, i32, C.c_uint32, i32, C.POINTER(i64), C.POINTER(i64), i64, c_p],
+    "b2_dpx_memcpy_async": [c_p, c_p, i64, c_p],
     "b2_dpx_finish": [c_p, C.c_uint32, c_p],
     "b2_dpx_destroy": [c_p],
     "b2_adamw": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, c_p, f32, f32, c_p, c_p],

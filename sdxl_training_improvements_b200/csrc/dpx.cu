@@ -15,6 +15,14 @@
 //        "delivered(c)".
 //   Before the optimizer step the main stream waits (stream memory op) for delivered(c) from every peer for every chunk.
 //
+// Three transports share that protocol (b2_dpx_create `mode`; dp.py picks one by timing them at start-up):
+//   0 "ce_pull": as above.
+//   1 "ce_push": the reduce-scatter is also a PUSH — r copies its piece of peer p's shard into p's staging slot and signals
+//      "pushed(c)"; NVLink then carries posted writes only (no read round trips).  Every chunk has its own staging region,
+//      so a sender never needs to ask whether the receiver's slot is free.
+//   2 "sm": one shared-memory-free kernel of many short 128-thread CTAs (they co-reside with the persistent GEMM /
+//      attention CTAs: 0 smem, ~5 K registers) reads shard r from every peer with 16-byte loads, sums in fp32 and stores
+//      the bf16 result into every peer's buffer — reduce-scatter and all-gather fused, no staging.
 // All of it runs on side streams owned by this object; the only coupling to the compute stream is one event at the cut
 // and one event before the optimizer.  Every rank ends with bit-identical reduced gradients (the owner of a shard is the
 // only one that sums it).  Host-side runtime in C++ behind the C ABI (include/sdxl_b200.h, "b2_dpx_*").
@@ -99,7 +107,82 @@ __global__ void __launch_bounds__(128) dpx_reduce_kernel(bf16* __restrict__ grad
   }
 }
 
+struct PeerBufs {
+  bf16* p[DPX_MAX_WORLD];
+};
+
+// "sm" transport: out_p[i] = bf16( sum_q fp32(in_q[i]) ) for every peer p, i over this rank's shard.  Each thread owns
+// its vectors from load to store, so reading and writing the same addresses in place is ordered by data dependence.
+template <int W, int U>
+__global__ void __launch_bounds__(128) dpx_fused_kernel(PeerBufs bufs, long long off, long long nvec) {
+  const long long base = ((long long)blockIdx.x * blockDim.x) * U + threadIdx.x;
+  bf16x8 t[U][W];
+  bool live[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long long v = base + (long long)u * blockDim.x;
+    live[u] = v < nvec;
+    if (live[u]) {
+#pragma unroll
+      for (int q = 0; q < W; ++q) t[u][q] = ld8(bufs.p[q] + off + v * 8);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!live[u]) continue;
+    const long long v = base + (long long)u * blockDim.x;
+    float acc[8];
+    unpack8(t[u][0], acc);
+#pragma unroll
+    for (int q = 1; q < W; ++q) {
+      float f[8];
+      unpack8(t[u][q], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+    const bf16x8 r = pack8(acc);
+#pragma unroll
+    for (int q = 0; q < W; ++q) st8(bufs.p[q] + off + v * 8, r);
+  }
+}
+
+// U vectors per thread: 2 up to four ranks, 1 beyond (register budget: the CTA must fit beside a 320-thread x 168-register
+// attention CTA, i.e. stay under ~11 K registers)
+template <int W>
+static void launch_fused(const PeerBufs& b, long long off, long long nvec, cudaStream_t s) {
+  constexpr int U = W <= 4 ? 2 : 1;
+  const long long blocks = (nvec + 128 * U - 1) / (128 * U);
+  dpx_fused_kernel<W, U><<<(unsigned)blocks, 128, 0, s>>>(b, off, nvec);
+}
+static bool launch_fused_any(int world, const PeerBufs& b, long long off, long long nvec, cudaStream_t s) {
+  switch (world) {
+    case 2: launch_fused<2>(b, off, nvec, s); return true;
+    case 3: launch_fused<3>(b, off, nvec, s); return true;
+    case 4: launch_fused<4>(b, off, nvec, s); return true;
+    case 5: launch_fused<5>(b, off, nvec, s); return true;
+    case 6: launch_fused<6>(b, off, nvec, s); return true;
+    case 7: launch_fused<7>(b, off, nvec, s); return true;
+    case 8: launch_fused<8>(b, off, nvec, s); return true;
+    default: return false;
+  }
+}
+
+// reduce-scatter ownership, the same arithmetic as dp.shard_plan(): a piece of `len` elements is cut into `world` shards
+// of ceil(len / world) rounded up to 8 elements
+static inline long long shard_size(long long len, int world) { return ((len + world - 1) / world + 7) / 8 * 8; }
+static inline void shard_of(long long off, long long len, int world, int r, long long* so, long long* sl) {
+  const long long ss = shard_size(len, world);
+  long long lo = (long long)r * ss;
+  if (lo > len) lo = len;
+  long long hi = lo + ss;
+  if (hi > len) hi = len;
+  *so = off + lo;
+  *sl = hi - lo;
+}
+
 struct Dpx {
+  int mode = 0;                         // 0 ce_pull, 1 ce_push, 2 sm
+  bf16* peer_staging[DPX_MAX_WORLD] = {};  // ce_push: every rank's staging base
   int rank = 0, world = 1;
   bf16* grad[DPX_MAX_WORLD] = {};      // [rank] = local buffer, others IPC-mapped
   uint32_t* flags[DPX_MAX_WORLD] = {};  // [rank] = local flag page
@@ -185,21 +268,27 @@ extern "C" int b2_dpx_alloc_flags(void** flags_out) {
 extern "C" int b2_dpx_max_chunks(void) { return DPX_MAX_CHUNKS; }
 
 // ---- object ----------------------------------------------------------------------------------------------------
-extern "C" int b2_dpx_create(int rank, int world, void* const* grad_ptrs, void* const* flag_ptrs, void* staging,
-                             int64_t staging_slot_elems, int n_copy_streams, void** handle_out) {
+extern "C" int b2_dpx_create(int rank, int world, int mode, void* const* grad_ptrs, void* const* flag_ptrs,
+                             void* const* staging_ptrs, int64_t staging_slot_elems, int n_copy_streams, void** handle_out) {
   B2_REQUIRE(world >= 2 && world <= DPX_MAX_WORLD && rank >= 0 && rank < world, "b2_dpx_create: bad rank/world");
-  B2_REQUIRE(grad_ptrs && flag_ptrs && staging && handle_out && staging_slot_elems > 0, "b2_dpx_create: bad args");
-  B2_REQUIRE(staging_slot_elems % 8 == 0 && ((uintptr_t)staging & 15) == 0, "b2_dpx_create: staging must be 16-byte aligned");
+  B2_REQUIRE(mode >= 0 && mode <= 2, "b2_dpx_create: mode must be 0 (ce_pull), 1 (ce_push) or 2 (sm)");
+  B2_REQUIRE(mode != 2 || world <= 8, "b2_dpx_create: the sm transport is instantiated for up to 8 ranks");
+  B2_REQUIRE(grad_ptrs && flag_ptrs && staging_ptrs && handle_out && staging_slot_elems > 0, "b2_dpx_create: bad args");
+  B2_REQUIRE(staging_slot_elems % 8 == 0, "b2_dpx_create: staging slot must be a multiple of 8 elements");
   Dpx* d = new Dpx();
   d->rank = rank;
   d->world = world;
+  d->mode = mode;
   for (int p = 0; p < world; ++p) {
     B2_REQUIRE(grad_ptrs[p] && flag_ptrs[p], "b2_dpx_create: null peer pointer");
     B2_REQUIRE(((uintptr_t)grad_ptrs[p] & 15) == 0, "b2_dpx_create: gradient buffers must be 16-byte aligned");
+    B2_REQUIRE(mode == 2 || (staging_ptrs[p] && ((uintptr_t)staging_ptrs[p] & 15) == 0) || (mode == 0 && p != rank),
+               "b2_dpx_create: staging pointers must be 16-byte aligned (ce_push needs every rank's)");
     d->grad[p] = (bf16*)grad_ptrs[p];
     d->flags[p] = (uint32_t*)flag_ptrs[p];
+    d->peer_staging[p] = (bf16*)staging_ptrs[p];
   }
-  d->staging = (bf16*)staging;
+  d->staging = (bf16*)staging_ptrs[rank];
   d->slot_stride = staging_slot_elems;
   d->wait32 = (WaitValue32Fn)driver_entry("cuStreamWaitValue32");
   if (!d->wait32) {
@@ -240,78 +329,158 @@ extern "C" int b2_dpx_destroy(void* handle) {
   return B2_OK;
 }
 
-// Exchange (sum over ranks) of this rank's view of one chunk: `n_ranges` pieces of the gradient buffer, for each the
-// element offset / length of THIS RANK'S SHARD (multiples of 8; length may be 0) and its offset inside a staging slot.
+namespace b2 {
+static int dpx_wait_flag(Dpx* d, cudaStream_t s, int kind, int chunk, int src, uint32_t seq) {
+  CUresult r = d->wait32((CUstream)s, (CUdeviceptr)(d->flags[d->rank] + flag_word(kind, chunk, src)), seq,
+                         CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) {
+    set_error("dpx: cuStreamWaitValue32 failed (%d)", (int)r);
+    return B2_ERR_CUDA;
+  }
+  return B2_OK;
+}
+static int dpx_signal(Dpx* d, int kind, int chunk, uint32_t seq) {
+  PeerFlags pf;
+  for (int p = 0; p < DPX_MAX_WORLD; ++p) pf.p[p] = p < d->world ? d->flags[p] : nullptr;
+  dpx_signal_kernel<<<1, 32, 0, d->xs>>>(pf, d->world, d->rank, flag_word(kind, chunk, d->rank), seq);
+  return check_launch("dpx_signal");
+}
+// every copy stream waits for what has been enqueued on xs so far
+static int dpx_fork(Dpx* d) {
+  DPX_CUDA(cudaEventRecord(d->ev_red, d->xs));
+  for (auto s : d->cs) DPX_CUDA(cudaStreamWaitEvent(s, d->ev_red, 0));
+  return B2_OK;
+}
+// xs waits for everything enqueued on the copy streams so far
+static int dpx_join(Dpx* d) {
+  for (size_t i = 0; i < d->cs.size(); ++i) {
+    DPX_CUDA(cudaEventRecord(d->ev_cs[i], d->cs[i]));
+    DPX_CUDA(cudaStreamWaitEvent(d->xs, d->ev_cs[i], 0));
+  }
+  return B2_OK;
+}
+}  // namespace b2
+
+// Exchange (sum over ranks) of one chunk: `n_ranges` pieces [range_off, range_off + range_len) of the gradient buffer
+// (elements, multiples of 8).  Each piece is cut into `world` shards (shard_of); rank r owns shard r.  staging_base:
+// element offset of this chunk's region inside a staging slot (ce_push: regions of different chunks must not overlap).
 // Work issued before the call on `main_stream` is ordered before the exchange; nothing is made to wait for it.
-extern "C" int b2_dpx_exchange(void* handle, int chunk, uint32_t seq, int n_ranges, const int64_t* shard_off,
-                               const int64_t* shard_len, const int64_t* staging_off, void* main_stream) {
+extern "C" int b2_dpx_exchange(void* handle, int chunk, uint32_t seq, int n_ranges, const int64_t* range_off,
+                               const int64_t* range_len, int64_t staging_base, void* main_stream) {
   Dpx* d = (Dpx*)handle;
-  B2_REQUIRE(d && chunk >= 0 && chunk < DPX_MAX_CHUNKS && n_ranges >= 0, "b2_dpx_exchange: bad args");
-  for (int i = 0; i < n_ranges; ++i)
-    B2_REQUIRE(shard_off[i] % 8 == 0 && shard_len[i] % 8 == 0 && staging_off[i] % 8 == 0 && shard_len[i] >= 0 &&
-                   staging_off[i] + shard_len[i] <= d->slot_stride,
-               "b2_dpx_exchange: shard %d not 16-byte granular or outside the staging slot", i);
+  B2_REQUIRE(d && chunk >= 0 && chunk < DPX_MAX_CHUNKS && n_ranges >= 0 && staging_base >= 0 && staging_base % 8 == 0,
+             "b2_dpx_exchange: bad args");
+  const int W = d->world, R = d->rank, ncs = (int)d->cs.size();
+  long long used = staging_base;
+  for (int i = 0; i < n_ranges; ++i) {
+    B2_REQUIRE(range_off[i] % 8 == 0 && range_len[i] % 8 == 0 && range_len[i] >= 0,
+               "b2_dpx_exchange: piece %d is not 16-byte granular", i);
+    used += shard_size(range_len[i], W);
+  }
+  B2_REQUIRE(d->mode == 2 || used <= d->slot_stride, "b2_dpx_exchange: chunk does not fit its staging slot");
   if (!d->pending.empty() && d->pending_seq != seq) {
     set_error("b2_dpx_exchange: chunks of sequence %u are still pending (call b2_dpx_finish first)", d->pending_seq);
     return B2_ERR_ARG;
   }
-  const int W = d->world, R = d->rank, ncs = (int)d->cs.size();
-  PeerFlags pf;
-  for (int p = 0; p < DPX_MAX_WORLD; ++p) pf.p[p] = p < W ? d->flags[p] : nullptr;
-
+  int rc;
   DPX_CUDA(cudaEventRecord(d->ev_in, (cudaStream_t)main_stream));
   DPX_CUDA(cudaStreamWaitEvent(d->xs, d->ev_in, 0));
-  // 1. ready(c): my part of chunk c is final
-  dpx_signal_kernel<<<1, 32, 0, d->xs>>>(pf, W, R, flag_word(0, chunk, R), seq);
-  if (int rc = check_launch("dpx_signal(ready)")) return rc;
-  DPX_CUDA(cudaEventRecord(d->ev_red, d->xs));  // reused below; here: "ready signalled" (orders copy streams after the cut)
-  // 2. reduce-scatter by copy engine: slot j holds peer (R + 1 + j) % W's copy of my shard
-  for (int i = 0; i < ncs; ++i) DPX_CUDA(cudaStreamWaitEvent(d->cs[i], d->ev_red, 0));
+
+  if (d->mode == 2) {
+    // ---- sm: ready -> wait all -> fused reduce + broadcast kernel -> delivered
+    if ((rc = dpx_signal(d, 0, chunk, seq))) return rc;
+    for (int p = 0; p < W; ++p)
+      if (p != R && (rc = dpx_wait_flag(d, d->xs, 0, chunk, p, seq))) return rc;
+    PeerBufs pb;
+    for (int q = 0; q < DPX_MAX_WORLD; ++q) pb.p[q] = q < W ? d->grad[(R + q) % W] : nullptr;  // own copy first
+    for (int i = 0; i < n_ranges; ++i) {
+      long long so, sl;
+      shard_of(range_off[i], range_len[i], W, R, &so, &sl);
+      if (sl == 0) continue;
+      if (!launch_fused_any(W, pb, so, sl / 8, d->xs)) {
+        set_error("b2_dpx_exchange: sm transport has no instantiation for %d ranks", W);
+        return B2_ERR_ARG;
+      }
+      if ((rc = check_launch("dpx_fused"))) return rc;
+    }
+    if ((rc = dpx_signal(d, 1, chunk, seq))) return rc;
+    d->pending.push_back(chunk);
+    d->pending_seq = seq;
+    return B2_OK;
+  }
+
+  if (d->mode == 0) {
+    // ---- ce_pull: ready -> (per peer: wait its ready, pull my shard from it)
+    if ((rc = dpx_signal(d, 0, chunk, seq))) return rc;
+    if ((rc = dpx_fork(d))) return rc;
+    for (int j = 0; j < W - 1; ++j) {
+      const int p = (R + 1 + j) % W;
+      cudaStream_t s = d->cs[j % ncs];
+      if ((rc = dpx_wait_flag(d, s, 0, chunk, p, seq))) return rc;
+      long long so_stage = staging_base;
+      for (int i = 0; i < n_ranges; ++i) {
+        long long so, sl;
+        shard_of(range_off[i], range_len[i], W, R, &so, &sl);
+        if (sl)
+          DPX_CUDA(cudaMemcpyAsync(d->staging + (long long)j * d->slot_stride + so_stage, d->grad[p] + so,
+                                   (size_t)sl * sizeof(bf16), cudaMemcpyDefault, s));
+        so_stage += shard_size(range_len[i], W);
+      }
+    }
+    if ((rc = dpx_join(d))) return rc;
+  } else {
+    // ---- ce_push: push my copy of peer p's shard into p's staging slot, then tell everyone; wait for everyone's pushes.
+    // My slot at receiver p is j = (R - p - 1) mod W  (slot j of rank p holds the copy of rank (p + 1 + j) mod W).
+    if ((rc = dpx_fork(d))) return rc;
+    for (int jj = 0; jj < W - 1; ++jj) {
+      const int p = (R + 1 + jj) % W;
+      const int j = ((R - p - 1) % W + W) % W;
+      cudaStream_t s = d->cs[jj % ncs];
+      long long so_stage = staging_base;
+      for (int i = 0; i < n_ranges; ++i) {
+        long long so, sl;
+        shard_of(range_off[i], range_len[i], W, p, &so, &sl);
+        if (sl)
+          DPX_CUDA(cudaMemcpyAsync(d->peer_staging[p] + (long long)j * d->slot_stride + so_stage, d->grad[R] + so,
+                                   (size_t)sl * sizeof(bf16), cudaMemcpyDefault, s));
+        so_stage += shard_size(range_len[i], W);
+      }
+    }
+    if ((rc = dpx_join(d))) return rc;
+    if ((rc = dpx_signal(d, 0, chunk, seq))) return rc;  // "pushed(c)"
+    for (int p = 0; p < W; ++p)
+      if (p != R && (rc = dpx_wait_flag(d, d->xs, 0, chunk, p, seq))) return rc;
+  }
+  // ---- reduce my shard (staged copies of every peer are in my slots)
+  {
+    long long so_stage = staging_base;
+    for (int i = 0; i < n_ranges; ++i) {
+      long long so, sl;
+      shard_of(range_off[i], range_len[i], W, R, &so, &sl);
+      if (sl) {
+        const long long nvec = sl / 8;
+        const long long blocks = (nvec + 128 * 4 - 1) / (128 * 4);
+        dpx_reduce_kernel<<<(unsigned)blocks, 128, 0, d->xs>>>(d->grad[R] + so, d->staging + so_stage, d->slot_stride, W - 1,
+                                                               nvec);
+        if ((rc = check_launch("dpx_reduce"))) return rc;
+      }
+      so_stage += shard_size(range_len[i], W);
+    }
+  }
+  // ---- all-gather by copy engine: push the reduced shard into every peer's gradient buffer, then "delivered(c)"
+  if ((rc = dpx_fork(d))) return rc;
   for (int j = 0; j < W - 1; ++j) {
     const int p = (R + 1 + j) % W;
     cudaStream_t s = d->cs[j % ncs];
-    CUresult r = d->wait32((CUstream)s, (CUdeviceptr)(d->flags[R] + flag_word(0, chunk, p)), seq, CU_STREAM_WAIT_VALUE_GEQ);
-    if (r != CUDA_SUCCESS) {
-      set_error("b2_dpx_exchange: cuStreamWaitValue32 failed (%d)", (int)r);
-      return B2_ERR_CUDA;
-    }
     for (int i = 0; i < n_ranges; ++i) {
-      if (shard_len[i] == 0) continue;
-      DPX_CUDA(cudaMemcpyAsync(d->staging + (long long)j * d->slot_stride + staging_off[i], d->grad[p] + shard_off[i],
-                               (size_t)shard_len[i] * sizeof(bf16), cudaMemcpyDefault, s));
+      long long so, sl;
+      shard_of(range_off[i], range_len[i], W, R, &so, &sl);
+      if (sl)
+        DPX_CUDA(cudaMemcpyAsync(d->grad[p] + so, d->grad[R] + so, (size_t)sl * sizeof(bf16), cudaMemcpyDefault, s));
     }
   }
-  for (int i = 0; i < ncs; ++i) {
-    DPX_CUDA(cudaEventRecord(d->ev_cs[i], d->cs[i]));
-    DPX_CUDA(cudaStreamWaitEvent(d->xs, d->ev_cs[i], 0));
-  }
-  // 3. reduce my shard
-  for (int i = 0; i < n_ranges; ++i) {
-    if (shard_len[i] == 0) continue;
-    const long long nvec = shard_len[i] / 8;
-    const long long blocks = (nvec + 128 * 4 - 1) / (128 * 4);
-    dpx_reduce_kernel<<<(unsigned)blocks, 128, 0, d->xs>>>(d->grad[R] + shard_off[i], d->staging + staging_off[i],
-                                                           d->slot_stride, W - 1, nvec);
-    if (int rc = check_launch("dpx_reduce")) return rc;
-  }
-  DPX_CUDA(cudaEventRecord(d->ev_red, d->xs));
-  // 4. all-gather by copy engine: push the reduced shard into every peer's buffer
-  for (int i = 0; i < ncs; ++i) DPX_CUDA(cudaStreamWaitEvent(d->cs[i], d->ev_red, 0));
-  for (int j = 0; j < W - 1; ++j) {
-    const int p = (R + 1 + j) % W;
-    cudaStream_t s = d->cs[j % ncs];
-    for (int i = 0; i < n_ranges; ++i) {
-      if (shard_len[i] == 0) continue;
-      DPX_CUDA(cudaMemcpyAsync(d->grad[p] + shard_off[i], d->grad[R] + shard_off[i], (size_t)shard_len[i] * sizeof(bf16),
-                               cudaMemcpyDefault, s));
-    }
-  }
-  for (int i = 0; i < ncs; ++i) {
-    DPX_CUDA(cudaEventRecord(d->ev_cs[i], d->cs[i]));
-    DPX_CUDA(cudaStreamWaitEvent(d->xs, d->ev_cs[i], 0));
-  }
-  dpx_signal_kernel<<<1, 32, 0, d->xs>>>(pf, W, R, flag_word(1, chunk, R), seq);
-  if (int rc = check_launch("dpx_signal(delivered)")) return rc;
+  if ((rc = dpx_join(d))) return rc;
+  if ((rc = dpx_signal(d, 1, chunk, seq))) return rc;
   d->pending.push_back(chunk);
   d->pending_seq = seq;
   return B2_OK;
@@ -324,19 +493,20 @@ extern "C" int b2_dpx_finish(void* handle, uint32_t seq, void* main_stream) {
   B2_REQUIRE(d, "b2_dpx_finish: bad args");
   if (d->pending.empty()) return B2_OK;
   B2_REQUIRE(d->pending_seq == seq, "b2_dpx_finish: sequence %u does not match the pending exchange %u", seq, d->pending_seq);
-  for (int chunk : d->pending) {
-    for (int p = 0; p < d->world; ++p) {
-      if (p == d->rank) continue;
-      CUresult r = d->wait32((CUstream)d->xs, (CUdeviceptr)(d->flags[d->rank] + flag_word(1, chunk, p)), seq,
-                             CU_STREAM_WAIT_VALUE_GEQ);
-      if (r != CUDA_SUCCESS) {
-        set_error("b2_dpx_finish: cuStreamWaitValue32 failed (%d)", (int)r);
-        return B2_ERR_CUDA;
-      }
-    }
-  }
+  int rc;
+  for (int chunk : d->pending)
+    for (int p = 0; p < d->world; ++p)
+      if (p != d->rank && (rc = dpx_wait_flag(d, d->xs, 1, chunk, p, seq))) return rc;
   d->pending.clear();
   DPX_CUDA(cudaEventRecord(d->ev_done, d->xs));
   DPX_CUDA(cudaStreamWaitEvent((cudaStream_t)main_stream, d->ev_done, 0));
+  return B2_OK;
+}
+
+// Raw async copy between two device pointers of this process (local or IPC-mapped): tools/dp_copy_probe.py times the
+// copy engines with it.
+extern "C" int b2_dpx_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  B2_REQUIRE(dst && src && bytes > 0, "b2_dpx_memcpy_async: bad args");
+  DPX_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
   return B2_OK;
 }

@@ -150,12 +150,16 @@ def staging_slot_elems(total: int, world: int, max_ranges: int = 4096) -> int:
 # ---------------------------------------------------------------------------------------------------------------------
 # transport
 # ---------------------------------------------------------------------------------------------------------------------
+MODES = ("ce_pull", "ce_push", "sm")
+
+
 class PeerGradExchange:
-    """Sum of the flat bf16 gradient buffer over the ranks of `group`, chunk by chunk, on copy engines (csrc/dpx.cu)."""
+    """Sum of the flat bf16 gradient buffer over the ranks of `group`, chunk by chunk, over peer memory (csrc/dpx.cu).
+    `mode`: "ce_pull" | "ce_push" | "sm" | "auto" (time the three on a 256 MB piece at start-up, all ranks agree on the
+    winner; a copy-engine transport is preferred when it is within 1.25x of the kernel one because it uses no SM)."""
 
-    WHOLE = None  # chunk id used by exchange_all(), set from b2_dpx_max_chunks()
-
-    def __init__(self, grad: torch.Tensor, group=None, n_copy_streams: int = 0, self_test: bool = True):
+    def __init__(self, grad: torch.Tensor, group=None, n_copy_streams: int = 0, self_test: bool = True,
+                 mode: Optional[str] = None, autotune: bool = True):
         from . import _lib
         dist = torch.distributed
         if not (dist.is_available() and dist.is_initialized()):
@@ -170,68 +174,89 @@ class PeerGradExchange:
             raise RuntimeError("PeerGradExchange: the gradient buffer must be a contiguous CUDA bf16 tensor")
         if grad.numel() % ALIGN:
             raise RuntimeError("PeerGradExchange: the gradient buffer length must be a multiple of 8 elements")
+        mode = (mode or os.environ.get("B2_DPX_MODE", "auto")).lower()
+        if mode not in MODES + ("auto",):
+            raise RuntimeError(f"PeerGradExchange: unknown mode {mode!r}")
+        n_copy_streams = n_copy_streams or int(os.environ.get("B2_DPX_COPY_STREAMS", "0"))
         self.grad = grad
         self.total = grad.numel()
         self.max_chunks = int(self.lib.b2_dpx_max_chunks())
-        self.WHOLE = self.max_chunks - 1
+        self.WHOLE = self.max_chunks - 1   # chunk id of exchange_all()
+        self.PROBE = self.max_chunks - 2   # chunk id of the start-up timing
         self.plan: Optional[ChunkPlan] = None
         self._chunk_args: Dict[int, tuple] = {}
         self._seg_dev: Dict[int, torch.Tensor] = {}
         self.seq = 1
         self.issued = False
-        self.handle = C.c_void_p()
+        self.handles: Dict[str, C.c_void_p] = {}
+        self.timings: Dict[str, float] = {}
         with torch.cuda.device(grad.device):
-            # --- IPC handles of my buffers
-            gh = (C.c_ubyte * 64)()
-            goff = C.c_int64()
-            _lib.check(self.lib.b2_dpx_ipc_export(C.c_void_p(grad.data_ptr()), gh, C.byref(goff)), "dpx_ipc_export(grad)")
+            self.slot = staging_slot_elems(self.total, self.world)
+            self.staging = torch.empty((self.world - 1) * self.slot, device=grad.device, dtype=torch.bfloat16)
             flags = C.c_void_p()
             _lib.check(self.lib.b2_dpx_alloc_flags(C.byref(flags)), "dpx_alloc_flags")
-            fh = (C.c_ubyte * 64)()
-            foff = C.c_int64()
-            _lib.check(self.lib.b2_dpx_ipc_export(flags, fh, C.byref(foff)), "dpx_ipc_export(flags)")
-            mine = (bytes(gh), int(goff.value), bytes(fh), int(foff.value), int(grad.device.index), self.total)
+
+            def export(ptr):
+                h = (C.c_ubyte * 64)()
+                off = C.c_int64()
+                _lib.check(self.lib.b2_dpx_ipc_export(C.c_void_p(ptr), h, C.byref(off)), "dpx_ipc_export")
+                return bytes(h), int(off.value)
+
+            mine = (export(grad.data_ptr()), export(flags.value), export(self.staging.data_ptr()), self.total)
             everyone: List = [None] * self.world
             dist.all_gather_object(everyone, mine, group=group)
+
+            def imp(hb, off):
+                ptr = C.c_void_p()
+                _lib.check(self.lib.b2_dpx_ipc_import((C.c_ubyte * 64).from_buffer_copy(hb), off, C.byref(ptr)),
+                           "dpx_ipc_import")
+                return ptr.value
+
             gp = (C.c_void_p * self.world)()
             fp = (C.c_void_p * self.world)()
-            for p, (pgh, pgoff, pfh, pfoff, _pdev, ptotal) in enumerate(everyone):
+            sp = (C.c_void_p * self.world)()
+            for p, (g_h, f_h, s_h, ptotal) in enumerate(everyone):
                 if ptotal != self.total:
                     raise RuntimeError("PeerGradExchange: ranks disagree on the gradient buffer size")
                 if p == self.rank:
-                    gp[p], fp[p] = grad.data_ptr(), flags.value
+                    gp[p], fp[p], sp[p] = grad.data_ptr(), flags.value, self.staging.data_ptr()
+                else:
+                    gp[p], fp[p], sp[p] = imp(*g_h), imp(*f_h), imp(*s_h)
+            for m in (MODES if mode == "auto" else (mode,)):
+                if m == "sm" and self.world > 8:
                     continue
-                ptr = C.c_void_p()
-                _lib.check(self.lib.b2_dpx_ipc_import((C.c_ubyte * 64).from_buffer_copy(pgh), pgoff, C.byref(ptr)),
-                           "dpx_ipc_import(grad)")
-                gp[p] = ptr.value
-                ptr2 = C.c_void_p()
-                _lib.check(self.lib.b2_dpx_ipc_import((C.c_ubyte * 64).from_buffer_copy(pfh), pfoff, C.byref(ptr2)),
-                           "dpx_ipc_import(flags)")
-                fp[p] = ptr2.value
-            self.slot = staging_slot_elems(self.total, self.world)
-            self.staging = torch.empty((self.world - 1) * self.slot, device=grad.device, dtype=torch.bfloat16)
-            _lib.check(self.lib.b2_dpx_create(self.rank, self.world, gp, fp, C.c_void_p(self.staging.data_ptr()),
-                                              self.slot, int(n_copy_streams), C.byref(self.handle)), "dpx_create")
-        self._set_chunk(self.WHOLE, [(0, self.total)])
+                h = C.c_void_p()
+                _lib.check(self.lib.b2_dpx_create(self.rank, self.world, MODES.index(m), gp, fp, sp, self.slot,
+                                                  int(n_copy_streams), C.byref(h)), f"dpx_create({m})")
+                self.handles[m] = h
+        self.mode = next(iter(self.handles))
+        self._set_chunk(self.WHOLE, [(0, self.total)], 0)
         if self_test:
             self.self_test()
+        if autotune and len(self.handles) > 1:
+            self.autotune()
+
+    @property
+    def handle(self):
+        return self.handles[self.mode]
 
     # ---- plan ----
-    def _set_chunk(self, k: int, ranges):
-        offs, lens, soffs, used = shard_plan(ranges, self.world, self.rank)
-        assert used <= self.slot, "staging slot too small for this chunk"
-        n = len(offs)
+    def _set_chunk(self, k: int, ranges, staging_base: int = 0):
+        _, _, _, used = shard_plan(ranges, self.world, self.rank)
+        assert staging_base % ALIGN == 0 and staging_base + used <= self.slot, "staging slot too small for this chunk"
+        n = len(ranges)
         arr = lambda v: (C.c_int64 * max(n, 1))(*v)  # noqa: E731
-        self._chunk_args[k] = (n, arr(offs), arr(lens), arr(soffs))
+        self._chunk_args[k] = (n, arr([o for o, _ in ranges]), arr([ln for _, ln in ranges]), int(staging_base))
+        return staging_base + used
 
     def set_plan(self, plan: ChunkPlan):
-        if plan.n_chunks > self.max_chunks - 1:
-            raise RuntimeError(f"PeerGradExchange: {plan.n_chunks} chunks > {self.max_chunks - 1}")
+        if plan.n_chunks > self.max_chunks - 2:
+            raise RuntimeError(f"PeerGradExchange: {plan.n_chunks} chunks > {self.max_chunks - 2}")
         self.plan = plan
         self._seg_dev = {}
+        base = 0  # every chunk gets its own region of the staging slots (the push transport relies on it)
         for k, rg in enumerate(plan.ranges):
-            self._set_chunk(k, rg)
+            base = self._set_chunk(k, rg, base)
             if plan.small_segs[k]:
                 self._seg_dev[k] = torch.tensor(plan.small_segs[k], dtype=torch.int64, device=self.grad.device)
 
@@ -250,9 +275,9 @@ class PeerGradExchange:
 
     def exchange_chunk(self, k: int):
         from . import _lib
-        n, offs, lens, soffs = self._chunk_args[k]
-        _lib.check(self.lib.b2_dpx_exchange(self.handle, int(k), C.c_uint32(self.seq & 0xFFFFFFFF), n, offs, lens, soffs,
-                                            self._stream()), "dpx_exchange")
+        n, offs, lens, base = self._chunk_args[k]
+        _lib.check(self.lib.b2_dpx_exchange(self.handle, int(k), C.c_uint32(self.seq & 0xFFFFFFFF), n, offs, lens, base,
+                                            self._stream()), f"dpx_exchange({self.mode})")
         self.issued = True
 
     def exchange_all(self):
@@ -267,43 +292,88 @@ class PeerGradExchange:
         self.seq += 1
         self.issued = False
 
-    def self_test(self, timeout_s: float = 60.0):
-        """Known-answer exchange of the (zero) gradient buffer: rank r fills element i with (r + 1) * (i % 5 + 1), small
-        integers that sum exactly in bf16.  A stuck flag would block the stream for ever, so completion is polled and the
-        process exits instead of hanging the job."""
-        g = self.grad
-        idx = torch.arange(self.total, device=g.device, dtype=torch.int32) % 5 + 1
-        g.copy_((idx * (self.rank + 1)).to(torch.bfloat16))
-        torch.cuda.synchronize(g.device)
-        torch.distributed.barrier(group=self.group)
-        self.exchange_all()
-        self.finish()
+    def _wait_or_die(self, what: str, timeout_s: float = 60.0):
+        """A stuck flag would block the stream for ever: poll for completion and exit instead of hanging the job."""
         ev = torch.cuda.Event()
         ev.record()
         t0 = time.time()
         while not ev.query():
             if time.time() - t0 > timeout_s:
-                print(f"[dpx] rank {self.rank}: self-test exchange did not complete in {timeout_s:.0f} s — aborting",
-                      flush=True)
+                print(f"[dpx] rank {self.rank}: {what} did not complete in {timeout_s:.0f} s — aborting", flush=True)
                 os._exit(17)
             time.sleep(0.002)
+
+    def self_test(self):
+        """Known-answer exchange of the (zero) gradient buffer with every transport: rank r fills element i with
+        (r + 1) * (i % 5 + 1), small integers whose sums are exact in bf16."""
+        g = self.grad
+        idx = torch.arange(self.total, device=g.device, dtype=torch.int32) % 5 + 1
         want = (idx * (self.world * (self.world + 1) // 2)).to(torch.bfloat16)
-        bad = int((g != want).sum())
-        g.zero_()
-        torch.cuda.synchronize(g.device)
-        torch.distributed.barrier(group=self.group)
-        if bad:
-            raise RuntimeError(f"PeerGradExchange self-test: {bad} of {self.total} elements differ from the known sums")
+        keep = self.mode
+        for m in self.handles:
+            self.mode = m
+            g.copy_((idx * (self.rank + 1)).to(torch.bfloat16))
+            torch.cuda.synchronize(g.device)
+            torch.distributed.barrier(group=self.group)
+            self.exchange_all()
+            self.finish()
+            self._wait_or_die(f"self-test exchange ({m})")
+            bad = int((g != want).sum())
+            g.zero_()
+            torch.cuda.synchronize(g.device)
+            torch.distributed.barrier(group=self.group)
+            if bad:
+                self.mode = keep
+                raise RuntimeError(f"PeerGradExchange self-test ({m}): {bad} of {self.total} elements differ from the "
+                                   "known sums")
+        self.mode = keep
+
+    def autotune(self, probe_elems: int = 128 * 1024 * 1024, iters: int = 3):
+        """Time every transport on one piece of the (idle, zero) buffer; all ranks pick the same winner."""
+        dist = torch.distributed
+        n = min(self.total, probe_elems) // ALIGN * ALIGN
+        self._set_chunk(self.PROBE, [(0, n)], 0)
+        names = list(self.handles)
+        t = torch.zeros(len(names), device=self.grad.device)
+        for i, m in enumerate(names):
+            self.mode = m
+            for it in range(iters + 1):
+                if it == 1:
+                    torch.cuda.synchronize(self.grad.device)
+                    dist.barrier(group=self.group)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                self.exchange_chunk(self.PROBE)
+                self.finish()
+            e1.record()
+            self._wait_or_die(f"autotune ({m})")
+            t[i] = e0.elapsed_time(e1) / iters
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.timings = {m: float(t[i]) for i, m in enumerate(names)}
+        best = min(names, key=lambda m: self.timings[m])
+        ce = [m for m in names if m != "sm"]
+        if best == "sm" and ce:
+            alt = min(ce, key=lambda m: self.timings[m])
+            if self.timings[alt] <= 1.25 * self.timings["sm"]:
+                best = alt
+        self.mode = best
+        self.probe_gbs = {m: 2 * (self.world - 1) / self.world * n * 2 / (ms * 1e-3) / 1e9 for m, ms in self.timings.items()}
+        if self.rank == 0:
+            print("[dpx] transports (ms for %.0f MB, NVLink ingress GB/s per GPU): %s -> %s" % (
+                n * 2 / 1e6, ", ".join(f"{m} {self.timings[m]:.2f} ms / {self.probe_gbs[m]:.0f}" for m in names), best),
+                flush=True)
+        self.grad.zero_()
+        torch.cuda.synchronize(self.grad.device)
 
     def close(self):
-        if self.handle:
-            self.lib.b2_dpx_destroy(self.handle)
-            self.handle = C.c_void_p()
+        for h in self.handles.values():
+            self.lib.b2_dpx_destroy(h)
+        self.handles = {}
 
 
 def try_create_exchange(grad: torch.Tensor, group=None) -> Optional[PeerGradExchange]:
     """Collective: every rank either gets an exchange object or None (then the caller uses one NCCL all-reduce).
-    `B2_DP_EXCHANGE=nccl` forces the NCCL path."""
+    `B2_DP_EXCHANGE=nccl` forces the NCCL path; `B2_DPX_MODE` picks the transport (default auto)."""
     dist = torch.distributed
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
         return None
@@ -311,7 +381,7 @@ def try_create_exchange(grad: torch.Tensor, group=None) -> Optional[PeerGradExch
         return None
     x, err = None, ""
     try:
-        x = PeerGradExchange(grad, group=group, self_test=False)
+        x = PeerGradExchange(grad, group=group, self_test=False, autotune=False)
     except Exception as e:  # noqa: BLE001
         err = f"{type(e).__name__}: {e}"
     ok = torch.tensor([1 if x is not None else 0], device=grad.device, dtype=torch.int32)
@@ -329,4 +399,6 @@ def try_create_exchange(grad: torch.Tensor, group=None) -> Optional[PeerGradExch
             print(f"[dpx] peer-memory gradient exchange unavailable ({err or 'another rank failed'}); using NCCL all-reduce",
                   flush=True)
         return None
+    if len(x.handles) > 1:
+        x.autotune()
     return x

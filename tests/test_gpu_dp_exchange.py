@@ -40,18 +40,20 @@ def _transport_worker(rank, world, port, q):
         total = 8 * 300_000 + 8 * 13
         g = torch.Generator(device="cuda").manual_seed(100 + rank)
         grad = torch.zeros(total, device="cuda", dtype=torch.bfloat16)
-        x = D.PeerGradExchange(grad, self_test=True)
+        x = D.PeerGradExchange(grad, self_test=True, mode="auto", autotune=False)  # all three transports
         # three chunks, one of them in two pieces, one tiny, plus a region nobody exchanges
         chunks = [[(0, 8 * 100_000)], [(8 * 100_000, 8 * 7), (8 * 150_000, 8 * 100_000)], [(8 * 250_000, 8 * 40_000)]]
+        base = 0
         for k, rg in enumerate(chunks):
-            x._set_chunk(k, rg)
+            base = x._set_chunk(k, rg, base)
         inside = torch.zeros(total, dtype=torch.bool, device="cuda")
         for rg in chunks:
             for o, n in rg:
                 inside[o:o + n] = True
         ok = True
         msgs = []
-        for it in range(4):
+        for it in range(6):
+            x.mode = list(x.handles)[it % len(x.handles)]
             mine = (torch.randn(total, device="cuda", generator=g) * (1 + rank)).to(torch.bfloat16)
             grad.copy_(mine)
             everyone = [torch.empty_like(mine) for _ in range(world)]
@@ -67,22 +69,25 @@ def _transport_worker(rank, world, port, q):
             bad_out = int((grad[~inside] != mine[~inside]).sum())
             if bad_in or bad_out:
                 ok = False
-                msgs.append(f"iter {it}: {bad_in} wrong sums, {bad_out} elements outside the chunks changed")
+                msgs.append(f"iter {it} ({x.mode}): {bad_in} wrong sums, {bad_out} elements outside the chunks changed")
             dist.barrier()
-        # whole buffer
-        mine = torch.randn(total, device="cuda", generator=g).to(torch.bfloat16)
-        grad.copy_(mine)
-        ref = mine.clone()
-        dist.all_reduce(ref)
-        torch.cuda.synchronize()
-        dist.barrier()
-        x.exchange_all()
-        x.finish()
-        torch.cuda.synchronize()
-        if world == 2 and not torch.equal(grad, ref):
-            ok = False
-            msgs.append("exchange_all differs from the NCCL all-reduce at world size 2")
-        dist.barrier()
+        # whole buffer, every transport
+        for m in x.handles:
+            x.mode = m
+            mine = torch.randn(total, device="cuda", generator=g).to(torch.bfloat16)
+            grad.copy_(mine)
+            ref = mine.clone()
+            dist.all_reduce(ref)
+            torch.cuda.synchronize()
+            dist.barrier()
+            x.exchange_all()
+            x.finish()
+            torch.cuda.synchronize()
+            if world == 2 and not torch.equal(grad, ref):
+                ok = False
+                msgs.append(f"exchange_all ({m}) differs from the NCCL all-reduce at world size 2")
+            dist.barrier()
+        x.autotune()
         x.close()
         q.put((rank, ok, msgs))
     finally:

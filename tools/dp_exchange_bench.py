@@ -19,11 +19,12 @@ def main():
     from sdxl_training_improvements_b200 import dp as D
     total = int(os.environ.get("DPX_ELEMS", 2_567_464_000)) // 8 * 8
     grad = torch.zeros(total, device="cuda", dtype=torch.bfloat16)
-    x = D.PeerGradExchange(grad, self_test=True)
+    x = D.PeerGradExchange(grad, self_test=True, mode="auto")
     nchunk = 10
     step = total // nchunk // 8 * 8
+    base = 0
     for k in range(nchunk):
-        x._set_chunk(k, [(k * step, step if k < nchunk - 1 else total - k * step)])
+        base = x._set_chunk(k, [(k * step, step if k < nchunk - 1 else total - k * step)], base)
 
     def timed(fn, iters=5):
         for _ in range(2):
@@ -52,12 +53,20 @@ def main():
     def nccl():
         dist.all_reduce(grad)
 
-    res = {"whole": timed(whole), "chunks10": timed(chunks), "nccl": timed(nccl)}
+    res = {}
+    chosen = x.mode
+    for m in x.handles:
+        x.mode = m
+        res[f"{m}/whole"] = timed(whole)
+        res[f"{m}/chunks10"] = timed(chunks)
+    x.mode = chosen
+    res["nccl"] = timed(nccl)
     if rank == 0:
         gb = total * 2 / 1e9
         for k, ms in res.items():
-            print(f"{k:9s} {ms:8.2f} ms  alg {gb / ms * 1e3:7.1f} GB/s  ingress/GPU {2 * (world - 1) / world * gb / ms * 1e3:7.1f} GB/s"
+            print(f"{k:17s} {ms:8.2f} ms  alg {gb / ms * 1e3:7.1f} GB/s  ingress/GPU {2 * (world - 1) / world * gb / ms * 1e3:7.1f} GB/s"
                   f"  (N={world}, {gb:.2f} GB)", flush=True)
+        print("autotune picked", chosen, x.timings, flush=True)
     x.close()
     dist.destroy_process_group()
 
