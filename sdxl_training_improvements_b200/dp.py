@@ -86,7 +86,7 @@ def last_touch_positions(store, log: Sequence[Tuple[int, str, int, int]]) -> Dic
     return last
 
 
-def plan_chunks(store, log, n_tape: int, target_chunks: int = 10, min_elems: int = 0) -> ChunkPlan:
+def plan_chunks(store, log, n_tape: int, target_chunks: int = 10, min_elems: int = 0, tail_div: int = 128) -> ChunkPlan:
     """Greedy cuts: walk the tape in replay order, cut whenever at least total/target_chunks elements have become final
     since the previous cut; whatever is left (always including everything written by the last tape entries) is the tail
     chunk, final at the end of the backward pass."""
@@ -109,6 +109,17 @@ def plan_chunks(store, log, n_tape: int, target_chunks: int = 10, min_elems: int
             acc = 0
     if not cuts or cuts[-1] != n_tape - 1:
         cuts.append(n_tape - 1)
+    # the tail chunk is the only one whose exchange cannot hide behind compute: keep it small (<= total / tail_div) with
+    # one extra cut as late as possible
+    tail_max = max(total // max(tail_div, 1), 1)
+    suffix, late = 0, None
+    for pos in sorted(by_pos, reverse=True):
+        if suffix + by_pos[pos] > tail_max:
+            late = pos
+            break
+        suffix += by_pos[pos]
+    if late is not None and 0 <= late < n_tape - 1 and late not in cuts and (len(cuts) < 2 or late > cuts[-2]):
+        cuts.insert(len(cuts) - 1, late)
     # a parameter goes to the first chunk whose cut is at or after its last write
     chunk_of = {}
     for _, _, name in lay:

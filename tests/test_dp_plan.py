@@ -105,7 +105,7 @@ def test_plan_chunks_invariants(cfg, target):
     plan = dp.plan_chunks(store, log, n_tape, target_chunks=target)
     last = dp.last_touch_positions(store, log)
     assert plan.cuts == sorted(set(plan.cuts)) and plan.cuts[-1] == n_tape - 1
-    assert 1 <= plan.n_chunks <= target + 1
+    assert 1 <= plan.n_chunks <= target + 2  # greedy cuts + the tail + one late cut that keeps the tail small
     # every parameter in exactly one chunk, final before its cut
     for name in store.offsets:
         k = plan.param_chunk[name]
