@@ -154,6 +154,107 @@ def _time_gemm_roofline(ops, peaks):
                       f"{flops / 1e9:.1f} GFLOP/launch, {ms * 1e3:.1f} us/launch, peak = {peaks['src']} burst bf16"}
 
 
+def _graph_time_us(fn, iters=10):
+    """Average device time of `fn` (a few kernel launches) inside a CUDA-graph replay of `iters` repetitions."""
+    fn()
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / iters
+
+
+def _extra_rooflines(ops, peaks):
+    """BASELINE.json asks for the attention / conv fraction of roofline next to images/s: the other hot kernels timed
+    live (CUDA-graph replay, CUDA events) at their SDXL shapes (B=4, 1024^2).  Peak = measured burst bf16 / measured
+    copy bandwidth (MEASURED_PEAKS.json).  FLOPs are algorithmic: attention core 4 n_q n_k 64 per head
+    forward, 10 n_q n_k 64 backward; conv 2 M Cout 9 Cin; the cross-attention "fused block" is LN -> Wq -> softmax(QK^T)V over
+    77 keys -> Wo + bias + residual = 28.46 GFLOP per layer call at C=1280 (the north-star figure; four launches today)."""
+    bf = torch.bfloat16
+    out = {}
+    try:
+        for tag, (B, H, n) in (("self_attn_n4096", (4, 10, 4096)), ("self_attn_n1024", (4, 20, 1024))):
+            Cc = H * 64
+            qkv = torch.randn(B * n, 3 * Cc, device="cuda").to(bf)
+            q, k, v = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
+            do = torch.randn(B * n, Cc, device="cuda").to(bf)
+            dqkv = torch.empty_like(qkv)
+            o, lse = ops.attn_fwd(q, k, v, B, H, n, n, 0.125)
+            tf = _graph_time_us(lambda: ops.attn_fwd(q, k, v, B, H, n, n, 0.125, out=o))
+            tb = _graph_time_us(lambda: ops.attn_bwd(q, k, v, o, lse, do, dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:],
+                                                     B, H, n, n, 0.125))
+            ff = 4.0 * n * n * 64 * B * H
+            out[tag] = {"fwd_us": round(tf, 1), "fwd_tflops": round(ff / tf / 1e6, 1),
+                        "fwd_frac_of_peak": round(ff / tf / 1e6 / peaks["burst"], 3),
+                        "bwd_us": round(tb, 1), "bwd_tflops": round(2.5 * ff / tb / 1e6, 1),
+                        "bwd_frac_of_peak": round(2.5 * ff / tb / 1e6 / peaks["burst"], 3), "bound": "SFU (exp2) / MMA issue, d=64"}
+        # cross-attention, C=1280, n=1024, 77 keys: the core alone (HBM-bound) and the fused-block definition
+        B, H, n, nk = 4, 20, 1024, 77
+        Cc = H * 64
+        x = torch.randn(B * n, Cc, device="cuda").to(bf)
+        gamma, beta = torch.ones(Cc, device="cuda", dtype=bf), torch.zeros(Cc, device="cuda", dtype=bf)
+        Wq = (torch.randn(Cc, Cc, device="cuda") * 0.02).to(bf)
+        Wo = (torch.randn(Cc, Cc, device="cuda") * 0.02).to(bf)
+        bo = torch.zeros(Cc, device="cuda", dtype=bf)
+        kv = torch.randn(B * nk, 2 * Cc, device="cuda").to(bf)
+        kk, vv = kv[:, :Cc], kv[:, Cc:]
+        qb = torch.empty_like(x)
+        ob = torch.empty_like(x)
+        yb = torch.empty_like(x)
+        tcore = _graph_time_us(lambda: ops.attn_fwd(qb, kk, vv, B, H, n, nk, 0.125, out=ob))
+
+        def block():
+            xn, _, _ = ops.ln_fwd(x, gamma, beta, 1e-5)
+            ops.linear_fwd(xn, Wq, out=qb)
+            ops.attn_fwd(qb, kk, vv, B, H, n, nk, 0.125, out=ob)
+            ops.linear_fwd(ob, Wo, bias=bo, residual=x, out=yb)
+
+        tblock = _graph_time_us(block)
+        core_flops = 4.0 * n * nk * 64 * B * H
+        core_bytes = 2 * x.numel() * 2 + kv.numel() * 2
+        block_flops = 2 * (2.0 * B * n * Cc * Cc) + core_flops
+        out["cross_attn_c1280"] = {
+            "core_us": round(tcore, 1), "core_gbs": round(core_bytes / tcore / 1e3, 0),
+            "core_frac_of_hbm_peak": round(core_bytes / tcore / 1e3 / peaks["hbm"], 3),
+            "core_tflops": round(core_flops / tcore / 1e6, 1),
+            "fused_block_us": round(tblock, 1), "fused_block_gflop": round(block_flops / 1e9, 2),
+            "fused_block_tflops": round(block_flops / tblock / 1e6, 1),
+            "fused_block_frac_of_peak": round(block_flops / tblock / 1e6 / peaks["burst"], 3),
+            "north_star_target_frac": 0.6, "launches_per_block": 4}
+        # implicit-GEMM 3x3 conv 640 -> 640 @ 64^2, B=4
+        B, Hh, Ww, Ci, Co = 4, 64, 64, 640, 640
+        M = B * Hh * Ww
+        xc = torch.randn(M, Ci, device="cuda").to(bf)
+        wk = (torch.randn(Co, 9 * Ci, device="cuda") / (9 * Ci) ** 0.5).to(bf)
+        dy = torch.randn(M, Co, device="cuda").to(bf)
+        dx = torch.empty_like(xc)
+        dw = torch.zeros_like(wk)
+        yc = torch.empty(M, Co, device="cuda", dtype=bf)
+        bias = torch.zeros(Co, device="cuda", dtype=bf)
+        cf = 2.0 * M * Co * 9 * Ci
+        t1 = _graph_time_us(lambda: ops.conv3x3_fwd(xc, wk, B, Hh, Ww, Ci, Co, bias=bias, out=yc))
+        t2 = _graph_time_us(lambda: ops.conv3x3_dgrad(dy, wk, dx, B, Hh, Ww, Ci, Co))
+        t3 = _graph_time_us(lambda: ops.conv3x3_wgrad(dy, xc, dw, B, Hh, Ww, Ci, Co))
+        out["conv3x3_640_64x64"] = {k: v for k, v in (
+            ("gflop", round(cf / 1e9, 1)),
+            ("fwd_us", round(t1, 1)), ("fwd_frac_of_peak", round(cf / t1 / 1e6 / peaks["burst"], 3)),
+            ("dgrad_us", round(t2, 1)), ("dgrad_frac_of_peak", round(cf / t2 / 1e6 / peaks["burst"], 3)),
+            ("wgrad_us", round(t3, 1)), ("wgrad_frac_of_peak", round(cf / t3 / 1e6 / peaks["burst"], 3)))}
+    except Exception as e:  # noqa: BLE001  (diagnostic extras must never lose the main measurement)
+        out["error"] = f"{type(e).__name__}: {str(e)[:160]}"
+    return out
+
+
 def _cpu_baseline(seconds_budget=30.0, threads=None):
     """The oracle (PyTorch-eager bf16 on the host CPU = the reference's own CPU path) on a bounded sample."""
     from oracle.unet_sdxl import OracleUNet
@@ -402,6 +503,7 @@ def run_ours(args):
         roof = _time_gemm_roofline(ops, peaks)
         roof["step_tflops_per_gpu"] = round(step_flops / (ms_dev * 1e-3) / 1e12, 1)
         roof["step_frac_of_sustained_peak"] = round(step_flops / (ms_dev * 1e-3) / 1e12 / peaks["sustained"], 4)
+        extra = _extra_rooflines(ops, peaks) if world == 1 else None
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             _, cb, _ = _cpu_baseline(seconds_budget=25.0)
@@ -414,17 +516,20 @@ def run_ours(args):
                           "cuda_graph": use_graph,
                           "global_batch": B * world * A, "parallelism": f"dp{world}",
                           "grad_exchange": ("none (1 GPU)" if world == 1 else
-                                            "peer-memory copy-engine reduce-scatter/all-gather overlapped with backward "
-                                            f"({core.dp.plan.n_chunks} chunks)" if core.dp is not None and core.dp.plan
+                                            f"peer-memory exchange ({core.dp.mode}: reduce-scatter + all-gather over IPC-mapped "
+                                            f"buffers) overlapped with backward, {core.dp.plan.n_chunks} chunks"
+                                            if core.dp is not None and core.dp.plan
                                             else "one NCCL all-reduce of the flat gradient buffer after backward"),
                           "l2": "working set >> L2: 5.1 GB of weights + ~40 GB activations streamed every step",
-                          "last_loss": last_loss},
+                          "last_loss": last_loss,
+                          "last_loss_note": "random-init weights under the zero-terminal-SNR schedule (sigma up to 2e4): the "
+                                            "reference clamps the loss at 1000 (ddpm_trainer.py:380-384)"},
                "e2e": {"value": round(e2e_v, 4), "unit": "images/s", "h2d_bytes_per_step": int(h2d) * A,
                        "d2h_bytes_per_step": (4 + 6 * 8) * A, "ms_per_step": round(ms_e2e, 2),
                        "api": "B200DDPMTrainer._execute_training_step(batch) with pinned host tensors"
                               + (" (cuda_graph=True)" if use_graph else "")},
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
-               "torch_eager_gpu": eager}
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_extra": extra,
+               "cpu_baseline": cb, "torch_eager_gpu": eager}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
