@@ -4,6 +4,8 @@
 // fixed 16-byte channel vector (t % nvec) and walks rows (t / nvec), (t / nvec) + rpi, ... so every row is read
 // as one fully coalesced burst and per-channel partial sums live in registers.  Partials are combined through
 // shared memory, per-group totals go out as one double atomicAdd per (CTA, group).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -35,7 +37,25 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, int HW, int C, int G
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   const bf16* xb = x + (size_t)b * HW * C + v * 8;
-  for (int r = r0 + slot; r < r1; r += rpi) {
+  int r = r0 + slot;
+  // four rows per trip with all four 16-byte loads issued before the first use: the plain loop keeps ONE load in flight
+  // per thread (SASS: each LDG feeds the next instruction), which leaves these HBM-bound kernels latency-bound
+  for (; r + 3 * rpi < r1; r += 4 * rpi) {
+    bf16x8 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) t[u] = ld8(xb + (size_t)(r + u * rpi) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(t[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        ss[j] += f[j] * f[j];
+      }
+    }
+  }
+  for (; r < r1; r += rpi) {
     float f[8];
     unpack8(ld8(xb + (size_t)r * C), f);
 #pragma unroll
@@ -92,7 +112,24 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y
     bb[j] = __bfloat162float(beta[c]) - m * a[j];
   }
   const size_t base = (size_t)b * HW * C + v * 8;
-  for (int r = r0 + slot; r < r1; r += rpi) {
+  int r = r0 + slot;
+  for (; r + 3 * rpi < r1; r += 4 * rpi) {  // four loads in flight per thread (see gn_stats_kernel)
+    bf16x8 t4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) t4[u] = ld8(x + base + (size_t)(r + u * rpi) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(t4[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = f[j] * a[j] + bb[j];
+        f[j] = silu ? silu_f(t) : t;
+      }
+      st8(y + base + (size_t)(r + u * rpi) * C, pack8(f));
+    }
+  }
+  for (; r < r1; r += rpi) {
     float f[8];
     unpack8(ld8(x + base + (size_t)r * C), f);
 #pragma unroll
@@ -128,7 +165,30 @@ __global__ void gn_bwd_reduce_kernel(const bf16* __restrict__ x, const bf16* __r
     dg[j] = db[j] = 0.f;
   }
   const size_t base = (size_t)b * HW * C + v * 8;
-  for (int r = r0 + slot; r < r1; r += rpi) {
+  int r = r0 + slot;
+  for (; r + rpi < r1; r += 2 * rpi) {  // two rows = four loads in flight per thread (see gn_stats_kernel)
+    bf16x8 tx[2], td[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      tx[u] = ld8(x + base + (size_t)(r + u * rpi) * C);
+      td[u] = ld8(dy + base + (size_t)(r + u * rpi) * C);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float f[8], d[8];
+      unpack8(tx[u], f);
+      unpack8(td[u], d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (f[j] - mu[j]) * rs[j];
+        float g = d[j];
+        if (silu) g *= dsilu_f(xh * ga[j] + be[j]);
+        dg[j] += g * xh;
+        db[j] += g;
+      }
+    }
+  }
+  for (; r < r1; r += rpi) {
     float f[8], d[8];
     unpack8(ld8(x + base + (size_t)r * C), f);
     unpack8(ld8(dy + base + (size_t)r * C), d);
@@ -195,7 +255,33 @@ __global__ void gn_bwd_dx_kernel(const bf16* __restrict__ x, const bf16* __restr
     m2[j] = (float)(ws[((size_t)b * G + g) * 2 + 1]) * invn;
   }
   const size_t base = (size_t)b * HW * C + v * 8;
-  for (int r = r0 + slot; r < r1; r += rpi) {
+  int r = r0 + slot;
+  for (; r + rpi < r1; r += 2 * rpi) {  // two rows = four to six loads in flight per thread (see gn_stats_kernel)
+    bf16x8 tx[2], td[2], to[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      tx[u] = ld8(x + base + (size_t)(r + u * rpi) * C);
+      td[u] = ld8(dy + base + (size_t)(r + u * rpi) * C);
+      if (accumulate) to[u] = ld8(dx + base + (size_t)(r + u * rpi) * C);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float f[8], d[8], o[8];
+      unpack8(tx[u], f);
+      unpack8(td[u], d);
+      if (accumulate) unpack8(to[u], o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (f[j] - mu[j]) * rs[j];
+        float g = d[j];
+        if (silu) g *= dsilu_f(xh * ga[j] + be[j]);
+        const float r_ = rs[j] * (g * ga[j] - m1[j] - xh * m2[j]);
+        f[j] = accumulate ? o[j] + r_ : r_;
+      }
+      st8(dx + base + (size_t)(r + u * rpi) * C, pack8(f));
+    }
+  }
+  for (; r < r1; r += rpi) {
     float f[8], d[8], o[8];
     unpack8(ld8(x + base + (size_t)r * C), f);
     unpack8(ld8(dy + base + (size_t)r * C), d);
@@ -406,6 +492,84 @@ ln_bwd_dx_reg_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf
   }
 }
 
+// LayerNorm backward in ONE pass over x / dy: dx (register-resident rows as above) and the column sums dgamma / dbeta,
+// which the two-kernel version re-read x and dy for.  A warp walks rows_per_cta / 8 rows and keeps its share of the column
+// sums in registers (2 x NV x 8 floats); the 8 warps of a CTA combine through shared-memory atomics and the CTA adds 2C
+// values to the fp32 staging buffer.  One CTA per SM-slot (grid sized to a single wave).
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_bwd_fused_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                    const bf16* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    float* __restrict__ dgb, int M, int C, int accumulate, int rows_per_cta) {
+  __shared__ float sred[2 * NV * 256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sred[i] = 0.f;
+  __syncthreads();
+  float ag[NV][8], ab[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+  const int r_end = min(M, (blockIdx.x + 1) * rows_per_cta);
+  for (int row = blockIdx.x * rows_per_cta + warp; row < r_end; row += 8) {
+    const bf16* xr = x + (size_t)row * C;
+    const bf16* dr = dy + (size_t)row * C;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NV][8], dg[NV][8];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float d[8], g[8];
+        unpack8(ld8(xr + v * 8), xh[i]);
+        unpack8(ld8(dr + v * 8), d);
+        unpack8(ld8(gamma + v * 8), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xh[i][j] - mu) * rs;
+          ag[i][j] += d[j] * xh[i][j];
+          ab[i][j] += d[j];
+          dg[i][j] = d[j] * g[j];
+          c1 += dg[i][j];
+          c2 += dg[i][j] * xh[i][j];
+        }
+      }
+    }
+    c1 = warp_sum(c1) / (float)C;
+    c2 = warp_sum(c2) / (float)C;
+    bf16* oxr = dx + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float o[8];
+        if (accumulate) unpack8(ld8(oxr + v * 8), o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float r_ = rs * (dg[i][j] - c1 - xh[i][j] * c2);
+          o[j] = accumulate ? o[j] + r_ : r_;
+        }
+        st8(oxr + v * 8, pack8(o));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sred[v * 8 + j], ag[i][j]);
+        atomicAdd(&sred[C + v * 8 + j], ab[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&dgb[i], sred[i]);
+}
+
 // dgamma[c] += sum_m dy*xhat, dbeta[c] += sum_m dy.  CTA = 64 columns x a chunk of rows; 8 column-vectors x 32 rows.
 __global__ void ln_bwd_dgb_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ mean,
                                   const float* __restrict__ rstd, float* dgb, int M, int C, int rows_per_cta) {
@@ -526,6 +690,25 @@ extern "C" int b2_ln_bwd(const void* x, const void* dy, void* dx, const void* ga
   B2_REQUIRE(C % 8 == 0, "b2_ln_bwd: C %% 8 != 0");
   cudaStream_t st = (cudaStream_t)stream;
   const int nv = (C / 8 + 31) / 32;
+  // Opt-in (B2_LN_BWD_FUSED=1): one fused pass, one wave of CTAs.  Measured SLOWER inside the training step than the two
+  // kernels below (130.9 vs 126.5 ms per step, profiles/r1_bench_n1_v8_notes.txt): at C = 1280 the column sums cost 80
+  // more registers per thread, occupancy drops to 8 warps per SM and the row loop becomes latency-bound.
+  static const bool fused = getenv("B2_LN_BWD_FUSED") != nullptr;
+  if (nv <= 5 && fused) {
+    const int per_sm = nv <= 3 ? 2 : 1;
+    const int slots = num_sms() * per_sm;
+    int rows_per_cta = ((M + slots - 1) / slots + 7) / 8 * 8;
+    if (rows_per_cta < 8) rows_per_cta = 8;
+    const int ctas = (M + rows_per_cta - 1) / rows_per_cta;
+#define B2_LN_BWD_F(NV)                                                                                          \
+  ln_bwd_fused_kernel<NV><<<ctas, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, (const bf16*)gamma, mean, \
+                                                rstd, dgb, M, C, accumulate_dx, rows_per_cta)
+    if (nv <= 2) B2_LN_BWD_F(2);
+    else if (nv <= 3) B2_LN_BWD_F(3);
+    else B2_LN_BWD_F(5);
+#undef B2_LN_BWD_F
+    return check_launch("ln_bwd_fused");
+  }
 #define B2_LN_BWD(NV)                                                                                                 \
   ln_bwd_dx_reg_kernel<NV><<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, (const bf16*)gamma, \
                                                         mean, rstd, M, C, accumulate_dx)

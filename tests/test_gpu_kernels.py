@@ -277,7 +277,7 @@ def test_groupnorm(ops, B, HW, Cc, silu):
     _close(dgb[Cc:], br.grad, rtol=1e-2, atol=5e-2, what="gn dbeta")
 
 
-@pytest.mark.parametrize("M,Cc", [(512, 640), (300, 1280), (64, 128)])
+@pytest.mark.parametrize("M,Cc", [(512, 640), (300, 1280), (64, 128), (4096, 1280), (16384, 640), (1003, 320)])
 def test_layernorm(ops, M, Cc):
     x = _rand(M, Cc, seed=19) * 1.5 + 0.2
     gamma = (1 + 0.1 * torch.randn(Cc, device="cuda")).to(bf16)
@@ -295,6 +295,13 @@ def test_layernorm(ops, M, Cc):
     _close(dx, xr.grad, atol=2e-2, what="ln dx")
     _close(dgb[:Cc], gr.grad, rtol=1e-2, atol=5e-2, what="ln dgamma")
     _close(dgb[Cc:], br.grad, rtol=1e-2, atol=5e-2, what="ln dbeta")
+    # accumulate: dx += and the fp32 staging of dgamma / dbeta += (what gradient accumulation and fan-out rely on)
+    dx0 = _rand(M, Cc, seed=23)
+    dx2 = dx0.clone()
+    dgb2 = dgb.clone()
+    ops.ln_bwd(x, dy, gamma, mean, rstd, dgb2, dx=dx2, accumulate=True)
+    _close(dx2, dx0.float() + xr.grad, atol=3e-2, what="ln dx accumulate")
+    _close(dgb2, 2 * dgb, rtol=1e-3, atol=1e-2 * max(1.0, float(dgb.abs().max())) * 1e-1, what="ln dgb accumulate")
 
 
 @pytest.mark.parametrize("rows,n", [(64, 77), (40, 1024), (8, 4096)])
