@@ -693,7 +693,7 @@ extern "C" int b2_ln_bwd(const void* x, const void* dy, void* dx, const void* ga
   // Opt-in (B2_LN_BWD_FUSED=1): one fused pass, one wave of CTAs.  Measured SLOWER inside the training step than the two
   // kernels below (130.9 vs 126.5 ms per step, profiles/r1_bench_n1_v8_notes.txt): at C = 1280 the column sums cost 80
   // more registers per thread, occupancy drops to 8 warps per SM and the row loop becomes latency-bound.
-  static const bool fused = getenv("B2_LN_BWD_FUSED") != nullptr;
+  const bool fused = getenv("B2_LN_BWD_FUSED") != nullptr;
   if (nv <= 5 && fused) {
     const int per_sm = nv <= 3 ? 2 : 1;
     const int slots = num_sms() * per_sm;

@@ -277,8 +277,14 @@ def test_groupnorm(ops, B, HW, Cc, silu):
     _close(dgb[Cc:], br.grad, rtol=1e-2, atol=5e-2, what="gn dbeta")
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("M,Cc", [(512, 640), (300, 1280), (64, 128), (4096, 1280), (16384, 640), (1003, 320)])
-def test_layernorm(ops, M, Cc):
+def test_layernorm(ops, M, Cc, fused, monkeypatch):
+    # fused: the opt-in one-pass backward (dx + dgamma / dbeta), selected per call through the environment
+    if fused:
+        monkeypatch.setenv("B2_LN_BWD_FUSED", "1")
+    else:
+        monkeypatch.delenv("B2_LN_BWD_FUSED", raising=False)
     x = _rand(M, Cc, seed=19) * 1.5 + 0.2
     gamma = (1 + 0.1 * torch.randn(Cc, device="cuda")).to(bf16)
     beta = (0.1 * torch.randn(Cc, device="cuda")).to(bf16)
