@@ -414,6 +414,9 @@ def run_ours(args):
         opt = B200AdamW(unet, lr=4e-7, weight_decay=1e-2, master_weights=True)
     use_graph = not args.no_graph
     trainer = create_trainer(cfg, unet, opt, device=f"cuda:{local}", seed=1000 + rank, cuda_graph=use_graph)
+    if args.no_grad_exchange and world > 1:
+        trainer.core.dp = None
+        trainer.world_size = 1
     batch = _synthetic_batch(B, H, W, seed=77 + rank)
     h2d = sum(v.numel() * v.element_size() for k, v in batch.items() if torch.is_tensor(v))
 
@@ -515,7 +518,7 @@ def run_ours(args):
                                       f"bf16, full fwd+bwd+loss+clip+{args.optimizer} (configs[1])",
                           "cuda_graph": use_graph,
                           "global_batch": B * world * A, "parallelism": f"dp{world}",
-                          "grad_exchange": ("none (1 GPU)" if world == 1 else
+                          "grad_exchange": ("none (1 GPU)" if world == 1 else "DISABLED (diagnostic)" if args.no_grad_exchange else
                                             f"peer-memory exchange ({core.dp.mode}: reduce-scatter + all-gather over IPC-mapped "
                                             f"buffers) overlapped with backward, {core.dp.plan.n_chunks} chunks"
                                             if core.dp is not None and core.dp.plan
@@ -529,6 +532,8 @@ def run_ours(args):
                        "api": "B200DDPMTrainer._execute_training_step(batch) with pinned host tensors"
                               + (" (cuda_graph=True)" if use_graph else "")},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_extra": extra,
+               **({"invalid": "diagnostic run without gradient exchange (independent replicas)"}
+                  if args.no_grad_exchange and world > 1 else {}),
                "cpu_baseline": cb, "torch_eager_gpu": eager}
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -549,6 +554,9 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU oracle timing")
     ap.add_argument("--optimizer", default="adamw_bf16", choices=["adamw_bf16", "adamw_fp32"])
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of CUDA graphs")
+    ap.add_argument("--no-grad-exchange", action="store_true",
+                    help="DIAGNOSTIC (N>1): skip the gradient exchange altogether — independent replicas, the max-over-ranks "
+                         "time then shows what the slowest GPU of the box costs; the JSON line is marked invalid")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
