@@ -68,6 +68,15 @@ __global__ void dpx_signal_kernel(PeerFlags flags, int world, int self, int word
   }
 }
 
+// Streaming (evict-first) accesses: the exchange moves gigabytes that are touched once, while the GEMMs running beside it
+// live off their operand tiles staying in the 126 MB L2.
+__device__ __forceinline__ bf16x8 ld8_stream(const bf16* p) {
+  bf16x8 r;
+  r.u = __ldcs(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+__device__ __forceinline__ void st8_stream(bf16* p, const bf16x8& v) { __stcs(reinterpret_cast<uint4*>(p), v.u); }
+
 // grad[i] = bf16( fp32(grad[i]) + sum_s fp32(staging[s * slot_stride + i]) ), 8 elements per 16-byte access, four
 // vectors per thread.  No shared memory and few registers, so its CTAs co-reside with the persistent GEMM / attention
 // CTAs instead of waiting for an SM; many short CTAs rather than a persistent grid for the same reason.
@@ -80,7 +89,7 @@ __global__ void __launch_bounds__(128) dpx_reduce_kernel(bf16* __restrict__ grad
   for (int u = 0; u < 4; ++u) {
     const long long v = base + (long long)u * blockDim.x;
     live[u] = v < nvec;
-    if (live[u]) unpack8(ld8(grad + v * 8), acc[u]);
+    if (live[u]) unpack8(ld8_stream(grad + v * 8), acc[u]);
   }
   for (int s = 0; s < nslots; ++s) {
     const bf16* src = staging + (long long)s * slot_stride;
@@ -88,7 +97,7 @@ __global__ void __launch_bounds__(128) dpx_reduce_kernel(bf16* __restrict__ grad
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long v = base + (long long)u * blockDim.x;
-      if (live[u]) t[u] = ld8(src + v * 8);
+      if (live[u]) t[u] = ld8_stream(src + v * 8);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -103,7 +112,7 @@ __global__ void __launch_bounds__(128) dpx_reduce_kernel(bf16* __restrict__ grad
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const long long v = base + (long long)u * blockDim.x;
-    if (live[u]) st8(grad + v * 8, pack8(acc[u]));
+    if (live[u]) st8_stream(grad + v * 8, pack8(acc[u]));
   }
 }
 
@@ -124,7 +133,7 @@ __global__ void __launch_bounds__(128) dpx_fused_kernel(PeerBufs bufs, long long
     live[u] = v < nvec;
     if (live[u]) {
 #pragma unroll
-      for (int q = 0; q < W; ++q) t[u][q] = ld8(bufs.p[q] + off + v * 8);
+      for (int q = 0; q < W; ++q) t[u][q] = ld8_stream(bufs.p[q] + off + v * 8);
     }
   }
 #pragma unroll
@@ -142,7 +151,7 @@ __global__ void __launch_bounds__(128) dpx_fused_kernel(PeerBufs bufs, long long
     }
     const bf16x8 r = pack8(acc);
 #pragma unroll
-    for (int q = 0; q < W; ++q) st8(bufs.p[q] + off + v * 8, r);
+    for (int q = 0; q < W; ++q) st8_stream(bufs.p[q] + off + v * 8, r);
   }
 }
 
