@@ -359,6 +359,13 @@ def run_reference(args):
     if rank != 0:
         return
     from sdxl_training_improvements_b200.flops import train_step_flops
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is entitled to all host cores it can use
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    if torch.get_num_threads() < ncores:
+        torch.set_num_threads(ncores)
     total_steps = args.steps + args.warmup
     per_step = max(3.0, 150.0 / max(1, total_steps))
     m, cb, one = _cpu_baseline(seconds_budget=per_step)
