@@ -86,6 +86,9 @@ __device__ __forceinline__ void store_row32(bf16* dst, const float* f) {
 constexpr int F3_STAGES = 5;
 constexpr int F3_SMEM = AT_TILE128 + F3_STAGES * 2 * AT_TILE128 + 1024;
 
+// POLY (opt-in, B2_ATTN_POLY_EXP2=1): every fourth exponential of the softmax is evaluated as a polynomial on the FMA pipe
+// (poly_exp2, tc.cuh) instead of ex2.approx — the phase counters put the exp2 phase of this kernel at the MUFU rate.
+template <bool POLY>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnP p) {
@@ -282,7 +285,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const float p0 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i]), p.c, -m_used));
           const float p1 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 1]), p.c, -m_used));
           const float p2 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 2]), p.c, -m_used));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 3]), p.c, -m_used));
+          const float x3 = fmaf(__uint_as_float(r[cc * 32 + 2 * i + 3]), p.c, -m_used);
+          const float p3 = POLY ? poly_exp2(x3) : fast_exp2(x3);
           l0 += p0; l1 += p1; l2 += p2; l3 += p3;
           pk[i] = pack_bf16x2(p0, p1);
           pk[i + 1] = pack_bf16x2(p2, p3);
@@ -1024,10 +1028,15 @@ extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
   if ((rc = make_map_bf16_4d(&tv, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 128, "attn V"))) return rc;
   static bool configured = false;
   if (!configured) {
-    if ((rc = set_smem(attn_fwd3_kernel, F3_SMEM, "b2_attn_fwd"))) return rc;
+    if ((rc = set_smem(attn_fwd3_kernel<false>, F3_SMEM, "b2_attn_fwd"))) return rc;
+    if ((rc = set_smem(attn_fwd3_kernel<true>, F3_SMEM, "b2_attn_fwd"))) return rc;
     configured = true;
   }
-  (void)launch_pdl(attn_fwd3_kernel, dim3((a->n_q + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)F3_SMEM, st, tq, tk, tv, p);
+  const dim3 grid3((a->n_q + 127) / 128, a->H, a->B);
+  if (getenv("B2_ATTN_POLY_EXP2"))  // opt-in until measured on the GPU (read per call so that tests can switch it)
+    (void)launch_pdl(attn_fwd3_kernel<true>, grid3, dim3(A3_THREADS), (size_t)F3_SMEM, st, tq, tk, tv, p);
+  else
+    (void)launch_pdl(attn_fwd3_kernel<false>, grid3, dim3(A3_THREADS), (size_t)F3_SMEM, st, tq, tk, tv, p);
   return check_launch("b2_attn_fwd");
 }
 

@@ -305,6 +305,19 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / integer pipes, no MUFU: x clamped to >= -126, split x = n + f (round to nearest through the 1.5 * 2^23
+// trick), degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below bf16's 2^-9 — the result
+// feeds a bf16 P), n added to the exponent as an integer.  Nine instructions against one ex2.approx: worth it only for a
+// fraction of the softmax elements, where ex2 (16 per clock per SM) is what bounds the d=64 forward kernel.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  const float xr = x + 12582912.f;
+  const float f = x - (xr - 12582912.f);
+  float p = fmaf(0.05517132f, f, 0.24261054f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992812f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
