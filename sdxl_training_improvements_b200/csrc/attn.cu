@@ -345,6 +345,252 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward v4 (EXPERIMENTAL, opt-in with B2_ATTN_FWD4=1 until it has been measured): the v3 kernel with SIXTEEN softmax warps.
+//   Why: the ncu capture of v3 has nothing saturated — issue slots 28 %, MUFU 35 %, tensor pipe 22 % of the elapsed cycles,
+//   10 warps resident (profiles/r1_attention_notes.md): each of the eight softmax warps walks a 128-element row per key
+//   block through one dependent chain (tcgen05.ld -> max -> FFMA -> ex2 -> pack -> tcgen05.st -> arrive) and two warps per
+//   scheduler cannot hide it.  A TMEM lane quadrant can only be read by warps with the matching (warp % 4), so more warps
+//   means splitting the COLUMNS: warps w and w + 4 of a group own the same 32 rows and one half (64 keys) of the block
+//   each — 64 registers of S per thread instead of 128, so the register file takes 18 warps.  The two halves agree on the
+//   running row maximum through shared memory (one named barrier per block, which also orders "both halves have read S"
+//   before "either half overwrites it with P"), keep separate partial row sums, and each rescales / finally reads its half
+//   of the O accumulator.  Producer and MMA warps are those of v3; bar_p counts 256 arrivals.
+// warps (576 threads): 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = group 0 (halves 0,1), 10..17 = group 1.
+// ---------------------------------------------------------------------------------------------
+constexpr int A4_THREADS = 576;
+
+__device__ __forceinline__ void a4_group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory"); }
+__device__ __forceinline__ void a4_all_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__global__ void __launch_bounds__(A4_THREADS, 1)
+attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnP p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q, bar_full[F3_STAGES], bar_empty[F3_STAGES], bar_s[3], bar_p[3], bar_pv[2], bar_o;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float xmax[2][2][2][128];  // [parity of the group's block count][group][half][row]: block-local row maxima
+  __shared__ float m_fin[2][128];       // [group][row] final running maximum
+  __shared__ float l_fin[2][2][128];    // [group][half][row] partial row sums
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sKV = smem_base + AT_TILE128;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nkb = (p.n_k + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(smem_u32(&bar_q), 1);
+#pragma unroll
+    for (int s = 0; s < F3_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(smem_u32(&bar_s[i]), 1);
+      mbar_init(smem_u32(&bar_p[i]), 256);
+    }
+    mbar_init(smem_u32(&bar_pv[0]), 1);
+    mbar_init(smem_u32(&bar_pv[1]), 1);
+    mbar_init(smem_u32(&bar_o), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u32(tmem_slot);
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    const bool el = elect_one();
+    if (el) {
+      mbar_expect_tx(smem_u32(&bar_q), AT_TILE128);
+      tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+      const uint32_t full = smem_u32(&bar_full[s]);
+      if (el) {
+        mbar_expect_tx(full, 2 * AT_TILE128);
+        tma_load_4d(sKV + s * 2 * AT_TILE128, &tmK, full, 0, j * 128, h, b);
+        tma_load_4d(sKV + s * 2 * AT_TILE128 + AT_TILE128, &tmV, full, 0, j * 128, h, b);
+      }
+      if (++s == F3_STAGES) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    const bool el = elect_one();
+    constexpr uint32_t idS = umma_idesc(128, 128, 0, 0);
+    constexpr uint32_t idO = umma_idesc(128, AT_D, 0, 1);
+    auto issue_S = [&](int buf, int stage) {
+      const uint32_t tS = tmem_base + buf * 128, sK = sKV + stage * 2 * AT_TILE128;
+#pragma unroll
+      for (int k = 0; k < AT_D / 16; ++k)
+        umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
+    };
+    mbar_wait(smem_u32(&bar_q), 0);
+    int ls = 0, issued = 0;
+    uint32_t lph = 0;
+    for (; issued < 3 && issued < nkb; ++issued) {
+      mbar_wait(smem_u32(&bar_full[ls]), lph);
+      tc_fence_after();
+      if (el) issue_S(issued, ls);
+      if (el) umma_commit(smem_u32(&bar_s[issued]));
+      if (++ls == F3_STAGES) { ls = 0; lph ^= 1u; }
+    }
+    int buf = 0, cs = 0;
+    uint32_t ppar = 0;
+    for (int j = 0; j < nkb; ++j) {
+      const int g = j & 1;
+      mbar_wait(smem_u32(&bar_p[buf]), ppar);
+      tc_fence_after();
+      const uint32_t tP = tmem_base + buf * 128, tO = tmem_base + 384 + g * 64;
+      const uint32_t sV = sKV + cs * 2 * AT_TILE128 + AT_TILE128;
+      if (el) {
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k)
+          umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (j >= 2) || k != 0);
+      }
+      if (el) umma_commit(smem_u32(&bar_pv[g]));
+      if (el) umma_commit(smem_u32(&bar_empty[cs]));
+      if (issued < nkb) {
+        mbar_wait(smem_u32(&bar_full[ls]), lph);
+        tc_fence_after();
+        if (el) issue_S(buf, ls);
+        if (el) umma_commit(smem_u32(&bar_s[buf]));
+        if (++ls == F3_STAGES) { ls = 0; lph ^= 1u; }
+        ++issued;
+      }
+      if (++cs == F3_STAGES) cs = 0;
+      if (++buf == 3) { buf = 0; ppar ^= 1u; }
+    }
+    if (el) umma_commit(smem_u32(&bar_o));
+  } else {
+    const int idx = warp - 2;
+    const int g = idx >> 3;          // group: alternate key blocks
+    const int hf = (idx >> 2) & 1;   // half of the block's 128 key columns
+    const int qd = warp & 3;         // TMEM lane quadrant this warp may touch
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = uint32_t(qd * 32) << 16;
+    const uint32_t tOh = tmem_base + 384 + g * 64 + hf * 32 + lane_off;  // my half of the group's O accumulator
+    float m_used = -INFINITY, l = 0.f;
+    int buf = g;
+    uint32_t spar = 0;
+    int kown = 0;
+    for (int j = g; j < nkb; j += 2, ++kown) {
+      mbar_wait(smem_u32(&bar_s[buf]), spar);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + buf * 128 + lane_off;
+      uint32_t r[64];
+      tmem_ld32_nowait(tS + hf * 64, r);
+      tmem_ld32_nowait(tS + hf * 64 + 32, r + 32);
+      tmem_ld_wait();
+      const int valid = min(128, p.n_k - j * 128) - hf * 64;  // valid key columns in my half (may be <= 0)
+      if (valid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) r[i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+      }
+      const float mxh = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.c;
+      xmax[kown & 1][g][hf][row] = mxh;
+      a4_group_sync(g);  // partner's maximum is visible; BOTH halves have read their S columns (P may now overwrite them)
+      const float mx = fmaxf(mxh, xmax[kown & 1][g][hf ^ 1][row]);
+      float factor = 1.f;
+      if (kown == 0) {
+        m_used = mx;
+      } else if (mx > m_used + 8.f) {  // lazy rescale, same decision in both halves (same mx, same m_used)
+        factor = fast_exp2(m_used - mx);
+        m_used = mx;
+      }
+      if (kown > 0 && __any_sync(AT_FULL, factor != 1.f)) {
+        mbar_wait(smem_u32(&bar_pv[g]), (uint32_t)(kown - 1) & 1u);
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld32(tOh, o);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+        tmem_st32(tOh, o);
+        l *= factor;
+      }
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i]), p.c, -m_used));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 1]), p.c, -m_used));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 2]), p.c, -m_used));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 3]), p.c, -m_used));
+          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+          pk[i] = pack_bf16x2(p0, p1);
+          pk[i + 1] = pack_bf16x2(p2, p3);
+        }
+        tmem_st16(tS + hf * 32 + cc * 16, pk);  // bf16 P of keys [64 hf + 32 cc, +32) -> P columns [32 hf + 16 cc, +16)
+      }
+      l += (l0 + l1) + (l2 + l3);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_p[buf]));
+      buf += 2;
+      if (buf >= 3) { buf -= 3; spar ^= 1u; }
+    }
+    // ---- merge: two groups (split-KV combine) x two halves (partial row sums); 16 output columns per (group, half)
+    if (hf == 0) m_fin[g][row] = m_used;
+    l_fin[g][hf][row] = l;
+    mbar_wait(smem_u32(&bar_o), 0);
+    tc_fence_after();
+    a4_all_sync();
+    const bool has1 = nkb > 1;
+    const float ma = m_fin[0][row], mb = m_fin[1][row];
+    const float la = l_fin[0][0][row] + l_fin[0][1][row], lb = l_fin[1][0][row] + l_fin[1][1][row];
+    const float m = has1 ? fmaxf(ma, mb) : ma;
+    const float w0 = fast_exp2(ma - m), w1 = has1 ? fast_exp2(mb - m) : 0.f;
+    const float lt = la * w0 + lb * w1;
+    const float inv = 1.f / lt;
+    const int c0 = (g * 2 + hf) * 16;
+    const uint32_t tO0 = tmem_base + 384 + c0 + lane_off, tO1 = tO0 + 64;
+    uint32_t a[16], c[16];
+    float f[16];
+    tmem_ld16_nowait(tO0, a);
+    if (has1) tmem_ld16_nowait(tO1, c);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      f[i] = (__uint_as_float(a[i]) * w0 + (has1 ? __uint_as_float(c[i]) * w1 : 0.f)) * inv;
+    const int gq = q0 + row;
+    if (gq < p.n_q) {
+      bf16* dst = p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + c0;
+      st8(dst, pack8(f));
+      st8(dst + 8, pack8(f + 8));
+    }
+    if (g == 0 && hf == 0 && gq < p.n_pad)
+      p.LSE[((long long)b * p.H + h) * p.n_pad + gq] = gq < p.n_q ? m + log2f(lt) : INFINITY;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, A3_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward, part 0: D[i] = sum_d dO[i,d] * O[i,d]   (8 lanes per (row, head))
 // ---------------------------------------------------------------------------------------------
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ D, int B,
@@ -1033,6 +1279,15 @@ extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
     configured = true;
   }
   const dim3 grid3((a->n_q + 127) / 128, a->H, a->B);
+  if (getenv("B2_ATTN_FWD4")) {  // experimental sixteen-softmax-warp kernel, opt-in until measured
+    static bool configured4 = false;
+    if (!configured4) {
+      if ((rc = set_smem(attn_fwd4_kernel, F3_SMEM, "b2_attn_fwd"))) return rc;
+      configured4 = true;
+    }
+    (void)launch_pdl(attn_fwd4_kernel, grid3, dim3(A4_THREADS), (size_t)F3_SMEM, st, tq, tk, tv, p);
+    return check_launch("b2_attn_fwd(v4)");
+  }
   if (getenv("B2_ATTN_POLY_EXP2"))  // opt-in until measured on the GPU (read per call so that tests can switch it)
     (void)launch_pdl(attn_fwd3_kernel<true>, grid3, dim3(A3_THREADS), (size_t)F3_SMEM, st, tq, tk, tv, p);
   else
