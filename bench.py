@@ -487,6 +487,8 @@ def run_ours(args):
     ms_dev = e0.elapsed_time(e1) / K
 
     # ---- (2) end-to-end through the plugin API with host buffers: `e2e` ----
+    for _ in range(2):  # untimed: bring the host-side path (pinned copies, RNG, graph launch) back into cache after loop (1)
+        api_step()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
