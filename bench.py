@@ -197,7 +197,7 @@ def _extra_rooflines(ops, peaks):
             out[tag] = {"fwd_us": round(tf, 1), "fwd_tflops": round(ff / tf / 1e6, 1),
                         "fwd_frac_of_peak": round(ff / tf / 1e6 / peaks["burst"], 3),
                         "bwd_us": round(tb, 1), "bwd_tflops": round(2.5 * ff / tb / 1e6, 1),
-                        "bwd_frac_of_peak": round(2.5 * ff / tb / 1e6 / peaks["burst"], 3), "bound": "softmax-warp instruction issue / single UMMA-issuing thread (ex2 throughput and warp count ruled out by experiment), d=64"}
+                        "bwd_frac_of_peak": round(2.5 * ff / tb / 1e6 / peaks["burst"], 3), "bound": "ex2 (XU pipe ~75 % busy inside the key-block loop) + per-CTA set-up / tear-down outside it (26-53 % of the kernel time), d=64"}
         # cross-attention, C=1280, n=1024, 77 keys: the core alone (HBM-bound) and the fused-block definition
         B, H, n, nk = 4, 20, 1024, 77
         Cc = H * 64
