@@ -591,6 +591,274 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward, PERSISTENT (EXPERIMENTAL, opt-in with B2_ATTN_PFWD=1 until it has been measured): the v3 pipeline with the
+// query tile as an outer loop inside the CTA, the way attn_xfwd_kernel already works for cross-attention.
+//   Why: inside the key-block loop v3 runs at 75 % of its ex2 bound, but 26 % (n = 4096) to 53 % (n = 1024, 60 of the 70
+//   self-attention layers) of the kernel time is per-CTA set-up and tear-down — TMEM allocation, barrier initialisation,
+//   descriptor prefetch, the first TMA round trip, the two-group merge, the O store, TMEM release, the next CTA's launch
+//   (profiles/r1_attention_notes.md).  Here one CTA per SM walks a contiguous range of (sample, head, query-tile) items:
+//   every barrier and ring keeps running across tiles (global block counter G: S ring slot G % 3, K/V stage G % 5), Q is
+//   double-buffered, and the MMA warp's S-issue cursor runs up to three blocks ahead ACROSS tile boundaries, so the next
+//   tile's loads, S MMAs and first softmax blocks overlap the current tile's merge and store.  O has no second buffer
+//   (TMEM is full: 3 x 128 + 2 x 64 columns), so the first PV of a tile waits until the previous tile's merge has read it.
+// warps (320 threads): 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = group 0, 6..9 = group 1 (as v3).
+// ---------------------------------------------------------------------------------------------
+constexpr int PF_SMEM = 2 * AT_TILE128 + F3_STAGES * 2 * AT_TILE128 + 1024;
+
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attn_pfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnP p, int nqt, int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q[2], bar_qfree[2], bar_full[F3_STAGES], bar_empty[F3_STAGES], bar_s[3], bar_p[3],
+      bar_pv[2], bar_o, bar_ofree;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float2 ml[2][2][128];  // [tile parity][group][row]
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ0 = smem_base;                     // two Q buffers
+  const uint32_t sKV = smem_base + 2 * AT_TILE128;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int t_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
+  const int t_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
+  const int ntiles = t_end - t_begin;
+  const int nkb = (p.n_k + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_q[i]), 1);
+      mbar_init(smem_u32(&bar_qfree[i]), 1);
+      mbar_init(smem_u32(&bar_pv[i]), 1);
+    }
+#pragma unroll
+    for (int s = 0; s < F3_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(smem_u32(&bar_s[i]), 1);
+      mbar_init(smem_u32(&bar_p[i]), 128);
+    }
+    mbar_init(smem_u32(&bar_o), 1);
+    mbar_init(smem_u32(&bar_ofree), 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u32(tmem_slot);
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ---------------- TMA producer: Q(t), then the K/V blocks of tile t, for every tile of this CTA
+    const bool el = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tl = 0; tl < ntiles; ++tl) {
+      const int gt = t_begin + tl;
+      const int qt = gt % nqt, bh = gt / nqt;
+      const int h = bh % p.H, b = bh / p.H;
+      const int qb = tl & 1;
+      if (tl >= 2) mbar_wait(smem_u32(&bar_qfree[qb]), (uint32_t)((tl >> 1) - 1) & 1u);  // S MMAs of tile tl-2 are done
+      if (el) {
+        mbar_expect_tx(smem_u32(&bar_q[qb]), AT_TILE128);
+        tma_load_4d(sQ0 + qb * AT_TILE128, &tmQ, smem_u32(&bar_q[qb]), 0, qt * 128, h, b);
+      }
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&bar_full[s]);
+        if (el) {
+          mbar_expect_tx(full, 2 * AT_TILE128);
+          tma_load_4d(sKV + s * 2 * AT_TILE128, &tmK, full, 0, j * 128, h, b);
+          tma_load_4d(sKV + s * 2 * AT_TILE128 + AT_TILE128, &tmV, full, 0, j * 128, h, b);
+        }
+        if (++s == F3_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: PV cursor (tile tl, block j, global block G) and an S cursor up to three blocks ahead
+    const bool el = elect_one();
+    constexpr uint32_t idS = umma_idesc(128, 128, 0, 0);
+    constexpr uint32_t idO = umma_idesc(128, AT_D, 0, 1);
+    int s_tl = 0, s_j = 0;   // S cursor: tile, block within the tile
+    int s_stage = 0;         // K/V stage of the S cursor's block (= global block index % F3_STAGES)
+    uint32_t s_sph = 0;      // parity of bar_full[s_stage] for that block
+    int s_buf = 0;           // S ring slot of the S cursor's block (= global block index % 3)
+    auto issue_next_S = [&]() {
+      if (s_tl >= ntiles) return;
+      const int qb = s_tl & 1;
+      if (s_j == 0) mbar_wait(smem_u32(&bar_q[qb]), (uint32_t)(s_tl >> 1) & 1u);
+      mbar_wait(smem_u32(&bar_full[s_stage]), s_sph);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + s_buf * 128, sQ = sQ0 + qb * AT_TILE128, sK = sKV + s_stage * 2 * AT_TILE128;
+      if (el) {
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
+        umma_commit(smem_u32(&bar_s[s_buf]));
+      }
+      if (++s_stage == F3_STAGES) { s_stage = 0; s_sph ^= 1u; }
+      if (++s_buf == 3) s_buf = 0;
+      if (++s_j == nkb) {
+        if (el) umma_commit(smem_u32(&bar_qfree[qb]));  // this tile's Q buffer may be reloaded once its S MMAs completed
+        s_j = 0;
+        ++s_tl;
+      }
+    };
+    issue_next_S();
+    issue_next_S();
+    issue_next_S();
+    int buf = 0, cs = 0;   // ring slot / K/V stage of the PV cursor's block
+    uint32_t ppar = 0;     // parity of bar_p[buf] for that block
+    for (int tl = 0; tl < ntiles; ++tl) {
+      for (int j = 0; j < nkb; ++j) {
+        const int g = j & 1;
+        mbar_wait(smem_u32(&bar_p[buf]), ppar);
+        if (j == 0 && tl > 0) mbar_wait(smem_u32(&bar_ofree), (uint32_t)(tl - 1) & 1u);  // previous tile's merge has read O
+        tc_fence_after();
+        const uint32_t tP = tmem_base + buf * 128, tO = tmem_base + 384 + g * 64;
+        const uint32_t sV = sKV + cs * 2 * AT_TILE128 + AT_TILE128;
+        if (el) {
+#pragma unroll
+          for (int k = 0; k < 128 / 16; ++k)
+            umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (j >= 2) || k != 0);
+          umma_commit(smem_u32(&bar_pv[g]));
+          umma_commit(smem_u32(&bar_empty[cs]));
+          if (j == nkb - 1) umma_commit(smem_u32(&bar_o));  // every PV of this tile has been issued
+        }
+        issue_next_S();  // refills ring slot `buf` (global block + 3), possibly with a block of the NEXT tile
+        if (++cs == F3_STAGES) cs = 0;
+        if (++buf == 3) { buf = 0; ppar ^= 1u; }
+      }
+    }
+  } else {
+    // ---------------- softmax groups
+    const int g = (warp - 2) >> 2;
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = uint32_t(qd * 32) << 16;
+    const uint32_t tOg = tmem_base + 384 + g * 64 + lane_off;
+    int gbase = 0;   // global index of the current tile's first block
+    int pvc = 0;     // own blocks finished so far (over all tiles) = PV commits this group has caused on bar_pv[g]
+    for (int tl = 0; tl < ntiles; ++tl, gbase += nkb) {
+      const int gt = t_begin + tl;
+      const int qt = gt % nqt, bh = gt / nqt;
+      const int h = bh % p.H, b = bh / p.H;
+      const int q0 = qt * 128;
+      float m_used = -INFINITY, l = 0.f;
+      int kown = 0;
+      for (int j = g; j < nkb; j += 2, ++kown, ++pvc) {
+        const int G = gbase + j;
+        const int buf = G % 3;
+        const uint32_t spar = (uint32_t)(G / 3) & 1u;
+        mbar_wait(smem_u32(&bar_s[buf]), spar);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + buf * 128 + lane_off;
+        const int valid = min(128, p.n_k - j * 128);
+        uint32_t r[128];
+        tmem_ld32_nowait(tS, r);
+        tmem_ld32_nowait(tS + 32, r + 32);
+        tmem_ld32_nowait(tS + 64, r + 64);
+        tmem_ld32_nowait(tS + 96, r + 96);
+        tmem_ld_wait();
+        if (valid < 128) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= valid) r[i] = 0xff800000u;
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.c;
+        float factor = 1.f;
+        if (kown == 0) {
+          m_used = mx;
+        } else if (mx > m_used + 8.f) {
+          factor = fast_exp2(m_used - mx);
+          m_used = mx;
+        }
+        if (kown > 0 && __any_sync(AT_FULL, factor != 1.f)) {
+          // the PV of this group's previous block (commit number pvc, 1-based, on bar_pv[g]) must have completed
+          mbar_wait(smem_u32(&bar_pv[g]), (uint32_t)(pvc - 1) & 1u);
+          tc_fence_after();
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t o[32];
+            tmem_ld32(tOg + cc * 32, o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st32(tOg + cc * 32, o);
+          }
+          l *= factor;
+        }
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i]), p.c, -m_used));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 1]), p.c, -m_used));
+            const float p2 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 2]), p.c, -m_used));
+            const float p3 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 3]), p.c, -m_used));
+            l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+            pk[i] = pack_bf16x2(p0, p1);
+            pk[i + 1] = pack_bf16x2(p2, p3);
+          }
+          tmem_st16(tS + cc * 16, pk);
+        }
+        l += (l0 + l1) + (l2 + l3);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bar_p[buf]));
+      }
+      // ---- merge the two groups' partial results of this tile, 32 output columns per group
+      ml[tl & 1][g][row] = make_float2(m_used, l);
+      mbar_wait(smem_u32(&bar_o), (uint32_t)tl & 1u);
+      tc_fence_after();
+      a3_group_sync();
+      const float2 s0 = ml[tl & 1][0][row], s1 = ml[tl & 1][1][row];
+      const bool has1 = nkb > 1;
+      const float m = has1 ? fmaxf(s0.x, s1.x) : s0.x;
+      const float w0 = fast_exp2(s0.x - m), w1 = has1 ? fast_exp2(s1.x - m) : 0.f;
+      const float lt = s0.y * w0 + s1.y * w1;
+      const float inv = 1.f / lt;
+      const uint32_t tO0 = tmem_base + 384 + g * 32 + lane_off, tO1 = tO0 + 64;
+      uint32_t a[32], c[32];
+      float f[32];
+      tmem_ld32_nowait(tO0, a);
+      if (has1) tmem_ld32_nowait(tO1, c);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_ofree));  // the MMA warp may start the next tile's PV into O_0 / O_1
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        f[i] = (__uint_as_float(a[i]) * w0 + (has1 ? __uint_as_float(c[i]) * w1 : 0.f)) * inv;
+      const int gq = q0 + row;
+      if (gq < p.n_q) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + g * 32, f);
+      if (g == 0 && gq < p.n_pad) p.LSE[((long long)b * p.H + h) * p.n_pad + gq] = gq < p.n_q ? m + log2f(lt) : INFINITY;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, A3_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward, part 0: D[i] = sum_d dO[i,d] * O[i,d]   (8 lanes per (row, head))
 // ---------------------------------------------------------------------------------------------
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ D, int B,
@@ -1279,6 +1547,19 @@ extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
     configured = true;
   }
   const dim3 grid3((a->n_q + 127) / 128, a->H, a->B);
+  if (getenv("B2_ATTN_PFWD")) {  // experimental persistent kernel (one CTA per SM over query tiles), opt-in until measured
+    static bool configured_p = false;
+    if (!configured_p) {
+      if ((rc = set_smem(attn_pfwd_kernel, PF_SMEM, "b2_attn_fwd"))) return rc;
+      configured_p = true;
+    }
+    const int nqt = (a->n_q + 127) / 128;
+    const long long total = (long long)nqt * a->H * a->B;
+    B2_REQUIRE(total < (1ll << 31), "b2_attn_fwd: too many tiles");
+    const int grid = (int)(total < num_sms() ? total : num_sms());
+    (void)launch_pdl(attn_pfwd_kernel, dim3(grid), dim3(A3_THREADS), (size_t)PF_SMEM, st, tq, tk, tv, p, nqt, (int)total);
+    return check_launch("b2_attn_fwd(persistent)");
+  }
   if (getenv("B2_ATTN_FWD4")) {  // experimental sixteen-softmax-warp kernel, opt-in until measured
     static bool configured4 = false;
     if (!configured4) {
