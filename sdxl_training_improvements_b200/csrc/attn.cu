@@ -1269,6 +1269,217 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// backward dQ, PERSISTENT (EXPERIMENTAL, opt-in with B2_ATTN_PBWD=1, never run on a GPU yet): attn_bwd_dq3_kernel with the
+// query tile as an outer loop inside the CTA — the same transformation, for the same reason, as attn_pfwd_kernel: per-CTA
+// set-up / tear-down is a large share of these kernels at n = 1024 (8-16 key blocks per CTA).  {Q, dO} double-buffered,
+// S / dP ring, K/V stages and all barriers keep running across tiles (global block counter), the S/dP issue cursor runs
+// up to three blocks ahead across tile boundaries; the single dQ accumulator is handed back by the softmax warps
+// (bar_ofree, 256 arrivals) before the next tile's first dQ MMA overwrites it.
+constexpr int PQ_SMEM = 4 * AT_TILE128 + Q3_STAGES * 2 * AT_TILE64 + 1024;
+
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attn_pbwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnP p, int nqt,
+                    int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q[2], bar_qfree[2], bar_full[Q3_STAGES], bar_empty[Q3_STAGES], bar_s[3], bar_p[3], bar_o,
+      bar_ofree;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQdO = smem_base;                    // buffer qb: Q at +qb*2*TILE128, dO right after it
+  const uint32_t sKV = smem_base + 4 * AT_TILE128;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int t_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
+  const int t_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
+  const int ntiles = t_end - t_begin;
+  const int nkb = (p.n_k + 63) / 64;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_q[i]), 1);
+      mbar_init(smem_u32(&bar_qfree[i]), 1);
+    }
+#pragma unroll
+    for (int s = 0; s < Q3_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(smem_u32(&bar_s[i]), 1);
+      mbar_init(smem_u32(&bar_p[i]), 128);
+    }
+    mbar_init(smem_u32(&bar_o), 1);
+    mbar_init(smem_u32(&bar_ofree), 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u32(tmem_slot);
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    const bool el = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tl = 0; tl < ntiles; ++tl) {
+      const int gt = t_begin + tl;
+      const int qt = gt % nqt, bh = gt / nqt;
+      const int h = bh % p.H, b = bh / p.H;
+      const int qb = tl & 1;
+      if (tl >= 2) mbar_wait(smem_u32(&bar_qfree[qb]), (uint32_t)((tl >> 1) - 1) & 1u);
+      if (el) {
+        const uint32_t dst = sQdO + qb * 2 * AT_TILE128;
+        mbar_expect_tx(smem_u32(&bar_q[qb]), 2 * AT_TILE128);
+        tma_load_4d(dst, &tmQ, smem_u32(&bar_q[qb]), 0, qt * 128, h, b);
+        tma_load_4d(dst + AT_TILE128, &tmdO, smem_u32(&bar_q[qb]), 0, qt * 128, h, b);
+      }
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&bar_full[s]);
+        if (el) {
+          mbar_expect_tx(full, 2 * AT_TILE64);
+          tma_load_4d(sKV + s * 2 * AT_TILE64, &tmK, full, 0, j * 64, h, b);
+          tma_load_4d(sKV + s * 2 * AT_TILE64 + AT_TILE64, &tmV, full, 0, j * 64, h, b);
+        }
+        if (++s == Q3_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const bool el = elect_one();
+    constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
+    constexpr uint32_t idQ = umma_idesc(128, AT_D, 0, 1);
+    int s_tl = 0, s_j = 0, s_stage = 0, s_buf = 0;
+    uint32_t s_sph = 0;
+    auto issue_next_SdP = [&]() {
+      if (s_tl >= ntiles) return;
+      const int qb = s_tl & 1;
+      if (s_j == 0) mbar_wait(smem_u32(&bar_q[qb]), (uint32_t)(s_tl >> 1) & 1u);
+      mbar_wait(smem_u32(&bar_full[s_stage]), s_sph);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + s_buf * 128, tdP = tS + 64;
+      const uint32_t sQ = sQdO + qb * 2 * AT_TILE128, sdO = sQ + AT_TILE128;
+      const uint32_t sK = sKV + s_stage * 2 * AT_TILE64, sV = sK + AT_TILE64;
+      if (el) {
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_bf16(tdP, umma_desc(sdO + k * 32, 16, 1024), umma_desc(sV + k * 32, 16, 1024), idS, k != 0);
+        umma_commit(smem_u32(&bar_s[s_buf]));
+      }
+      if (++s_stage == Q3_STAGES) { s_stage = 0; s_sph ^= 1u; }
+      if (++s_buf == 3) s_buf = 0;
+      if (++s_j == nkb) {
+        if (el) umma_commit(smem_u32(&bar_qfree[qb]));
+        s_j = 0;
+        ++s_tl;
+      }
+    };
+    issue_next_SdP();
+    issue_next_SdP();
+    issue_next_SdP();
+    int buf = 0, cs = 0;
+    uint32_t ppar = 0;
+    const uint32_t tdQ = tmem_base + 384;
+    for (int tl = 0; tl < ntiles; ++tl) {
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(smem_u32(&bar_p[buf]), ppar);
+        if (j == 0 && tl > 0) mbar_wait(smem_u32(&bar_ofree), (uint32_t)(tl - 1) & 1u);  // previous tile's dQ has been read
+        tc_fence_after();
+        const uint32_t tdS = tmem_base + buf * 128;
+        const uint32_t sK = sKV + cs * 2 * AT_TILE64;
+        if (el) {
+#pragma unroll
+          for (int k = 0; k < 64 / 16; ++k)
+            umma_bf16_ts(tdQ, tdS + k * 8, umma_desc(sK + k * 2048, 8192, 1024), idQ, (j | k) != 0);
+          umma_commit(smem_u32(&bar_empty[cs]));
+          if (j == nkb - 1) umma_commit(smem_u32(&bar_o));
+        }
+        issue_next_SdP();
+        if (++cs == Q3_STAGES) cs = 0;
+        if (++buf == 3) { buf = 0; ppar ^= 1u; }
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = uint32_t(qd * 32) << 16;
+    int gbase = 0;
+    for (int tl = 0; tl < ntiles; ++tl, gbase += nkb) {
+      const int gt = t_begin + tl;
+      const int qt = gt % nqt, bh = gt / nqt;
+      const int h = bh % p.H, b = bh / p.H;
+      const int gq = qt * 128 + row;
+      const long long sidx = ((long long)b * p.H + h) * p.n_pad + gq;
+      const float L2 = p.LSE[sidx];
+      const float Dr = p.D[sidx];
+      for (int j = g; j < nkb; j += 2) {
+        const int G = gbase + j;
+        const int buf = G % 3;
+        const uint32_t spar = (uint32_t)(G / 3) & 1u;
+        mbar_wait(smem_u32(&bar_s[buf]), spar);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + buf * 128 + lane_off, tdP = tS + 64;
+        const int valid = min(64, p.n_k - j * 64);
+        uint32_t rs[64], rd[64];
+        tmem_ld32_nowait(tS, rs);
+        tmem_ld32_nowait(tS + 32, rs + 32);
+        tmem_ld32_nowait(tdP, rd);
+        tmem_ld32_nowait(tdP + 32, rd + 32);
+        tmem_ld_wait();
+        if (valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= valid) rs[i] = 0xff800000u;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(rs[cc * 32 + 2 * i]), p.c, -L2));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(rs[cc * 32 + 2 * i + 1]), p.c, -L2));
+            pk[i] = pack_bf16x2(p0 * (__uint_as_float(rd[cc * 32 + 2 * i]) - Dr),
+                                p1 * (__uint_as_float(rd[cc * 32 + 2 * i + 1]) - Dr));
+          }
+          tmem_st16(tS + cc * 16, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bar_p[buf]));
+      }
+      mbar_wait(smem_u32(&bar_o), (uint32_t)tl & 1u);
+      tc_fence_after();
+      uint32_t a[32];
+      float f[32];
+      tmem_ld32(tmem_base + 384 + g * 32 + lane_off, a);
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_ofree));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(a[i]) * p.scale;
+      if (gq < p.n_q) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + g * 32, f);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, A3_TMEM_COLS);
+  }
+}
+
 // backward dK / dV: CTA = 128 keys x query blocks of 64.  TMEM: ring of three {S^T | dP^T} pairs [0,384) (bf16 P^T / dS^T
 // in place), dV [384,448), dK [448,512).  The S^T / dP^T MMAs that refill a ring slot are issued after the dV / dK MMAs
 // that read it as their A operand; tcgen05.mma instructions of one thread execute in issue order.
@@ -1479,6 +1690,229 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   }
 }
 
+// backward dK / dV, PERSISTENT (EXPERIMENTAL, opt-in with B2_ATTN_PBWD=1, never run on a GPU yet): attn_bwd_dkv3_kernel with
+// the KEY tile as an outer loop inside the CTA (see attn_pfwd_kernel for the reasoning).  {K, V} double-buffered, the
+// {Q, dO, LSE, D} stages, the S^T / dP^T ring and all barriers keep running across tiles (global query-block counter); the
+// dV / dK accumulators are handed back by the softmax warps (bar_ofree) before the next tile's first MMA overwrites them.
+constexpr int PK_SMEM = 4 * AT_TILE128 + Q3_STAGES * 2 * AT_TILE64 + 1024;
+
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attn_pbwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO, const AttnP p, int nkt,
+                     int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_kv[2], bar_kvfree[2], bar_full[Q3_STAGES], bar_empty[Q3_STAGES], bar_s[3], bar_p[3], bar_o,
+      bar_ofree;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float ld_s[Q3_STAGES][128];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sKVb = smem_base;                    // buffer kb: K at +kb*2*TILE128, V right after it
+  const uint32_t sQdO = smem_base + 4 * AT_TILE128;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int t_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
+  const int t_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
+  const int ntiles = t_end - t_begin;
+  const int nqb = (p.n_q + 63) / 64;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmdO);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_kv[i]), 1);
+      mbar_init(smem_u32(&bar_kvfree[i]), 1);
+    }
+#pragma unroll
+    for (int s = 0; s < Q3_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(smem_u32(&bar_s[i]), 1);
+      mbar_init(smem_u32(&bar_p[i]), 128);
+    }
+    mbar_init(smem_u32(&bar_o), 1);
+    mbar_init(smem_u32(&bar_ofree), 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u32(tmem_slot);
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    const bool el = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tl = 0; tl < ntiles; ++tl) {
+      const int gt = t_begin + tl;
+      const int kt = gt % nkt, bh = gt / nkt;
+      const int h = bh % p.H, b = bh / p.H;
+      const int kb = tl & 1;
+      // K / V of tile tl-2 are read by its S^T / dP^T MMAs only (dV / dK take Q / dO from the stages): free once those are done
+      if (tl >= 2) mbar_wait(smem_u32(&bar_kvfree[kb]), (uint32_t)((tl >> 1) - 1) & 1u);
+      if (el) {
+        const uint32_t dst = sKVb + kb * 2 * AT_TILE128;
+        mbar_expect_tx(smem_u32(&bar_kv[kb]), 2 * AT_TILE128);
+        tma_load_4d(dst, &tmK, smem_u32(&bar_kv[kb]), 0, kt * 128, h, b);
+        tma_load_4d(dst + AT_TILE128, &tmV, smem_u32(&bar_kv[kb]), 0, kt * 128, h, b);
+      }
+      for (int i = 0; i < nqb; ++i) {
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&bar_full[s]);
+        if (el) {
+          mbar_expect_tx(full, 2 * AT_TILE64 + 512);
+          tma_load_4d(sQdO + s * 2 * AT_TILE64, &tmQ, full, 0, i * 64, h, b);
+          tma_load_4d(sQdO + s * 2 * AT_TILE64 + AT_TILE64, &tmdO, full, 0, i * 64, h, b);
+          const long long off = ((long long)b * p.H + h) * p.n_pad + (long long)i * 64;
+          bulk_load_1d(smem_u32(&ld_s[s][0]), p.LSE + off, 256, full);
+          bulk_load_1d(smem_u32(&ld_s[s][64]), p.D + off, 256, full);
+        }
+        if (++s == Q3_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const bool el = elect_one();
+    constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
+    constexpr uint32_t idG = umma_idesc(128, AT_D, 0, 1);
+    int s_tl = 0, s_i = 0, s_stage = 0, s_buf = 0;
+    uint32_t s_sph = 0;
+    auto issue_next_SdP = [&]() {
+      if (s_tl >= ntiles) return;
+      const int kb = s_tl & 1;
+      if (s_i == 0) mbar_wait(smem_u32(&bar_kv[kb]), (uint32_t)(s_tl >> 1) & 1u);
+      mbar_wait(smem_u32(&bar_full[s_stage]), s_sph);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + s_buf * 128, tdP = tS + 64;
+      const uint32_t sK = sKVb + kb * 2 * AT_TILE128, sV = sK + AT_TILE128;
+      const uint32_t sQb = sQdO + s_stage * 2 * AT_TILE64, sdOb = sQb + AT_TILE64;
+      if (el) {
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_bf16(tS, umma_desc(sK + k * 32, 16, 1024), umma_desc(sQb + k * 32, 16, 1024), idS, k != 0);
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_bf16(tdP, umma_desc(sV + k * 32, 16, 1024), umma_desc(sdOb + k * 32, 16, 1024), idS, k != 0);
+        umma_commit(smem_u32(&bar_s[s_buf]));
+      }
+      if (++s_stage == Q3_STAGES) { s_stage = 0; s_sph ^= 1u; }
+      if (++s_buf == 3) s_buf = 0;
+      if (++s_i == nqb) {
+        if (el) umma_commit(smem_u32(&bar_kvfree[kb]));
+        s_i = 0;
+        ++s_tl;
+      }
+    };
+    issue_next_SdP();
+    issue_next_SdP();
+    issue_next_SdP();
+    int buf = 0, cs = 0;
+    uint32_t ppar = 0;
+    const uint32_t tdV = tmem_base + 384, tdK = tmem_base + 448;
+    for (int tl = 0; tl < ntiles; ++tl) {
+      for (int i = 0; i < nqb; ++i) {
+        mbar_wait(smem_u32(&bar_p[buf]), ppar);
+        if (i == 0 && tl > 0) mbar_wait(smem_u32(&bar_ofree), (uint32_t)(tl - 1) & 1u);  // previous tile's dV / dK were read
+        tc_fence_after();
+        const uint32_t tP = tmem_base + buf * 128, tdS = tP + 64;
+        const uint32_t sQb = sQdO + cs * 2 * AT_TILE64, sdOb = sQb + AT_TILE64;
+        if (el) {
+#pragma unroll
+          for (int k = 0; k < 64 / 16; ++k)
+            umma_bf16_ts(tdV, tP + k * 8, umma_desc(sdOb + k * 2048, 8192, 1024), idG, (i | k) != 0);
+#pragma unroll
+          for (int k = 0; k < 64 / 16; ++k)
+            umma_bf16_ts(tdK, tdS + k * 8, umma_desc(sQb + k * 2048, 8192, 1024), idG, (i | k) != 0);
+          umma_commit(smem_u32(&bar_empty[cs]));
+          if (i == nqb - 1) umma_commit(smem_u32(&bar_o));
+        }
+        issue_next_SdP();
+        if (++cs == Q3_STAGES) cs = 0;
+        if (++buf == 3) { buf = 0; ppar ^= 1u; }
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = uint32_t(qd * 32) << 16;
+    int gbase = 0;  // global index of the current tile's first query block
+    for (int tl = 0; tl < ntiles; ++tl, gbase += nqb) {
+      const int gt = t_begin + tl;
+      const int kt = gt % nkt, bh = gt / nkt;
+      const int h = bh % p.H, b = bh / p.H;
+      for (int i = g; i < nqb; i += 2) {
+        const int G = gbase + i;
+        const int buf = G % 3, stg = G % Q3_STAGES;
+        const uint32_t spar = (uint32_t)(G / 3) & 1u, fpar = (uint32_t)(G / Q3_STAGES) & 1u;
+        mbar_wait(smem_u32(&bar_s[buf]), spar);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + buf * 128 + lane_off, tdP = tS + 64;
+        uint32_t rs[64], rd[64];
+        tmem_ld32_nowait(tS, rs);
+        tmem_ld32_nowait(tS + 32, rs + 32);
+        tmem_ld32_nowait(tdP, rd);
+        tmem_ld32_nowait(tdP + 32, rd + 32);
+        mbar_wait(smem_u32(&bar_full[stg]), fpar);  // already complete: makes the bulk-copied LSE / D visible to this thread
+        const float4* L4 = reinterpret_cast<const float4*>(&ld_s[stg][0]);
+        const float4* D4 = reinterpret_cast<const float4*>(&ld_s[stg][64]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t pp[16], pd[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 lv = L4[cc * 8 + q], dv = D4[cc * 8 + q];
+            const int o = cc * 32 + 4 * q;
+            const float p0 = fast_exp2(fmaf(__uint_as_float(rs[o + 0]), p.c, -lv.x));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(rs[o + 1]), p.c, -lv.y));
+            const float p2 = fast_exp2(fmaf(__uint_as_float(rs[o + 2]), p.c, -lv.z));
+            const float p3 = fast_exp2(fmaf(__uint_as_float(rs[o + 3]), p.c, -lv.w));
+            pp[2 * q] = pack_bf16x2(p0, p1);
+            pp[2 * q + 1] = pack_bf16x2(p2, p3);
+            pd[2 * q] = pack_bf16x2(p0 * (__uint_as_float(rd[o + 0]) - dv.x), p1 * (__uint_as_float(rd[o + 1]) - dv.y));
+            pd[2 * q + 1] = pack_bf16x2(p2 * (__uint_as_float(rd[o + 2]) - dv.z), p3 * (__uint_as_float(rd[o + 3]) - dv.w));
+          }
+          tmem_st16(tS + cc * 16, pp);
+          tmem_st16(tdP + cc * 16, pd);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bar_p[buf]));
+      }
+      mbar_wait(smem_u32(&bar_o), (uint32_t)tl & 1u);
+      tc_fence_after();
+      const int gk = kt * 128 + row;
+      uint32_t a[32], c[32];
+      float f[32];
+      tmem_ld32_nowait(tmem_base + 384 + g * 32 + lane_off, a);  // dV
+      tmem_ld32_nowait(tmem_base + 448 + g * 32 + lane_off, c);  // dK
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_ofree));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(a[i]);
+      if (gk < p.n_k) store_row32(p.out1 + (long long)b * p.bs1 + (long long)gk * p.ld1 + h * AT_D + g * 32, f);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(c[i]) * p.scale;
+      if (gk < p.n_k) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gk * p.ld0 + h * AT_D + g * 32, f);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, A3_TMEM_COLS);
+  }
+}
+
 template <typename K>
 static int set_smem(K kernel, int bytes, const char* what) {
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -1610,12 +2044,41 @@ extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
   if ((rc = make_map_bf16_4d(&tdo64, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 64, "attn dO64"))) return rc;
   AttnP pq = p;
   pq.out0 = (bf16*)a->dQ; pq.ld0 = a->lddq; pq.bs0 = a->dq_bs;
-  (void)launch_pdl(attn_bwd_dq3_kernel, dim3((a->n_q + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)Q3_SMEM, st, tq128,
-                   tdo128, tk64, tv64, pq);
-  if ((rc = check_launch("b2_attn_bwd dq3"))) return rc;
+  if (getenv("B2_ATTN_PBWD")) {  // experimental persistent dQ kernel, opt-in until measured
+    static bool configured_pq = false;
+    if (!configured_pq) {
+      if ((rc = set_smem(attn_pbwd_dq_kernel, PQ_SMEM, "b2_attn_bwd"))) return rc;
+      configured_pq = true;
+    }
+    const int nqt = (a->n_q + 127) / 128;
+    const long long total = (long long)nqt * a->H * a->B;
+    B2_REQUIRE(total < (1ll << 31), "b2_attn_bwd: too many tiles");
+    const int grid = (int)(total < num_sms() ? total : num_sms());
+    (void)launch_pdl(attn_pbwd_dq_kernel, dim3(grid), dim3(A3_THREADS), (size_t)PQ_SMEM, st, tq128, tdo128, tk64, tv64, pq, nqt,
+                     (int)total);
+    if ((rc = check_launch("b2_attn_bwd dq(persistent)"))) return rc;
+  } else {
+    (void)launch_pdl(attn_bwd_dq3_kernel, dim3((a->n_q + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)Q3_SMEM, st, tq128,
+                     tdo128, tk64, tv64, pq);
+    if ((rc = check_launch("b2_attn_bwd dq3"))) return rc;
+  }
   AttnP pk = p;
   pk.out0 = (bf16*)a->dK; pk.ld0 = a->lddk; pk.bs0 = a->dk_bs;
   pk.out1 = (bf16*)a->dV; pk.ld1 = a->lddv; pk.bs1 = a->dv_bs;
+  if (getenv("B2_ATTN_PBWD")) {  // experimental persistent dK / dV kernel, opt-in until measured
+    static bool configured_pk = false;
+    if (!configured_pk) {
+      if ((rc = set_smem(attn_pbwd_dkv_kernel, PK_SMEM, "b2_attn_bwd"))) return rc;
+      configured_pk = true;
+    }
+    const int nkt = (a->n_k + 127) / 128;
+    const long long total = (long long)nkt * a->H * a->B;
+    B2_REQUIRE(total < (1ll << 31), "b2_attn_bwd: too many tiles");
+    const int grid = (int)(total < num_sms() ? total : num_sms());
+    (void)launch_pdl(attn_pbwd_dkv_kernel, dim3(grid), dim3(A3_THREADS), (size_t)PK_SMEM, st, tk128, tv128, tq64, tdo64, pk, nkt,
+                     (int)total);
+    return check_launch("b2_attn_bwd dkv(persistent)");
+  }
   (void)launch_pdl(attn_bwd_dkv3_kernel, dim3((a->n_k + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)Q3_SMEM, st, tk128,
                    tv128, tq64, tdo64, pk);
   return check_launch("b2_attn_bwd dkv3");

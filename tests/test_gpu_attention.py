@@ -45,22 +45,25 @@ def _select_variant(variant, monkeypatch, n_k=1024):
     FMA pipe (opt-in, csrc/tc.cuh poly_exp2; tests/test_poly_exp2.py pins its arithmetic on CPU).  fwd4: the experimental
     sixteen-softmax-warp kernel (measured once: parity green, 20 % slower).  pfwd: the experimental PERSISTENT forward kernel
     (one CTA per SM over query tiles) — written after round 1's GPU budget was spent, never run.  Both experimental kernels
-    only run when B2_TEST_EXPERIMENTAL=1 (a protocol bug in an unmeasured kernel would trap the whole GPU test run)."""
+    pbwd: the experimental persistent BACKWARD kernels (dQ over query tiles, dK/dV over key tiles), same status.  The
+    experimental kernels only run when B2_TEST_EXPERIMENTAL=1 (a protocol bug in an unmeasured kernel would trap the whole GPU
+    test run)."""
     import os
     monkeypatch.delenv("B2_ATTN_POLY_EXP2", raising=False)
     monkeypatch.delenv("B2_ATTN_FWD4", raising=False)
     monkeypatch.delenv("B2_ATTN_PFWD", raising=False)
-    if variant != "v3" and n_k <= 96:
+    monkeypatch.delenv("B2_ATTN_PBWD", raising=False)
+    if variant not in ("v3", "pbwd") and n_k <= 96:
         pytest.skip("the cross-attention kernel has no variants")
     if variant == "poly":
         monkeypatch.setenv("B2_ATTN_POLY_EXP2", "1")
-    elif variant in ("fwd4", "pfwd"):
+    elif variant in ("fwd4", "pfwd", "pbwd"):
         if not os.environ.get("B2_TEST_EXPERIMENTAL"):
             pytest.skip("experimental kernel: set B2_TEST_EXPERIMENTAL=1")
-        monkeypatch.setenv("B2_ATTN_FWD4" if variant == "fwd4" else "B2_ATTN_PFWD", "1")
+        monkeypatch.setenv({"fwd4": "B2_ATTN_FWD4", "pfwd": "B2_ATTN_PFWD", "pbwd": "B2_ATTN_PBWD"}[variant], "1")
 
 
-@pytest.mark.parametrize("variant", ["v3", "poly", "fwd4", "pfwd"])
+@pytest.mark.parametrize("variant", ["v3", "poly", "fwd4", "pfwd", "pbwd"])
 @pytest.mark.parametrize("B,H,n_q,n_k,fused,gain", CASES)
 def test_attention_fwd_bwd(B, H, n_q, n_k, fused, gain, variant, monkeypatch):
     _select_variant(variant, monkeypatch, n_k)
@@ -107,7 +110,7 @@ def test_attention_fwd_bwd(B, H, n_q, n_k, fused, gain, variant, monkeypatch):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("variant", ["v3", "poly", "fwd4", "pfwd"])
+@pytest.mark.parametrize("variant", ["v3", "poly", "fwd4", "pfwd", "pbwd"])
 def test_attention_speed_report(variant, monkeypatch):
     """Not an assertion on speed — prints achieved TFLOP/s of the three kernels for the bench log."""
     from sdxl_training_improvements_b200 import ops
