@@ -17,7 +17,7 @@ import random
 
 import pytest
 
-STAGES = 5  # F3_STAGES
+STAGES = 5  # F3_STAGES (forward); the backward kernels use Q3_STAGES = 6, see Sim(stages=...)
 
 
 class Barrier:
@@ -41,7 +41,10 @@ class Barrier:
 
 
 class Sim:
-    def __init__(self, ntiles, nkb, seed):
+    def __init__(self, ntiles, nkb, seed, stages=STAGES, groups_read_stage=False):
+        global STAGES
+        STAGES = stages
+        self.groups_read_stage = groups_read_stage  # dK/dV kernel: the softmax warps read LSE / D from the TMA stage
         self.rnd = random.Random(seed)
         self.ntiles, self.nkb = ntiles, nkb
         B = Barrier
@@ -177,6 +180,10 @@ class Sim:
                 buf, spar = G % 3, (G // 3) & 1
                 yield lambda buf=buf, spar=spar, G=G: self.bar_s[buf].ready(spar, G // 3)
                 assert self.ring[buf] == ("S", G), f"group {g} reads ring slot {buf} = {self.ring[buf]}, wants S({G})"
+                if self.groups_read_stage:  # attn_pbwd_dkv_kernel: mbar_wait(bar_full[stg], fpar) before reading ld_s[stg]
+                    stg, fpar = G % STAGES, (G // STAGES) & 1
+                    yield lambda stg=stg, fpar=fpar, G=G: self.bar_full[stg].ready(fpar, G // STAGES)
+                    assert self.stage[stg] == G, f"group {g} reads LSE / D of stage {stg} holding block {self.stage[stg]}"
                 if kown > 0 and self.rnd.random() < 0.5:  # the lazy-rescale path: needs the previous own PV to be complete
                     yield lambda pvc=pvc: self.bar_pv[g].ready((pvc - 1) & 1, pvc - 1)
                     assert self.o_acc[g] == (tl, kown), f"rescale of O_{g}: {self.o_acc[g]} vs tile {tl}, {kown} PVs"
@@ -252,3 +259,14 @@ class Sim:
 def test_persistent_forward_protocol(ntiles, nkb):
     for seed in range(12):
         Sim(ntiles, nkb, seed).run()
+
+
+@pytest.mark.parametrize("nkb", [1, 2, 5, 6, 7, 16])
+@pytest.mark.parametrize("ntiles", [1, 2, 4, 5])
+def test_persistent_backward_protocol(ntiles, nkb):
+    """Same skeleton with six stages; the dK/dV variant's softmax warps additionally wait on the stage's full barrier to
+    read the bulk-copied LSE / D.  (bar_pv and the per-group accumulators of the forward model are a superset of the single
+    accumulator of the backward kernels.)"""
+    for seed in range(8):
+        Sim(ntiles, nkb, seed, stages=6, groups_read_stage=True).run()
+
