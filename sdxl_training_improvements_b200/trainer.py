@@ -26,6 +26,11 @@ from .unet import B200UNet, bf16
 LATENT_PAD = 8
 
 
+class FatalStepError(RuntimeError):
+    """A training step failed after part of the data-parallel gradient exchange had been issued: peers already hold
+    (and have flagged) some of this step's chunks, so the step cannot be skipped or retried — the job must stop."""
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # schedule (host side; reference: novelai_v3.py)
 # ----------------------------------------------------------------------------------------------------------------
@@ -226,6 +231,7 @@ class GraphedMicroStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graphs: Optional[list] = None  # data parallel: one graph per exchange chunk
         self.loss: Optional[torch.Tensor] = None
+        self.static_last: Dict[str, torch.Tensor] = {}
         self.launches_per_replay = 0
 
     def _run(self):
@@ -233,7 +239,7 @@ class GraphedMicroStep:
                                           pooled=self.pooled, time_ids=self.time_ids, t_embed=self.t_embed,
                                           sig_or_t=self.sig_or_t, weight=self.weight, loss_scale=1.0)
 
-    def capture(self):
+    def capture(self, pool=None):
         """Call at an optimizer-step boundary: the warm-up passes accumulate into the gradient buffer, which is zeroed
         again afterwards.  Data parallel (core.dp set): the micro-step is captured as one graph PER CHUNK of the exchange
         plan — segment k ends when chunk k of the gradient buffer is final — sharing one memory pool and replayed in
@@ -249,18 +255,19 @@ class GraphedMicroStep:
                 self._run()
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()  # the warm-up passes' activations go back to the driver before the pool grows
         n0 = _lib.launch_count()
         x = core.dp
         if x is None:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, pool=pool):
                 self.loss = self._run()
         else:
             eng, st = core.unet.engine, core.unet.store
             cuts = x.plan.cuts
             self.graphs = []
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, pool=pool):
                 self.loss = core._forward(latents=self.latents, ctx=self.ctx, pooled=self.pooled, time_ids=self.time_ids,
                                           t_embed=self.t_embed, sig_or_t=self.sig_or_t, weight=self.weight, loss_scale=1.0)
                 tape, dpred = core._saved
@@ -282,6 +289,9 @@ class GraphedMicroStep:
             assert lo == len(order)
             order.clear()
         core.dp_last = was_last
+        # static tensors of the captured micro-step (noise drawn in-graph, noisy latents, target, prediction): a replay
+        # refreshes them in place; parity tests read the noise from here to feed the oracle the same draw
+        self.static_last = dict(core.last)
         self.launches_per_replay = _lib.launch_count() - n0
         self.core.unet.store.grad.zero_()
         torch.cuda.synchronize()
@@ -323,11 +333,20 @@ class GraphedOptimizerStep:
         self.max_norm, self.gscale = max_norm, grad_scale
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_replay = 0
+        self._hyper = None
+
+    def _hyper_now(self):
+        g = self.optimizer.param_groups[0]
+        return (float(g["lr"]), tuple(float(b) for b in g["betas"]), float(g["eps"]), float(g.get("weight_decay", 0.0)),
+                float(self.max_norm), float(self.gscale))
 
     def capture(self):
-        """Captures WITHOUT executing: optimizer state is not advanced by the capture itself."""
+        """Captures WITHOUT executing: optimizer state is not advanced by the capture itself.  lr / betas / eps / weight
+        decay / clip norm are kernel ARGUMENTS, i.e. baked into the graph: `replay()` re-captures when any of them has
+        changed (an lr schedule that changes every step should drive the un-captured `fused_step` instead)."""
         from . import _lib
         opt = self.optimizer
+        self._hyper = self._hyper_now()
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
@@ -339,6 +358,8 @@ class GraphedOptimizerStep:
         return self
 
     def replay(self):
+        if self._hyper_now() != self._hyper:
+            self.capture()
         self.graph.replay()
         self.optimizer.after_graph_step()
 
@@ -360,7 +381,8 @@ def _prep_batch(batch: Dict[str, Any], device) -> Dict[str, torch.Tensor]:
 
 
 def _tag_weight_mean(batch) -> Optional[float]:
-    """ddpm_trainer.py:348-368: mean over samples of the mean tag weight, if every sample has weights."""
+    """ddpm_trainer.py:348-368: mean over samples of the mean tag weight, if every sample has weights.  The reference
+    builds the per-sample weights as a tensor in the model dtype (bf16, :365) and takes `.mean()` of that."""
     md = batch.get("metadata")
     if isinstance(md, (list, tuple)) and md and all(isinstance(m, dict) and isinstance(m.get("tag_info"), dict)
                                                      and "tags" in m["tag_info"] for m in md):
@@ -370,7 +392,7 @@ def _tag_weight_mean(batch) -> Optional[float]:
             if not iw:
                 return None
             ws.append(sum(iw) / len(iw))
-        return float(sum(ws) / len(ws))
+        return float(torch.tensor(ws, dtype=bf16).mean())
     return None
 
 
@@ -397,6 +419,9 @@ class _StepBase:
         # p.grad with the 1/accumulation scale the step protocol announces), and `loss.backward()` is a no-op.
         self.cuda_graph = bool(kwargs.get("cuda_graph", False))
         self._micro_graphs: Dict[Any, GraphedMicroStep] = {}
+        self._graph_pool = None                      # shared by all captured shapes
+        self.max_graphed_shapes = int(kwargs.get("max_graphed_shapes", 8))
+        self.uncaptured_micro_steps = 0              # micro-steps cuda_graph mode ran un-captured (new shape mid-window / cap)
         self._opt_graph: Optional[GraphedOptimizerStep] = None
         self._pending_grad_scale = 1.0
 
@@ -417,6 +442,13 @@ class _StepBase:
             if accumulate:
                 loss = loss / self.gradient_accumulation_steps
             loss.backward()
+        except Exception as e:
+            x = self.core.dp
+            if x is not None and x.issued:
+                # chunks of this step are already with the peers under the current sequence number: a "skip and continue"
+                # (ddpm_trainer.py:202-204) would re-issue them unsynchronised and silently corrupt the gradients
+                raise FatalStepError(f"step failed after the gradient exchange had started: {type(e).__name__}: {e}") from e
+            raise
         finally:
             self.core.dp_last = False
         if not accumulate or is_last_accumulation_step:
@@ -430,14 +462,31 @@ class _StepBase:
         key = (B, H, W, t["ctx"].shape[0] // B)
         gm = self._micro_graphs.get(key)
         if gm is None:
-            chk = torch.zeros(1, device=self.unet.device, dtype=torch.float64)
-            ops.sumsq(self.unet.store.grad, chk)
-            if float(chk) != 0.0:
-                raise RuntimeError("cuda_graph capture must happen at an optimizer-step boundary (gradients not zero)")
+            # A capture runs warm-up passes that accumulate into the gradient buffer, so it can only happen at an optimizer-
+            # step boundary (gradients all zero).  A shape first seen in the middle of an accumulation window (aspect buckets
+            # + gradient_accumulation_steps > 1) therefore runs this micro-step through the SAME kernels un-captured and is
+            # captured the next time it shows up at a boundary; shapes beyond `max_graphed_shapes` always run un-captured.
+            at_boundary = False
+            if len(self._micro_graphs) < self.max_graphed_shapes:
+                chk = torch.zeros(1, device=self.unet.device, dtype=torch.float64)
+                ops.sumsq(self.unet.store.grad, chk)
+                at_boundary = float(chk) == 0.0
+            if not at_boundary:
+                self.uncaptured_micro_steps += 1
+                loss = self.core.step_no_autograd(grad_scale=self._pending_grad_scale, latents=t["latents"], ctx=t["ctx"],
+                                                  pooled=t["pooled"], time_ids=t["time_ids"],
+                                                  t_embed=t_embed.to(self.unet.device), sig_or_t=sig_or_t.to(self.unet.device),
+                                                  weight=weight, loss_scale=1.0)
+                return _PrecomputedBackward.apply(loss.reshape(()), self.core._anchor)
             torch.cuda.empty_cache()
+            if self._graph_pool is None:
+                # ONE memory pool for every captured shape: a micro-step graph is self-contained (activations die inside
+                # it) and graphs replay one at a time on one stream, so the pool's size is the LARGEST shape's activation
+                # set (~40 GB at 1024^2, B=4), not the sum over buckets
+                self._graph_pool = torch.cuda.graph_pool_handle()
             gm = GraphedMicroStep(self.core, B, H, W, key[3])
             gm.load(t["latents"], t["ctx"], t["pooled"], t["time_ids"], t_embed, sig_or_t, weight, 1.0)
-            gm.capture()
+            gm.capture(pool=self._graph_pool)
             self._micro_graphs[key] = gm
         gm.load(t["latents"], t["ctx"], t["pooled"], t["time_ids"], t_embed, sig_or_t, weight, self._pending_grad_scale)
         loss = gm.replay(last=self.core.dp_last)
@@ -486,6 +535,8 @@ class _StepBase:
                 try:
                     loss, metrics = self._execute_training_step(batch, accumulate=N > 1,
                                                                 is_last_accumulation_step=(step + 1) % N == 0)
+                except FatalStepError:
+                    raise
                 except Exception:
                     if isinstance(self, B200FlowMatchingTrainer):
                         raise  # flow loop re-raises (flow_matching_trainer.py:226-228)

@@ -56,6 +56,7 @@ class UNetEngine:
         self.cfg = store.cfg
         self.tape: List[Callable[[], None]] = []
         self._ws: Dict[str, torch.Tensor] = {}
+        self._ws_retired: List[torch.Tensor] = []
         st = store
         for pfx in self._attn_prefixes():
             assert st.adjacent(f"{pfx}.attn1.to_q.weight", f"{pfx}.attn1.to_k.weight", f"{pfx}.attn1.to_v.weight")
@@ -70,6 +71,9 @@ class UNetEngine:
         cur = self._ws.get(key)
         if cur is None or cur.numel() < numel or cur.dtype != dtype:
             dev = self.store.flat.device
+            if cur is not None:
+                # a CUDA graph captured for a smaller shape keeps the OLD buffer's address: it must stay allocated
+                self._ws_retired.append(cur)
             cur = torch.empty(numel, device=dev, dtype=dtype)
             self._ws[key] = cur
         return cur[:numel]
@@ -564,6 +568,7 @@ class B200UNet:
         self.engine = UNetEngine(self.store)
         self.training = True
         self.dtype = bf16
+        self._disk_config: Optional[dict] = None
         self._anchor = torch.zeros(1, device=device, requires_grad=True)
 
     # --- nn.Module-like surface ---
@@ -616,6 +621,68 @@ class B200UNet:
     def enable_xformers_memory_efficient_attention(self, *a, **k):  # attention is our own kernel
         return None
 
+    def diffusers_config(self) -> dict:
+        """The `config.json` diffusers' `UNet2DConditionModel.from_pretrained` needs to rebuild this network (the
+        reference reloads checkpoints through `StableDiffusionXLPipeline.from_pretrained`, src/models/sdxl.py:25-40).
+        A config read by `from_pretrained` is written back unchanged; otherwise the SDXL-architecture fields are emitted
+        in diffusers' own vocabulary: `attention_head_dim` is the per-level head COUNT, every level lists a
+        `transformer_layers_per_block` entry (levels without attention are `DownBlock2D` / `UpBlock2D` and ignore it)."""
+        if getattr(self, "_disk_config", None) is not None:
+            return dict(self._disk_config)
+        c = self.config
+        depth = list(c["transformer_layers_per_block"])
+        down = ["CrossAttnDownBlock2D" if d > 0 else "DownBlock2D" for d in depth]
+        up = ["CrossAttnUpBlock2D" if d > 0 else "UpBlock2D" for d in reversed(depth)]
+        return {
+            "_class_name": "UNet2DConditionModel",
+            "_diffusers_version": "0.21.0",
+            "act_fn": "silu",
+            "addition_embed_type": "text_time",
+            "addition_embed_type_num_heads": 64,
+            "addition_time_embed_dim": c["addition_time_embed_dim"],
+            "attention_head_dim": list(c["num_heads"]),
+            "block_out_channels": list(c["block_out_channels"]),
+            "center_input_sample": False,
+            "class_embed_type": None,
+            "class_embeddings_concat": False,
+            "conv_in_kernel": 3,
+            "conv_out_kernel": 3,
+            "cross_attention_dim": c["cross_attention_dim"],
+            "cross_attention_norm": None,
+            "down_block_types": down,
+            "downsample_padding": 1,
+            "dual_cross_attention": False,
+            "encoder_hid_dim": None,
+            "encoder_hid_dim_type": None,
+            "flip_sin_to_cos": True,
+            "freq_shift": 0,
+            "in_channels": c["in_channels"],
+            "layers_per_block": c["layers_per_block"],
+            "mid_block_only_cross_attention": None,
+            "mid_block_scale_factor": 1,
+            "mid_block_type": "UNetMidBlock2DCrossAttn",
+            "norm_eps": c["norm_eps"],
+            "norm_num_groups": c["norm_num_groups"],
+            "num_attention_heads": None,
+            "num_class_embeds": None,
+            "only_cross_attention": False,
+            "out_channels": c["out_channels"],
+            "projection_class_embeddings_input_dim": c["projection_class_embeddings_input_dim"],
+            "resnet_out_scale_factor": 1.0,
+            "resnet_skip_time_act": False,
+            "resnet_time_scale_shift": "default",
+            "sample_size": 128,
+            "time_cond_proj_dim": None,
+            "time_embedding_act_fn": None,
+            "time_embedding_dim": None,
+            "time_embedding_type": "positional",
+            "timestep_post_act": None,
+            "transformer_layers_per_block": [max(1, d) for d in depth],
+            "up_block_types": up,
+            "upcast_attention": None,
+            "use_linear_projection": True,
+        }
+
     def save_pretrained(self, path, safe_serialization=True, **kw):
         import json
         import os
@@ -623,12 +690,12 @@ class B200UNet:
         sd = {k: v.contiguous() for k, v in self.state_dict().items()}
         if safe_serialization:
             from safetensors.torch import save_file
-            save_file({k: v.cpu() for k, v in sd.items()}, os.path.join(path, "diffusion_pytorch_model.safetensors"))
+            save_file({k: v.cpu() for k, v in sd.items()}, os.path.join(path, "diffusion_pytorch_model.safetensors"),
+                      metadata={"format": "pt"})
         else:
             torch.save(sd, os.path.join(path, "diffusion_pytorch_model.bin"))
         with open(os.path.join(path, "config.json"), "w") as f:
-            json.dump({"_class_name": "UNet2DConditionModel", **{k: (list(v) if isinstance(v, tuple) else v)
-                                                                for k, v in self.config.items()}}, f, indent=1)
+            json.dump(self.diffusers_config(), f, indent=2, sort_keys=True)
 
     @classmethod
     def from_pretrained(cls, path, device="cuda", subfolder: Optional[str] = None, **kw):
@@ -642,9 +709,17 @@ class B200UNet:
         root = os.path.join(path, subfolder) if subfolder else path
         cfg = dict(SDXL_BASE)
         cj = os.path.join(root, "config.json")
+        disk_config = None
         if os.path.exists(cj):
             with open(cj) as f:
                 disk = json.load(f)
+            disk_config = dict(disk)
+            unsupported = {k: disk[k] for k, want in (("use_linear_projection", True), ("addition_embed_type", "text_time"),
+                                                      ("act_fn", "silu"), ("resnet_time_scale_shift", "default"),
+                                                      ("flip_sin_to_cos", True), ("freq_shift", 0))
+                           if k in disk and disk[k] != want}
+            if unsupported:
+                raise ValueError(f"B200UNet implements the SDXL UNet architecture only; unsupported config: {unsupported}")
             if "num_heads" not in disk and "attention_head_dim" in disk:  # diffusers names the head COUNT this way
                 disk["num_heads"] = disk["attention_head_dim"]
             if "transformer_layers_per_block" in disk and "down_block_types" in disk:
@@ -656,6 +731,7 @@ class B200UNet:
                 if k in disk:
                     cfg[k] = tuple(disk[k]) if isinstance(disk[k], list) else disk[k]
         net = cls(cfg, device=device)
+        net._disk_config = disk_config  # written back unchanged by save_pretrained
         st_single = os.path.join(root, "diffusion_pytorch_model.safetensors")
         st_index = st_single + ".index.json"
         sd = {}

@@ -53,3 +53,44 @@ def test_from_pretrained_bin_and_missing(tmp_path):
     import pytest
     with pytest.raises(FileNotFoundError):
         B200UNet.from_pretrained(str(tmp_path / "nothing_here"), device="cpu")
+
+
+def test_config_json_is_a_complete_diffusers_unet_config(tmp_path):
+    """diffusers' UNet2DConditionModel.from_pretrained must be able to rebuild the network from config.json
+    (the reference reloads through StableDiffusionXLPipeline.from_pretrained, src/models/sdxl.py:25-40): block types,
+    attention_head_dim (= head count per level), text_time addition embedding, linear projections."""
+    net = B200UNet(device="cpu") if False else None  # full size is not needed: the config is a pure function of cfg
+    from sdxl_training_improvements_b200.params import SDXL_BASE
+    shell = B200UNet.__new__(B200UNet)
+    shell.config, shell._disk_config = dict(SDXL_BASE), None
+    c = shell.diffusers_config()
+    assert c["_class_name"] == "UNet2DConditionModel"
+    assert c["down_block_types"] == ["DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"]
+    assert c["up_block_types"] == ["CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"]
+    assert c["mid_block_type"] == "UNetMidBlock2DCrossAttn"
+    assert c["attention_head_dim"] == [5, 10, 20] and c["transformer_layers_per_block"] == [1, 2, 10]
+    assert c["addition_embed_type"] == "text_time" and c["use_linear_projection"] is True
+    assert c["block_out_channels"] == [320, 640, 1280] and c["cross_attention_dim"] == 2048
+    assert c["projection_class_embeddings_input_dim"] == 2816 and c["addition_time_embed_dim"] == 256
+    assert "num_heads" not in c  # no internal keys leak into the file
+    # tiny config: write -> read -> the internal config is recovered; a config read from disk is written back unchanged
+    cfg = tiny_config()
+    net = B200UNet(cfg, device="cpu")
+    d = str(tmp_path / "u")
+    net.save_pretrained(d)
+    disk = json.load(open(os.path.join(d, "config.json")))
+    disk["_diffusers_version"] = "0.32.1"
+    disk["some_future_key"] = 7
+    json.dump(disk, open(os.path.join(d, "config.json"), "w"))
+    net2 = B200UNet.from_pretrained(d, device="cpu")
+    for k in ("block_out_channels", "transformer_layers_per_block", "num_heads", "cross_attention_dim"):
+        assert tuple(net2.config[k]) == tuple(cfg[k]) if isinstance(cfg[k], tuple) else net2.config[k] == cfg[k], k
+    d2 = str(tmp_path / "u2")
+    net2.save_pretrained(d2)
+    assert json.load(open(os.path.join(d2, "config.json"))) == disk
+    # an architecture this UNet does not implement is refused rather than mis-built
+    disk["use_linear_projection"] = False
+    json.dump(disk, open(os.path.join(d, "config.json"), "w"))
+    import pytest
+    with pytest.raises(ValueError):
+        B200UNet.from_pretrained(d, device="cpu")

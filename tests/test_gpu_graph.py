@@ -88,3 +88,53 @@ def test_graph_replay_matches_eager(method, optname):
     if optname == "fp32":
         assert _rel(opts[0].master - before, opts[1].master - before) <= 0.2
     assert opts[0].steps == opts[1].steps == 2
+
+
+def test_new_shape_mid_accumulation_runs_uncaptured_then_captures_at_the_next_boundary():
+    """ADVICE r1 (trainer.py:436): aspect buckets + gradient_accumulation_steps > 1 — a latent shape first seen on the second
+    micro-step of an accumulation window cannot be captured (gradients are not zero).  It must run through the same
+    kernels un-captured (no exception, nothing dropped, accumulation phase intact) and be captured the next time it shows
+    up at a boundary; all captured shapes share ONE graph memory pool; an lr change re-captures the optimizer graph."""
+    from oracle.unet_sdxl import OracleUNet, seeded_init_, tiny_config
+    from sdxl_training_improvements_b200.trainer import B200AdamW, create_trainer
+    from sdxl_training_improvements_b200.unet import B200UNet
+    cfg = tiny_config()
+    sd = seeded_init_(OracleUNet(cfg), 3).state_dict()
+    nets, trs = [], []
+    for graph in (True, False):
+        net = B200UNet(cfg, device="cuda")
+        net.load_state_dict(sd)
+        nets.append(net)
+        trs.append(create_trainer(_conf("flow_matching", accum=2), net, B200AdamW(net, lr=1e-3), device="cuda", seed=5,
+                                  cuda_graph=graph))
+    tg, te = trs
+    gen = torch.Generator().manual_seed(4)
+    shapes = [(16, 16), (16, 24), (16, 24), (16, 16), (24, 16), (16, 24)]   # window 1: A then NEW B; window 2: B, A; ...
+    for k, (H, W) in enumerate(shapes):
+        b = _batch(cfg, 2, H, W, 300 + k)
+        t = torch.sigmoid(torch.randn(2, generator=gen)).to(bf16)
+        last = k % 2 == 1
+        tg._pending_grad_scale = 0.5   # what _execute_training_step(accumulate=True) announces before compute_loss
+        og = tg.compute_loss(None, b, t=t)
+        # the eager twin must see the graph trainer's in-graph / un-captured noise draw: same Philox counter
+        te.core.seed_offset.copy_(tg.core.seed_offset - torch.tensor([0, 1], device="cuda"))
+        oe = te.compute_loss(None, b, t=t)
+        (og["loss"] / 2).backward(); (oe["loss"] / 2).backward()
+        assert abs(float(og["loss"]) - float(oe["loss"])) <= 1e-3 * max(1.0, abs(float(oe["loss"]))), k
+        if last:
+            assert _rel(nets[0].store.grad, nets[1].store.grad) <= 1e-2, k
+            if k == 3:
+                tg.optimizer.param_groups[0]["lr"] = 5e-4   # a scheduler changes lr: the optimizer graph must follow
+                te.optimizer.param_groups[0]["lr"] = 5e-4
+            tg.optimizer_step(); te.optimizer_step()
+            assert _rel(nets[0].store.flat, nets[1].store.flat) <= 1e-3, k
+    # (16,24) first arrived mid-window -> un-captured once, captured at k=2 (a boundary); (24,16) arrived at a boundary
+    assert tg.uncaptured_micro_steps == 1
+    assert set(tg._micro_graphs) == {(2, 16, 16, 77), (2, 16, 24, 77), (2, 24, 16, 77)}
+    pools = {tuple(g.graph.pool()) for g in tg._micro_graphs.values()}
+    assert len(pools) == 1, "captured shapes must share one graph memory pool"
+    tg.max_graphed_shapes = 3
+    b = _batch(cfg, 2, 24, 24, 999)
+    tg._pending_grad_scale = 1.0
+    tg.compute_loss(None, b, t=torch.tensor([0.3, 0.6]).to(bf16))["loss"].backward()
+    assert (2, 24, 24, 77) not in tg._micro_graphs and tg.uncaptured_micro_steps == 2   # cap reached: runs un-captured
