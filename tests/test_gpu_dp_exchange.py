@@ -144,6 +144,79 @@ def _trainer_worker(rank, world, port, q, mode):
         dist.destroy_process_group()
 
 
+def _equivalence_worker(rank, world, port, q):
+    """T6: N ranks x batch b == 1 rank x batch N*b (DDP's contract, src/core/distributed.py:142-163: gradients are the
+    MEAN over ranks of per-rank mean-loss gradients).  Global batch of 4 samples with explicit noise / timesteps; rank r
+    takes samples [2r, 2r+2) through the plugin + the overlapped peer exchange; every rank also runs all 4 samples on
+    its own GPU without any exchange.  reduced_gradient / world must equal the single-GPU gradient."""
+    sys.path.insert(0, ROOT)
+    dist = _init(rank, world, port)
+    try:
+        from types import SimpleNamespace
+        from oracle.unet_sdxl import OracleUNet, seeded_init_, tiny_config
+        from sdxl_training_improvements_b200.trainer import B200AdamW, B200DDPMTrainer
+        from sdxl_training_improvements_b200.unet import B200UNet
+        cfg = tiny_config()
+        sd = seeded_init_(OracleUNet(cfg), 0).state_dict()
+        conf = SimpleNamespace(model=SimpleNamespace(num_timesteps=1000, sigma_min=0.002, sigma_max=20000.0,
+                                                     use_ztsnr=True, min_snr_gamma=5.0),
+                               training=SimpleNamespace(method="ddpm", prediction_type="v_prediction",
+                                                        gradient_accumulation_steps=1, clip_grad_norm=1.0))
+        nets, trs = [], []
+        for _ in range(2):
+            net = B200UNet(cfg, device=f"cuda:{rank}")
+            net.load_state_dict(sd)
+            nets.append(net)
+            trs.append(B200DDPMTrainer(net, B200AdamW(net, lr=1e-3), None, f"cuda:{rank}", config=conf, seed=3))
+        tr_dp, tr_one = trs
+        tr_one.core.dp, tr_one.world_size = None, 1          # the single-GPU twin: no exchange
+        used_peer = tr_dp.core.dp is not None
+        Bg, H, W = 4, 16, 16
+        g = torch.Generator().manual_seed(77)                 # the same global batch on every rank
+        full = {"vae_latents": torch.randn(Bg, 4, H, W, generator=g),
+                "prompt_embeds": torch.randn(Bg, 77, cfg["cross_attention_dim"], generator=g),
+                "pooled_prompt_embeds": torch.randn(Bg, 96, generator=g),
+                "time_ids": torch.tensor([[128., 128., 0., 0., 128., 128.]]).repeat(Bg, 1)[:, None],
+                "metadata": [{} for _ in range(Bg)]}
+        noise = torch.randn(Bg, 4, H, W, generator=g)
+        ts = torch.tensor([650, 720, 800, 880])
+        b = Bg // world
+        sl = slice(rank * b, (rank + 1) * b)
+        mine = {k: (v[sl] if torch.is_tensor(v) else v[sl]) for k, v in full.items()}
+        rels = []
+        for rep in range(2):   # pass 0: no chunk plan yet -> whole-buffer exchange; pass 1: chunks leave during backward
+            for n_ in nets:
+                n_.zero_grad()
+            tr_dp.core.dp_last = True
+            out = tr_dp.training_step(mine, noise=noise[sl], timesteps=ts[sl])
+            out["loss"].backward()
+            tr_dp.core.dp_last = False
+            if used_peer:
+                x = tr_dp.core.dp
+                if not x.issued:
+                    x.exchange_all()
+                x.finish()
+            else:
+                dist.all_reduce(nets[0].store.grad)
+            out1 = tr_one.training_step(full, noise=noise, timesteps=ts)
+            out1["loss"].backward()
+            torch.cuda.synchronize()
+            red = nets[0].store.grad.float() / world
+            one = nets[1].store.grad.float()
+            rels.append(float((red - one).norm() / one.norm()))
+            lsum = torch.tensor([float(out["loss"])], device="cuda")
+            dist.all_reduce(lsum)
+            loss_dp, loss_one = float(lsum) / world, float(out1["loss"])
+        flat = nets[0].store.grad.clone()
+        everyone = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(everyone, flat)
+        same = all(torch.equal(everyone[0], e) for e in everyone)
+        q.put((rank, used_peer, rels, loss_dp, loss_one, same))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
 def _spawn(target, world, extra=()):
     import torch.multiprocessing as mp
     port = 32500 + (os.getpid() % 2000) + len(extra) * 7 + (hash(extra) % 50)
@@ -192,6 +265,18 @@ def test_trainer_overlapped_exchange_matches_nccl_allreduce():
         assert rel <= 2e-2, f"{mode}: parameter update differs from the NCCL all-reduce path, rel-L2 {rel:.3e}"
         assert all(abs(a - b) <= 1e-3 * max(1.0, abs(b)) for a, b in zip(out[mode][4], out[base][4])), \
             (out[mode][4], out[base][4])
+
+
+@pytest.mark.timeout(600)
+def test_two_ranks_times_b_equals_one_rank_times_2b():
+    """T6 (VERDICT r1 missing #4).  Tolerances (stated): gradient rel-L2 <= 1e-2 (two bf16 partial sums vs one bf16 sum of
+    four samples: different rounding points, same fp32 mathematics), loss |d| <= 1e-3 * max(1, loss)."""
+    _world()
+    for rank, used_peer, rels, loss_dp, loss_one, same in _spawn(_equivalence_worker, 2):
+        assert used_peer, "the peer-memory exchange was not in use"
+        assert same, "reduced gradients differ across ranks"
+        assert all(r <= 1e-2 for r in rels), f"rank {rank}: reduced gradient / world vs single-GPU gradient rel-L2 {rels}"
+        assert abs(loss_dp - loss_one) <= 1e-3 * max(1.0, abs(loss_one)), (loss_dp, loss_one)
 
 
 if __name__ == "__main__":
