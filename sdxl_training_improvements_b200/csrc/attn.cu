@@ -5,7 +5,8 @@
 // Kernels (all: TMA-staged bf16 tiles in SWIZZLE_128B smem -> tcgen05.mma (SS) into TMEM -> softmax warps read their TMEM
 // lane with tcgen05.ld, do the exp2 / rescale math in registers, write the bf16 result back IN PLACE with tcgen05.st ->
 // tcgen05.mma (TS: A operand from TMEM) accumulates the output tile in TMEM):
-//   attn_fwd3   : CTA = 128 queries x key blocks of 128; ring of three S accumulators, two softmax groups on alternate blocks
+//   attn_pfwd2  : persistent CTA per SM over (sample, head, 128-query tile) x key blocks of 128; ring of three S accumulators,
+//                 two softmax groups on alternate blocks, deferred two-group merge            (attn_fwd3: its per-tile ancestor)
 //   attn_xfwd   : cross-attention (<= 96 keys): persistent CTA per SM over (sample, head, query-tile) work items
 //   attn_bwd_dq3: CTA = 128 queries x key blocks of 64;   S, dP -> dS -> dQ += dS K
 //   attn_bwd_dkv3: CTA = 128 keys x query blocks of 64;   S^T, dP^T -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q
@@ -86,9 +87,6 @@ __device__ __forceinline__ void store_row32(bf16* dst, const float* f) {
 constexpr int F3_STAGES = 5;
 constexpr int F3_SMEM = AT_TILE128 + F3_STAGES * 2 * AT_TILE128 + 1024;
 
-// POLY (opt-in, B2_ATTN_POLY_EXP2=1): every fourth exponential of the softmax is evaluated as a polynomial on the FMA pipe
-// (poly_exp2, tc.cuh) instead of ex2.approx — the phase counters put the exp2 phase of this kernel at the MUFU rate.
-template <bool POLY>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnP p) {
@@ -285,8 +283,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const float p0 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i]), p.c, -m_used));
           const float p1 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 1]), p.c, -m_used));
           const float p2 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 2]), p.c, -m_used));
-          const float x3 = fmaf(__uint_as_float(r[cc * 32 + 2 * i + 3]), p.c, -m_used);
-          const float p3 = POLY ? poly_exp2(x3) : fast_exp2(x3);
+          const float p3 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 3]), p.c, -m_used));
           l0 += p0; l1 += p1; l2 += p2; l3 += p3;
           pk[i] = pack_bf16x2(p0, p1);
           pk[i + 1] = pack_bf16x2(p2, p3);
@@ -345,272 +342,40 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward v4 (EXPERIMENTAL, opt-in with B2_ATTN_FWD4=1 until it has been measured): the v3 kernel with SIXTEEN softmax warps.
-//   Why: the ncu capture of v3 has nothing saturated — issue slots 28 %, MUFU 35 %, tensor pipe 22 % of the elapsed cycles,
-//   10 warps resident (profiles/r1_attention_notes.md): each of the eight softmax warps walks a 128-element row per key
-//   block through one dependent chain (tcgen05.ld -> max -> FFMA -> ex2 -> pack -> tcgen05.st -> arrive) and two warps per
-//   scheduler cannot hide it.  A TMEM lane quadrant can only be read by warps with the matching (warp % 4), so more warps
-//   means splitting the COLUMNS: warps w and w + 4 of a group own the same 32 rows and one half (64 keys) of the block
-//   each — 64 registers of S per thread instead of 128, so the register file takes 18 warps.  The two halves agree on the
-//   running row maximum through shared memory (one named barrier per block, which also orders "both halves have read S"
-//   before "either half overwrites it with P"), keep separate partial row sums, and each rescales / finally reads its half
-//   of the O accumulator.  Producer and MMA warps are those of v3; bar_p counts 256 arrivals.
-// warps (576 threads): 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = group 0 (halves 0,1), 10..17 = group 1.
+// forward, PERSISTENT (attn_pfwd2): the v3 pipeline with the query tile as an outer loop inside the CTA.
+//   What round 2's first GPU run said about the first persistent draft (profiles/r2_attention_notes.md): parity green but
+//   SLOWER than v3 (n = 1024: 70 vs 55 us; n = 4096: 366 vs 262 us) for two reasons visible without a profiler —
+//   ptxas spilled 512 bytes in the softmax loop (168 registers per thread at 320 threads, one TMEM row of 128 logits live),
+//   and the two-group merge sat between tiles un-overlapped (the group that finishes first idles for a whole block).
+//   This version fixes both and trims the MMA thread's critical path:
+//   * 384 threads = three warpgroups: softmax group 0, softmax group 1, {TMA producer, MMA issuer, 2 idle warps}.
+//     setmaxnreg moves registers from the third warpgroup (56) to the softmax warpgroups (224): no spills.
+//   * DEFERRED MERGE: a group that has finished its last key block of tile t goes straight on to its first key block of
+//     tile t+1 (whose S was issued ahead) and only then merges tile t; the MMA thread holds back the first PV of tile t+1
+//     (which overwrites O) until both groups have read O of tile t (bar_ofree).  The skew between the groups and the
+//     PV-completion latency are hidden behind a block of useful softmax work.
+//   * MMA thread: descriptors built once and advanced with one add (tc.cuh desc_adv), the K/V-stage wait for the S that
+//     will be issued after a PV is taken BEFORE waiting for P (off the critical path), and no separate "PV done" barrier:
+//     the lazy-rescale path waits on the K/V stage's bar_empty, which the same PV commits.
+// Every ring keeps running across tiles on a global block counter G: S ring slot G % 3, K/V stage G % 5.
+// warps: 0..3 = softmax group 0, 4..7 = group 1 (warp w owns TMEM lanes 32*(w%4)..+31), 8 = TMA producer, 9 = MMA issuer +
+// TMEM allocator, 10..11 = idle.
 // ---------------------------------------------------------------------------------------------
-constexpr int A4_THREADS = 576;
+constexpr int P2_THREADS = 384;
+constexpr int P2_SMEM = 2 * AT_TILE128 + F3_STAGES * 2 * AT_TILE128 + 1024;
 
-__device__ __forceinline__ void a4_group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory"); }
-__device__ __forceinline__ void a4_all_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void p2_groups_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__global__ void __launch_bounds__(A4_THREADS, 1)
-attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const AttnP p) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_full[F3_STAGES], bar_empty[F3_STAGES], bar_s[3], bar_p[3], bar_pv[2], bar_o;
-  __shared__ uint32_t tmem_slot;
-  __shared__ float xmax[2][2][2][128];  // [parity of the group's block count][group][half][row]: block-local row maxima
-  __shared__ float m_fin[2][128];       // [group][row] final running maximum
-  __shared__ float l_fin[2][2][128];    // [group][half][row] partial row sums
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;
-  const uint32_t sKV = smem_base + AT_TILE128;
-  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nkb = (p.n_k + 127) / 128;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(smem_u32(&bar_q), 1);
-#pragma unroll
-    for (int s = 0; s < F3_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(smem_u32(&bar_s[i]), 1);
-      mbar_init(smem_u32(&bar_p[i]), 256);
-    }
-    mbar_init(smem_u32(&bar_pv[0]), 1);
-    mbar_init(smem_u32(&bar_pv[1]), 1);
-    mbar_init(smem_u32(&bar_o), 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = uniform_u32(tmem_slot);
-  pdl_wait();
-  pdl_launch_dependents();
-
-  if (warp == 0) {
-    const bool el = elect_one();
-    if (el) {
-      mbar_expect_tx(smem_u32(&bar_q), AT_TILE128);
-      tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
-    }
-    int s = 0;
-    uint32_t ph = 0;
-    for (int j = 0; j < nkb; ++j) {
-      mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-      const uint32_t full = smem_u32(&bar_full[s]);
-      if (el) {
-        mbar_expect_tx(full, 2 * AT_TILE128);
-        tma_load_4d(sKV + s * 2 * AT_TILE128, &tmK, full, 0, j * 128, h, b);
-        tma_load_4d(sKV + s * 2 * AT_TILE128 + AT_TILE128, &tmV, full, 0, j * 128, h, b);
-      }
-      if (++s == F3_STAGES) { s = 0; ph ^= 1u; }
-    }
-  } else if (warp == 1) {
-    const bool el = elect_one();
-    constexpr uint32_t idS = umma_idesc(128, 128, 0, 0);
-    constexpr uint32_t idO = umma_idesc(128, AT_D, 0, 1);
-    auto issue_S = [&](int buf, int stage) {
-      const uint32_t tS = tmem_base + buf * 128, sK = sKV + stage * 2 * AT_TILE128;
-#pragma unroll
-      for (int k = 0; k < AT_D / 16; ++k)
-        umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
-    };
-    mbar_wait(smem_u32(&bar_q), 0);
-    int ls = 0, issued = 0;
-    uint32_t lph = 0;
-    for (; issued < 3 && issued < nkb; ++issued) {
-      mbar_wait(smem_u32(&bar_full[ls]), lph);
-      tc_fence_after();
-      if (el) issue_S(issued, ls);
-      if (el) umma_commit(smem_u32(&bar_s[issued]));
-      if (++ls == F3_STAGES) { ls = 0; lph ^= 1u; }
-    }
-    int buf = 0, cs = 0;
-    uint32_t ppar = 0;
-    for (int j = 0; j < nkb; ++j) {
-      const int g = j & 1;
-      mbar_wait(smem_u32(&bar_p[buf]), ppar);
-      tc_fence_after();
-      const uint32_t tP = tmem_base + buf * 128, tO = tmem_base + 384 + g * 64;
-      const uint32_t sV = sKV + cs * 2 * AT_TILE128 + AT_TILE128;
-      if (el) {
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k)
-          umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (j >= 2) || k != 0);
-      }
-      if (el) umma_commit(smem_u32(&bar_pv[g]));
-      if (el) umma_commit(smem_u32(&bar_empty[cs]));
-      if (issued < nkb) {
-        mbar_wait(smem_u32(&bar_full[ls]), lph);
-        tc_fence_after();
-        if (el) issue_S(buf, ls);
-        if (el) umma_commit(smem_u32(&bar_s[buf]));
-        if (++ls == F3_STAGES) { ls = 0; lph ^= 1u; }
-        ++issued;
-      }
-      if (++cs == F3_STAGES) cs = 0;
-      if (++buf == 3) { buf = 0; ppar ^= 1u; }
-    }
-    if (el) umma_commit(smem_u32(&bar_o));
-  } else {
-    const int idx = warp - 2;
-    const int g = idx >> 3;          // group: alternate key blocks
-    const int hf = (idx >> 2) & 1;   // half of the block's 128 key columns
-    const int qd = warp & 3;         // TMEM lane quadrant this warp may touch
-    const int row = qd * 32 + lane;
-    const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    const uint32_t tOh = tmem_base + 384 + g * 64 + hf * 32 + lane_off;  // my half of the group's O accumulator
-    float m_used = -INFINITY, l = 0.f;
-    int buf = g;
-    uint32_t spar = 0;
-    int kown = 0;
-    for (int j = g; j < nkb; j += 2, ++kown) {
-      mbar_wait(smem_u32(&bar_s[buf]), spar);
-      tc_fence_after();
-      const uint32_t tS = tmem_base + buf * 128 + lane_off;
-      uint32_t r[64];
-      tmem_ld32_nowait(tS + hf * 64, r);
-      tmem_ld32_nowait(tS + hf * 64 + 32, r + 32);
-      tmem_ld_wait();
-      const int valid = min(128, p.n_k - j * 128) - hf * 64;  // valid key columns in my half (may be <= 0)
-      if (valid < 64) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= valid) r[i] = 0xff800000u;
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(r[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
-      }
-      const float mxh = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.c;
-      xmax[kown & 1][g][hf][row] = mxh;
-      a4_group_sync(g);  // partner's maximum is visible; BOTH halves have read their S columns (P may now overwrite them)
-      const float mx = fmaxf(mxh, xmax[kown & 1][g][hf ^ 1][row]);
-      float factor = 1.f;
-      if (kown == 0) {
-        m_used = mx;
-      } else if (mx > m_used + 8.f) {  // lazy rescale, same decision in both halves (same mx, same m_used)
-        factor = fast_exp2(m_used - mx);
-        m_used = mx;
-      }
-      if (kown > 0 && __any_sync(AT_FULL, factor != 1.f)) {
-        mbar_wait(smem_u32(&bar_pv[g]), (uint32_t)(kown - 1) & 1u);
-        tc_fence_after();
-        uint32_t o[32];
-        tmem_ld32(tOh, o);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-        tmem_st32(tOh, o);
-        l *= factor;
-      }
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i]), p.c, -m_used));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 1]), p.c, -m_used));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 2]), p.c, -m_used));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 3]), p.c, -m_used));
-          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-          pk[i] = pack_bf16x2(p0, p1);
-          pk[i + 1] = pack_bf16x2(p2, p3);
-        }
-        tmem_st16(tS + hf * 32 + cc * 16, pk);  // bf16 P of keys [64 hf + 32 cc, +32) -> P columns [32 hf + 16 cc, +16)
-      }
-      l += (l0 + l1) + (l2 + l3);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bar_p[buf]));
-      buf += 2;
-      if (buf >= 3) { buf -= 3; spar ^= 1u; }
-    }
-    // ---- merge: two groups (split-KV combine) x two halves (partial row sums); 16 output columns per (group, half)
-    if (hf == 0) m_fin[g][row] = m_used;
-    l_fin[g][hf][row] = l;
-    mbar_wait(smem_u32(&bar_o), 0);
-    tc_fence_after();
-    a4_all_sync();
-    const bool has1 = nkb > 1;
-    const float ma = m_fin[0][row], mb = m_fin[1][row];
-    const float la = l_fin[0][0][row] + l_fin[0][1][row], lb = l_fin[1][0][row] + l_fin[1][1][row];
-    const float m = has1 ? fmaxf(ma, mb) : ma;
-    const float w0 = fast_exp2(ma - m), w1 = has1 ? fast_exp2(mb - m) : 0.f;
-    const float lt = la * w0 + lb * w1;
-    const float inv = 1.f / lt;
-    const int c0 = (g * 2 + hf) * 16;
-    const uint32_t tO0 = tmem_base + 384 + c0 + lane_off, tO1 = tO0 + 64;
-    uint32_t a[16], c[16];
-    float f[16];
-    tmem_ld16_nowait(tO0, a);
-    if (has1) tmem_ld16_nowait(tO1, c);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      f[i] = (__uint_as_float(a[i]) * w0 + (has1 ? __uint_as_float(c[i]) * w1 : 0.f)) * inv;
-    const int gq = q0 + row;
-    if (gq < p.n_q) {
-      bf16* dst = p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + c0;
-      st8(dst, pack8(f));
-      st8(dst + 8, pack8(f + 8));
-    }
-    if (g == 0 && hf == 0 && gq < p.n_pad)
-      p.LSE[((long long)b * p.H + h) * p.n_pad + gq] = gq < p.n_q ? m + log2f(lt) : INFINITY;
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, A3_TMEM_COLS);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward, PERSISTENT (EXPERIMENTAL, opt-in with B2_ATTN_PFWD=1 until it has been measured): the v3 pipeline with the
-// query tile as an outer loop inside the CTA, the way attn_xfwd_kernel already works for cross-attention.
-//   Why: inside the key-block loop v3 runs at 75 % of its ex2 bound, but 26 % (n = 4096) to 53 % (n = 1024, 60 of the 70
-//   self-attention layers) of the kernel time is per-CTA set-up and tear-down — TMEM allocation, barrier initialisation,
-//   descriptor prefetch, the first TMA round trip, the two-group merge, the O store, TMEM release, the next CTA's launch
-//   (profiles/r1_attention_notes.md).  Here one CTA per SM walks a contiguous range of (sample, head, query-tile) items:
-//   every barrier and ring keeps running across tiles (global block counter G: S ring slot G % 3, K/V stage G % 5), Q is
-//   double-buffered, and the MMA warp's S-issue cursor runs up to three blocks ahead ACROSS tile boundaries, so the next
-//   tile's loads, S MMAs and first softmax blocks overlap the current tile's merge and store.  O has no second buffer
-//   (TMEM is full: 3 x 128 + 2 x 64 columns), so the first PV of a tile waits until the previous tile's merge has read it.
-// warps (320 threads): 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = group 0, 6..9 = group 1 (as v3).
-// ---------------------------------------------------------------------------------------------
-constexpr int PF_SMEM = 2 * AT_TILE128 + F3_STAGES * 2 * AT_TILE128 + 1024;
-
-__global__ void __launch_bounds__(A3_THREADS, 1)
-attn_pfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const AttnP p, int nqt, int total_tiles) {
+// RAGGED: n_k is not a multiple of 128 (aspect buckets: 576, 1200, ... keys) — the last key block's out-of-range columns are
+// masked to -inf.  Compiled out for the multiple-of-128 case (every 1024^2 shape): the masking made ptxas copy and spill a
+// quarter of the logits row in BOTH paths.
+template <bool RAGGED>
+__global__ void __launch_bounds__(P2_THREADS, 1)
+attn_pfwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnP p, int nqt, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_q[2], bar_qfree[2], bar_full[F3_STAGES], bar_empty[F3_STAGES], bar_s[3], bar_p[3],
-      bar_pv[2], bar_o, bar_ofree;
+      bar_o, bar_ofree;
   __shared__ uint32_t tmem_slot;
   __shared__ float2 ml[2][2][128];  // [tile parity][group][row]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -622,7 +387,7 @@ attn_pfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int ntiles = t_end - t_begin;
   const int nkb = (p.n_k + 127) / 128;
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 256) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -630,7 +395,6 @@ attn_pfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_q[i]), 1);
       mbar_init(smem_u32(&bar_qfree[i]), 1);
-      mbar_init(smem_u32(&bar_pv[i]), 1);
     }
 #pragma unroll
     for (int s = 0; s < F3_STAGES; ++s) {
@@ -646,7 +410,7 @@ attn_pfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(smem_u32(&bar_ofree), 256);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
+  if (warp == 9) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -654,105 +418,145 @@ attn_pfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   pdl_wait();
   pdl_launch_dependents();
 
-  if (warp == 0) {
-    // ---------------- TMA producer: Q(t), then the K/V blocks of tile t, for every tile of this CTA
-    const bool el = elect_one();
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tl = 0; tl < ntiles; ++tl) {
-      const int gt = t_begin + tl;
-      const int qt = gt % nqt, bh = gt / nqt;
-      const int h = bh % p.H, b = bh / p.H;
-      const int qb = tl & 1;
-      if (tl >= 2) mbar_wait(smem_u32(&bar_qfree[qb]), (uint32_t)((tl >> 1) - 1) & 1u);  // S MMAs of tile tl-2 are done
-      if (el) {
-        mbar_expect_tx(smem_u32(&bar_q[qb]), AT_TILE128);
-        tma_load_4d(sQ0 + qb * AT_TILE128, &tmQ, smem_u32(&bar_q[qb]), 0, qt * 128, h, b);
-      }
-      for (int j = 0; j < nkb; ++j) {
-        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-        const uint32_t full = smem_u32(&bar_full[s]);
+  if (warp >= 8) {
+    setmaxnreg_dec<56>();
+    if (warp == 8) {
+      // ---------------- TMA producer: Q(t), then the K/V blocks of tile t, for every tile of this CTA
+      const bool el = elect_one();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tl = 0; tl < ntiles; ++tl) {
+        const int gt = t_begin + tl;
+        const int qt = gt % nqt, bh = gt / nqt;
+        const int h = bh % p.H, b = bh / p.H;
+        const int qb = tl & 1;
+        if (tl >= 2) mbar_wait(smem_u32(&bar_qfree[qb]), (uint32_t)((tl >> 1) - 1) & 1u);  // S MMAs of tile tl-2 are done
         if (el) {
-          mbar_expect_tx(full, 2 * AT_TILE128);
-          tma_load_4d(sKV + s * 2 * AT_TILE128, &tmK, full, 0, j * 128, h, b);
-          tma_load_4d(sKV + s * 2 * AT_TILE128 + AT_TILE128, &tmV, full, 0, j * 128, h, b);
+          mbar_expect_tx(smem_u32(&bar_q[qb]), AT_TILE128);
+          tma_load_4d(sQ0 + qb * AT_TILE128, &tmQ, smem_u32(&bar_q[qb]), 0, qt * 128, h, b);
         }
-        if (++s == F3_STAGES) { s = 0; ph ^= 1u; }
+        for (int j = 0; j < nkb; ++j) {
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[s]);
+          if (el) {
+            mbar_expect_tx(full, 2 * AT_TILE128);
+            tma_load_4d(sKV + s * 2 * AT_TILE128, &tmK, full, 0, j * 128, h, b);
+            tma_load_4d(sKV + s * 2 * AT_TILE128 + AT_TILE128, &tmV, full, 0, j * 128, h, b);
+          }
+          if (++s == F3_STAGES) { s = 0; ph ^= 1u; }
+        }
       }
-    }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer: PV cursor (tile tl, block j, global block G) and an S cursor up to three blocks ahead
-    const bool el = elect_one();
-    constexpr uint32_t idS = umma_idesc(128, 128, 0, 0);
-    constexpr uint32_t idO = umma_idesc(128, AT_D, 0, 1);
-    int s_tl = 0, s_j = 0;   // S cursor: tile, block within the tile
-    int s_stage = 0;         // K/V stage of the S cursor's block (= global block index % F3_STAGES)
-    uint32_t s_sph = 0;      // parity of bar_full[s_stage] for that block
-    int s_buf = 0;           // S ring slot of the S cursor's block (= global block index % 3)
-    auto issue_next_S = [&]() {
-      if (s_tl >= ntiles) return;
-      const int qb = s_tl & 1;
-      if (s_j == 0) mbar_wait(smem_u32(&bar_q[qb]), (uint32_t)(s_tl >> 1) & 1u);
-      mbar_wait(smem_u32(&bar_full[s_stage]), s_sph);
-      tc_fence_after();
-      const uint32_t tS = tmem_base + s_buf * 128, sQ = sQ0 + qb * AT_TILE128, sK = sKV + s_stage * 2 * AT_TILE128;
-      if (el) {
+    } else if (warp == 9) {
+      // ---------------- MMA issuer: PV cursor (tile tl, block j) and an S cursor up to three blocks ahead
+      const bool el = elect_one();
+      constexpr uint32_t idS = umma_idesc(128, 128, 0, 0);
+      constexpr uint32_t idO = umma_idesc(128, AT_D, 0, 1);
+      constexpr uint32_t STAGE_B = 2 * AT_TILE128;
+      const uint64_t dQ = umma_desc(sQ0, 16, 1024);                    // + qb * TILE128; k-step + 32 B
+      const uint64_t dK = umma_desc(sKV, 16, 1024);                    // + stage * STAGE_B; k-step + 32 B
+      const uint64_t dV = umma_desc(sKV + AT_TILE128, 16384, 1024);    // + stage * STAGE_B; k-step + 2048 B
+      int s_tl = 0, s_j = 0;   // S cursor: tile, block within the tile
+      int s_stage = 0;         // K/V stage of the S cursor's block (= global block index % F3_STAGES)
+      uint32_t s_sph = 0;      // parity of bar_full[s_stage] for that block
+      int s_buf = 0;           // S ring slot of the S cursor's block (= global block index % 3)
+      // the waits an S issue needs (its tile's Q, its K/V stage); both complete long before they are needed in steady state
+      auto wait_next_S = [&]() {
+        if (s_tl >= ntiles) return;
+        if (s_j == 0) mbar_wait(smem_u32(&bar_q[s_tl & 1]), (uint32_t)(s_tl >> 1) & 1u);
+        mbar_wait(smem_u32(&bar_full[s_stage]), s_sph);
+      };
+      auto issue_next_S = [&]() {
+        if (s_tl >= ntiles) return;
+        const int qb = s_tl & 1;
+        const uint32_t tS = tmem_base + s_buf * 128;
+        const uint64_t dq = desc_adv(dQ, qb * AT_TILE128), dk = desc_adv(dK, s_stage * STAGE_B);
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
-        umma_commit(smem_u32(&bar_s[s_buf]));
-      }
-      if (++s_stage == F3_STAGES) { s_stage = 0; s_sph ^= 1u; }
-      if (++s_buf == 3) s_buf = 0;
-      if (++s_j == nkb) {
-        if (el) umma_commit(smem_u32(&bar_qfree[qb]));  // this tile's Q buffer may be reloaded once its S MMAs completed
-        s_j = 0;
-        ++s_tl;
-      }
-    };
-    issue_next_S();
-    issue_next_S();
-    issue_next_S();
-    int buf = 0, cs = 0;   // ring slot / K/V stage of the PV cursor's block
-    uint32_t ppar = 0;     // parity of bar_p[buf] for that block
-    for (int tl = 0; tl < ntiles; ++tl) {
-      for (int j = 0; j < nkb; ++j) {
-        const int g = j & 1;
-        mbar_wait(smem_u32(&bar_p[buf]), ppar);
-        if (j == 0 && tl > 0) mbar_wait(smem_u32(&bar_ofree), (uint32_t)(tl - 1) & 1u);  // previous tile's merge has read O
+          for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tS, desc_adv(dq, k * 32), desc_adv(dk, k * 32), idS, k != 0);
+          umma_commit(smem_u32(&bar_s[s_buf]));
+        }
+        if (++s_stage == F3_STAGES) { s_stage = 0; s_sph ^= 1u; }
+        if (++s_buf == 3) s_buf = 0;
+        if (++s_j == nkb) {
+          if (el) umma_commit(smem_u32(&bar_qfree[qb]));  // this tile's Q buffer may be reloaded once its S MMAs completed
+          s_j = 0;
+          ++s_tl;
+        }
+      };
+      for (int i = 0; i < 3; ++i) {
+        wait_next_S();
         tc_fence_after();
-        const uint32_t tP = tmem_base + buf * 128, tO = tmem_base + 384 + g * 64;
-        const uint32_t sV = sKV + cs * 2 * AT_TILE128 + AT_TILE128;
-        if (el) {
+        issue_next_S();
+      }
+      int buf = 0, cs = 0;   // ring slot / K/V stage of the PV cursor's block
+      uint32_t ppar = 0;     // parity of bar_p[buf] for that block
+      for (int tl = 0; tl < ntiles; ++tl) {
+        for (int j = 0; j < nkb; ++j) {
+          const int g = j & 1;
+          wait_next_S();  // off the critical path: taken while the softmax warps are still working on this block's P
+          mbar_wait(smem_u32(&bar_p[buf]), ppar);
+          if (j == 0 && tl > 0) mbar_wait(smem_u32(&bar_ofree), (uint32_t)(tl - 1) & 1u);  // previous tile's merge has read O
+          tc_fence_after();
+          const uint32_t tP = tmem_base + buf * 128, tO = tmem_base + 384 + g * 64;
+          const uint64_t dv = desc_adv(dV, cs * STAGE_B);
+          if (el) {
 #pragma unroll
-          for (int k = 0; k < 128 / 16; ++k)
-            umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, (j >= 2) || k != 0);
-          umma_commit(smem_u32(&bar_pv[g]));
-          umma_commit(smem_u32(&bar_empty[cs]));
-          if (j == nkb - 1) umma_commit(smem_u32(&bar_o));  // every PV of this tile has been issued
+            for (int k = 0; k < 128 / 16; ++k) umma_bf16_ts(tO, tP + k * 8, desc_adv(dv, k * 2048), idO, (j >= 2) || k != 0);
+            umma_commit(smem_u32(&bar_empty[cs]));  // K/V stage free; also "PV of this block done" for the lazy rescale
+            if (j == nkb - 1) umma_commit(smem_u32(&bar_o));  // every PV of this tile has been issued
+          }
+          issue_next_S();  // refills ring slot `buf` (global block + 3), possibly with a block of the NEXT tile
+          if (++cs == F3_STAGES) cs = 0;
+          if (++buf == 3) { buf = 0; ppar ^= 1u; }
         }
-        issue_next_S();  // refills ring slot `buf` (global block + 3), possibly with a block of the NEXT tile
-        if (++cs == F3_STAGES) cs = 0;
-        if (++buf == 3) { buf = 0; ppar ^= 1u; }
       }
     }
   } else {
+    setmaxnreg_inc<224>();
     // ---------------- softmax groups
-    const int g = (warp - 2) >> 2;
+    const int g = warp >> 2;
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_off = uint32_t(qd * 32) << 16;
     const uint32_t tOg = tmem_base + 384 + g * 64 + lane_off;
-    int gbase = 0;   // global index of the current tile's first block
-    int pvc = 0;     // own blocks finished so far (over all tiles) = PV commits this group has caused on bar_pv[g]
-    for (int tl = 0; tl < ntiles; ++tl, gbase += nkb) {
+    const bool has1 = nkb > 1;
+    // merge of tile `tl` (whose partial state this thread saved as m_t, l_t): O = (w0 O_0 + w1 O_1) / (w0 l_0 + w1 l_1),
+    // 32 output columns per group; hands the O accumulators back to the MMA thread as soon as they are in registers
+    auto merge_tile = [&](int tl, float m_t, float l_t) {
       const int gt = t_begin + tl;
       const int qt = gt % nqt, bh = gt / nqt;
       const int h = bh % p.H, b = bh / p.H;
-      const int q0 = qt * 128;
+      ml[tl & 1][g][row] = make_float2(m_t, l_t);
+      mbar_wait(smem_u32(&bar_o), (uint32_t)tl & 1u);
+      tc_fence_after();
+      p2_groups_sync();
+      const float2 s0 = ml[tl & 1][0][row], s1 = ml[tl & 1][1][row];
+      const float m = has1 ? fmaxf(s0.x, s1.x) : s0.x;
+      const float w0 = fast_exp2(s0.x - m), w1 = has1 ? fast_exp2(s1.x - m) : 0.f;
+      const float lt = s0.y * w0 + s1.y * w1;
+      const float inv = 1.f / lt;
+      const uint32_t tO0 = tmem_base + 384 + g * 32 + lane_off, tO1 = tO0 + 64;
+      uint32_t a[32], c[32];
+      float f[32];
+      tmem_ld32_nowait(tO0, a);
+      if (has1) tmem_ld32_nowait(tO1, c);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_ofree));  // the MMA warp may start the next tile's PV into O_0 / O_1
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        f[i] = (__uint_as_float(a[i]) * w0 + (has1 ? __uint_as_float(c[i]) * w1 : 0.f)) * inv;
+      const int gq = qt * 128 + row;
+      if (gq < p.n_q) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + g * 32, f);
+      if (g == 0 && gq < p.n_pad) p.LSE[((long long)b * p.H + h) * p.n_pad + gq] = gq < p.n_q ? m + log2f(lt) : INFINITY;
+    };
+    int gbase = 0;   // global index of the current tile's first block
+    float m_prev = 0.f, l_prev = 0.f;
+    for (int tl = 0; tl < ntiles; ++tl, gbase += nkb) {
       float m_used = -INFINITY, l = 0.f;
       int kown = 0;
-      for (int j = g; j < nkb; j += 2, ++kown, ++pvc) {
+      bool merged_prev = tl == 0;
+      for (int j = g; j < nkb; j += 2, ++kown) {
         const int G = gbase + j;
         const int buf = G % 3;
         const uint32_t spar = (uint32_t)(G / 3) & 1u;
@@ -766,7 +570,7 @@ attn_pfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld32_nowait(tS + 64, r + 64);
         tmem_ld32_nowait(tS + 96, r + 96);
         tmem_ld_wait();
-        if (valid < 128) {
+        if (RAGGED && valid < 128) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
             if (i >= valid) r[i] = 0xff800000u;
@@ -783,13 +587,17 @@ attn_pfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         float factor = 1.f;
         if (kown == 0) {
           m_used = mx;
-        } else if (mx > m_used + 8.f) {
+        } else if (mx > m_used + 8.f) {  // lazy rescale: a stale max is fine while 2^(s - m) <= 2^8
           factor = fast_exp2(m_used - mx);
           m_used = mx;
         }
         if (kown > 0 && __any_sync(AT_FULL, factor != 1.f)) {
-          // the PV of this group's previous block (commit number pvc, 1-based, on bar_pv[g]) must have completed
-          mbar_wait(smem_u32(&bar_pv[g]), (uint32_t)(pvc - 1) & 1u);
+          // O_g is being accumulated by the PV of this group's previous block (global index G - 2): its completion is what
+          // frees that block's K/V stage.  (That PV was issued after bar_ofree of the previous tile, so the merge — which
+          // reads both groups' accumulators — is over too; no later completion of the same barrier can have happened:
+          // PV(G + 3) is issued after PV(G), which needs this block's P.)
+          const int Gp = G - 2;
+          mbar_wait(smem_u32(&bar_empty[Gp % F3_STAGES]), (uint32_t)(Gp / F3_STAGES) & 1u);
           tc_fence_after();
 #pragma unroll 1
           for (int cc = 0; cc < 2; ++cc) {
@@ -815,48 +623,32 @@ attn_pfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             pk[i] = pack_bf16x2(p0, p1);
             pk[i + 1] = pack_bf16x2(p2, p3);
           }
-          tmem_st16(tS + cc * 16, pk);
+          tmem_st16(tS + cc * 16, pk);  // in place: this thread's row was read out completely above
         }
         l += (l0 + l1) + (l2 + l3);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(smem_u32(&bar_p[buf]));
+        if (!merged_prev) {  // deferred merge of the previous tile, behind this tile's first block
+          merge_tile(tl - 1, m_prev, l_prev);
+          merged_prev = true;
+        }
       }
-      // ---- merge the two groups' partial results of this tile, 32 output columns per group
-      ml[tl & 1][g][row] = make_float2(m_used, l);
-      mbar_wait(smem_u32(&bar_o), (uint32_t)tl & 1u);
-      tc_fence_after();
-      a3_group_sync();
-      const float2 s0 = ml[tl & 1][0][row], s1 = ml[tl & 1][1][row];
-      const bool has1 = nkb > 1;
-      const float m = has1 ? fmaxf(s0.x, s1.x) : s0.x;
-      const float w0 = fast_exp2(s0.x - m), w1 = has1 ? fast_exp2(s1.x - m) : 0.f;
-      const float lt = s0.y * w0 + s1.y * w1;
-      const float inv = 1.f / lt;
-      const uint32_t tO0 = tmem_base + 384 + g * 32 + lane_off, tO1 = tO0 + 64;
-      uint32_t a[32], c[32];
-      float f[32];
-      tmem_ld32_nowait(tO0, a);
-      if (has1) tmem_ld32_nowait(tO1, c);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bar_ofree));  // the MMA warp may start the next tile's PV into O_0 / O_1
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        f[i] = (__uint_as_float(a[i]) * w0 + (has1 ? __uint_as_float(c[i]) * w1 : 0.f)) * inv;
-      const int gq = q0 + row;
-      if (gq < p.n_q) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + g * 32, f);
-      if (g == 0 && gq < p.n_pad) p.LSE[((long long)b * p.H + h) * p.n_pad + gq] = gq < p.n_q ? m + log2f(lt) : INFINITY;
+      if (!merged_prev) merge_tile(tl - 1, m_prev, l_prev);  // this group has no block in the tile (one key block, group 1)
+      m_prev = m_used;
+      l_prev = l;
     }
+    if (ntiles > 0) merge_tile(ntiles - 1, m_prev, l_prev);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, A3_TMEM_COLS);
   }
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // backward, part 0: D[i] = sum_d dO[i,d] * O[i,d]   (8 lanes per (row, head))
@@ -968,11 +760,14 @@ attn_xfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t idS = umma_idesc(128, nkp, 0, 0);
     constexpr uint32_t idO = umma_idesc(128, AT_D, 0, 1);
     const int ksteps = nkp >> 4;
+    // descriptors built once, advanced with one add per MMA (tc.cuh desc_adv)
+    const uint64_t dQ = umma_desc(smem_base, 16, 1024), dK = umma_desc(smem_base + AT_TILE128, 16, 1024);
+    const uint64_t dV = umma_desc(smem_base + AT_TILE128 + X_KV_BYTES, 16384, 1024);
     auto issue_S = [&](int buf, int stage) {
-      const uint32_t tS = tmem_base + buf * 128, sQ = smem_base + stage * X_STAGE_BYTES, sK = sQ + AT_TILE128;
+      const uint32_t tS = tmem_base + buf * 128;
+      const uint64_t dq = desc_adv(dQ, stage * X_STAGE_BYTES), dk = desc_adv(dK, stage * X_STAGE_BYTES);
 #pragma unroll
-      for (int k = 0; k < AT_D / 16; ++k)
-        umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
+      for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tS, desc_adv(dq, k * 32), desc_adv(dk, k * 32), idS, k != 0);
     };
     int ls = 0, issued = 0;
     uint32_t lph = 0;
@@ -987,20 +782,18 @@ attn_xfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint32_t ppar = 0;
     for (int i = 0; i < ntiles; ++i) {
       const int g = i & 1, kown = i >> 1;
+      if (issued < ntiles) mbar_wait(smem_u32(&bar_full[ls]), lph);  // stage of the S issued below: off the critical path
       mbar_wait(smem_u32(&bar_p[buf]), ppar);
       if (kown > 0) mbar_wait(smem_u32(&bar_ofree[g]), (uint32_t)(kown - 1) & 1u);  // group g drained O_g of its last tile
       tc_fence_after();
       const uint32_t tP = tmem_base + buf * 128, tO = tmem_base + 384 + g * 64;
-      const uint32_t sV = smem_base + cs * X_STAGE_BYTES + AT_TILE128 + X_KV_BYTES;
+      const uint64_t dv = desc_adv(dV, cs * X_STAGE_BYTES);
       if (el) {
-        for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ts(tO, tP + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idO, k != 0);
+        for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tO, tP + k * 8, desc_adv(dv, k * 2048), idO, k != 0);
         umma_commit(smem_u32(&bar_o[g]));
         umma_commit(smem_u32(&bar_empty[cs]));
       }
       if (issued < ntiles) {
-        mbar_wait(smem_u32(&bar_full[ls]), lph);
-        tc_fence_after();
         if (el) issue_S(buf, ls);
         if (el) umma_commit(smem_u32(&bar_s[buf]));
         if (++ls == X_STAGES) { ls = 0; lph ^= 1u; }
@@ -1159,15 +952,18 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     {
       constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
       constexpr uint32_t idQ = umma_idesc(128, AT_D, 0, 1);
+      constexpr uint32_t STAGE_B = 2 * AT_TILE64;
+      // descriptors are built once and advanced with one add per MMA (tc.cuh desc_adv): this thread's issue rate bounds the kernel
+      const uint64_t dQd = umma_desc(sQ, 16, 1024), ddO = umma_desc(sdO, 16, 1024);            // A of S / dP (K-major)
+      const uint64_t dKk = umma_desc(sKV, 16, 1024), dVk = umma_desc(sKV + AT_TILE64, 16, 1024);  // B of S / dP (K-major)
+      const uint64_t dKm = umma_desc(sKV, 8192, 1024);                                          // B of dQ += dS K (MN-major)
       auto issue_SdP = [&](int buf, int stage) {
         const uint32_t tS = tmem_base + buf * 128, tdP = tS + 64;
-        const uint32_t sK = sKV + stage * 2 * AT_TILE64, sV = sK + AT_TILE64;
+        const uint64_t dk = desc_adv(dKk, stage * STAGE_B), dv = desc_adv(dVk, stage * STAGE_B);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
+        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tS, desc_adv(dQd, k * 32), desc_adv(dk, k * 32), idS, k != 0);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tdP, umma_desc(sdO + k * 32, 16, 1024), umma_desc(sV + k * 32, 16, 1024), idS, k != 0);
+        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tdP, desc_adv(ddO, k * 32), desc_adv(dv, k * 32), idS, k != 0);
       };
       mbar_wait(smem_u32(&bar_q), 0);
       int ls = 0, issued = 0;
@@ -1183,19 +979,17 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t ppar = 0;
       const uint32_t tdQ = tmem_base + 384;
       for (int j = 0; j < nkb; ++j) {
+        if (issued < nkb) mbar_wait(smem_u32(&bar_full[ls]), lph);  // K/V of the S / dP issued below: off the critical path
         mbar_wait(smem_u32(&bar_p[buf]), ppar);
         tc_fence_after();
         const uint32_t tdS = tmem_base + buf * 128;
-        const uint32_t sK = sKV + cs * 2 * AT_TILE64;
+        const uint64_t dk = desc_adv(dKm, cs * STAGE_B);
         if (el) {
 #pragma unroll
-          for (int k = 0; k < 64 / 16; ++k)
-            umma_bf16_ts(tdQ, tdS + k * 8, umma_desc(sK + k * 2048, 8192, 1024), idQ, (j | k) != 0);
+          for (int k = 0; k < 64 / 16; ++k) umma_bf16_ts(tdQ, tdS + k * 8, desc_adv(dk, k * 2048), idQ, (j | k) != 0);
+          umma_commit(smem_u32(&bar_empty[cs]));
         }
-        if (el) umma_commit(smem_u32(&bar_empty[cs]));
         if (issued < nkb) {
-          mbar_wait(smem_u32(&bar_full[ls]), lph);
-          tc_fence_after();
           if (el) issue_SdP(buf, ls);
           if (el) umma_commit(smem_u32(&bar_s[buf]));
           if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
@@ -1259,217 +1053,6 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(a[i]) * p.scale;
     if (gq < p.n_q) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + g * 32, f);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, A3_TMEM_COLS);
-  }
-}
-
-// backward dQ, PERSISTENT (EXPERIMENTAL, opt-in with B2_ATTN_PBWD=1, never run on a GPU yet): attn_bwd_dq3_kernel with the
-// query tile as an outer loop inside the CTA — the same transformation, for the same reason, as attn_pfwd_kernel: per-CTA
-// set-up / tear-down is a large share of these kernels at n = 1024 (8-16 key blocks per CTA).  {Q, dO} double-buffered,
-// S / dP ring, K/V stages and all barriers keep running across tiles (global block counter), the S/dP issue cursor runs
-// up to three blocks ahead across tile boundaries; the single dQ accumulator is handed back by the softmax warps
-// (bar_ofree, 256 arrivals) before the next tile's first dQ MMA overwrites it.
-constexpr int PQ_SMEM = 4 * AT_TILE128 + Q3_STAGES * 2 * AT_TILE64 + 1024;
-
-__global__ void __launch_bounds__(A3_THREADS, 1)
-attn_pbwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnP p, int nqt,
-                    int total_tiles) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q[2], bar_qfree[2], bar_full[Q3_STAGES], bar_empty[Q3_STAGES], bar_s[3], bar_p[3], bar_o,
-      bar_ofree;
-  __shared__ uint32_t tmem_slot;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQdO = smem_base;                    // buffer qb: Q at +qb*2*TILE128, dO right after it
-  const uint32_t sKV = smem_base + 4 * AT_TILE128;
-  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const int t_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
-  const int t_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
-  const int ntiles = t_end - t_begin;
-  const int nkb = (p.n_k + 63) / 64;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmdO);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bar_q[i]), 1);
-      mbar_init(smem_u32(&bar_qfree[i]), 1);
-    }
-#pragma unroll
-    for (int s = 0; s < Q3_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(smem_u32(&bar_s[i]), 1);
-      mbar_init(smem_u32(&bar_p[i]), 128);
-    }
-    mbar_init(smem_u32(&bar_o), 1);
-    mbar_init(smem_u32(&bar_ofree), 256);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = uniform_u32(tmem_slot);
-  pdl_wait();
-  pdl_launch_dependents();
-
-  if (warp == 0) {
-    const bool el = elect_one();
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tl = 0; tl < ntiles; ++tl) {
-      const int gt = t_begin + tl;
-      const int qt = gt % nqt, bh = gt / nqt;
-      const int h = bh % p.H, b = bh / p.H;
-      const int qb = tl & 1;
-      if (tl >= 2) mbar_wait(smem_u32(&bar_qfree[qb]), (uint32_t)((tl >> 1) - 1) & 1u);
-      if (el) {
-        const uint32_t dst = sQdO + qb * 2 * AT_TILE128;
-        mbar_expect_tx(smem_u32(&bar_q[qb]), 2 * AT_TILE128);
-        tma_load_4d(dst, &tmQ, smem_u32(&bar_q[qb]), 0, qt * 128, h, b);
-        tma_load_4d(dst + AT_TILE128, &tmdO, smem_u32(&bar_q[qb]), 0, qt * 128, h, b);
-      }
-      for (int j = 0; j < nkb; ++j) {
-        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-        const uint32_t full = smem_u32(&bar_full[s]);
-        if (el) {
-          mbar_expect_tx(full, 2 * AT_TILE64);
-          tma_load_4d(sKV + s * 2 * AT_TILE64, &tmK, full, 0, j * 64, h, b);
-          tma_load_4d(sKV + s * 2 * AT_TILE64 + AT_TILE64, &tmV, full, 0, j * 64, h, b);
-        }
-        if (++s == Q3_STAGES) { s = 0; ph ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    const bool el = elect_one();
-    constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
-    constexpr uint32_t idQ = umma_idesc(128, AT_D, 0, 1);
-    int s_tl = 0, s_j = 0, s_stage = 0, s_buf = 0;
-    uint32_t s_sph = 0;
-    auto issue_next_SdP = [&]() {
-      if (s_tl >= ntiles) return;
-      const int qb = s_tl & 1;
-      if (s_j == 0) mbar_wait(smem_u32(&bar_q[qb]), (uint32_t)(s_tl >> 1) & 1u);
-      mbar_wait(smem_u32(&bar_full[s_stage]), s_sph);
-      tc_fence_after();
-      const uint32_t tS = tmem_base + s_buf * 128, tdP = tS + 64;
-      const uint32_t sQ = sQdO + qb * 2 * AT_TILE128, sdO = sQ + AT_TILE128;
-      const uint32_t sK = sKV + s_stage * 2 * AT_TILE64, sV = sK + AT_TILE64;
-      if (el) {
-#pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idS, k != 0);
-#pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tdP, umma_desc(sdO + k * 32, 16, 1024), umma_desc(sV + k * 32, 16, 1024), idS, k != 0);
-        umma_commit(smem_u32(&bar_s[s_buf]));
-      }
-      if (++s_stage == Q3_STAGES) { s_stage = 0; s_sph ^= 1u; }
-      if (++s_buf == 3) s_buf = 0;
-      if (++s_j == nkb) {
-        if (el) umma_commit(smem_u32(&bar_qfree[qb]));
-        s_j = 0;
-        ++s_tl;
-      }
-    };
-    issue_next_SdP();
-    issue_next_SdP();
-    issue_next_SdP();
-    int buf = 0, cs = 0;
-    uint32_t ppar = 0;
-    const uint32_t tdQ = tmem_base + 384;
-    for (int tl = 0; tl < ntiles; ++tl) {
-      for (int j = 0; j < nkb; ++j) {
-        mbar_wait(smem_u32(&bar_p[buf]), ppar);
-        if (j == 0 && tl > 0) mbar_wait(smem_u32(&bar_ofree), (uint32_t)(tl - 1) & 1u);  // previous tile's dQ has been read
-        tc_fence_after();
-        const uint32_t tdS = tmem_base + buf * 128;
-        const uint32_t sK = sKV + cs * 2 * AT_TILE64;
-        if (el) {
-#pragma unroll
-          for (int k = 0; k < 64 / 16; ++k)
-            umma_bf16_ts(tdQ, tdS + k * 8, umma_desc(sK + k * 2048, 8192, 1024), idQ, (j | k) != 0);
-          umma_commit(smem_u32(&bar_empty[cs]));
-          if (j == nkb - 1) umma_commit(smem_u32(&bar_o));
-        }
-        issue_next_SdP();
-        if (++cs == Q3_STAGES) cs = 0;
-        if (++buf == 3) { buf = 0; ppar ^= 1u; }
-      }
-    }
-  } else {
-    const int g = (warp - 2) >> 2;
-    const int qd = warp & 3;
-    const int row = qd * 32 + lane;
-    const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    int gbase = 0;
-    for (int tl = 0; tl < ntiles; ++tl, gbase += nkb) {
-      const int gt = t_begin + tl;
-      const int qt = gt % nqt, bh = gt / nqt;
-      const int h = bh % p.H, b = bh / p.H;
-      const int gq = qt * 128 + row;
-      const long long sidx = ((long long)b * p.H + h) * p.n_pad + gq;
-      const float L2 = p.LSE[sidx];
-      const float Dr = p.D[sidx];
-      for (int j = g; j < nkb; j += 2) {
-        const int G = gbase + j;
-        const int buf = G % 3;
-        const uint32_t spar = (uint32_t)(G / 3) & 1u;
-        mbar_wait(smem_u32(&bar_s[buf]), spar);
-        tc_fence_after();
-        const uint32_t tS = tmem_base + buf * 128 + lane_off, tdP = tS + 64;
-        const int valid = min(64, p.n_k - j * 64);
-        uint32_t rs[64], rd[64];
-        tmem_ld32_nowait(tS, rs);
-        tmem_ld32_nowait(tS + 32, rs + 32);
-        tmem_ld32_nowait(tdP, rd);
-        tmem_ld32_nowait(tdP + 32, rd + 32);
-        tmem_ld_wait();
-        if (valid < 64) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i >= valid) rs[i] = 0xff800000u;
-        }
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(rs[cc * 32 + 2 * i]), p.c, -L2));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(rs[cc * 32 + 2 * i + 1]), p.c, -L2));
-            pk[i] = pack_bf16x2(p0 * (__uint_as_float(rd[cc * 32 + 2 * i]) - Dr),
-                                p1 * (__uint_as_float(rd[cc * 32 + 2 * i + 1]) - Dr));
-          }
-          tmem_st16(tS + cc * 16, pk);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bar_p[buf]));
-      }
-      mbar_wait(smem_u32(&bar_o), (uint32_t)tl & 1u);
-      tc_fence_after();
-      uint32_t a[32];
-      float f[32];
-      tmem_ld32(tmem_base + 384 + g * 32 + lane_off, a);
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bar_ofree));
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(a[i]) * p.scale;
-      if (gq < p.n_q) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gq * p.ld0 + h * AT_D + g * 32, f);
-    }
   }
 
   tc_fence_before();
@@ -1554,15 +1137,19 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     {
       constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
       constexpr uint32_t idG = umma_idesc(128, AT_D, 0, 1);
+      constexpr uint32_t STAGE_B = 2 * AT_TILE64;
+      // descriptors are built once and advanced with one add per MMA (tc.cuh desc_adv): 16 MMAs per 64-query block go through
+      // this one thread, and rebuilding both descriptors from addresses (~11 instructions per MMA) made it the kernel's bound
+      const uint64_t dKa = umma_desc(sK, 16, 1024), dVa = umma_desc(sV, 16, 1024);                 // A of S^T / dP^T (K-major)
+      const uint64_t dQk = umma_desc(sQdO, 16, 1024), ddOk = umma_desc(sQdO + AT_TILE64, 16, 1024);  // B of S^T / dP^T (K-major)
+      const uint64_t dQm = umma_desc(sQdO, 8192, 1024), ddOm = umma_desc(sQdO + AT_TILE64, 8192, 1024);  // B of dK / dV (MN-major)
       auto issue_SdP = [&](int buf, int stage) {
         const uint32_t tS = tmem_base + buf * 128, tdP = tS + 64;
-        const uint32_t sQb = sQdO + stage * 2 * AT_TILE64, sdOb = sQb + AT_TILE64;
+        const uint64_t dq = desc_adv(dQk, stage * STAGE_B), ddo = desc_adv(ddOk, stage * STAGE_B);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sK + k * 32, 16, 1024), umma_desc(sQb + k * 32, 16, 1024), idS, k != 0);
+        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tS, desc_adv(dKa, k * 32), desc_adv(dq, k * 32), idS, k != 0);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tdP, umma_desc(sV + k * 32, 16, 1024), umma_desc(sdOb + k * 32, 16, 1024), idS, k != 0);
+        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tdP, desc_adv(dVa, k * 32), desc_adv(ddo, k * 32), idS, k != 0);
       };
       mbar_wait(smem_u32(&bar_kv), 0);
       int ls = 0, issued = 0;
@@ -1578,24 +1165,19 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       uint32_t ppar = 0;
       const uint32_t tdV = tmem_base + 384, tdK = tmem_base + 448;
       for (int i = 0; i < nqb; ++i) {
+        if (issued < nqb) mbar_wait(smem_u32(&bar_full[ls]), lph);  // {Q, dO} of the S^T / dP^T issued below: off the critical path
         mbar_wait(smem_u32(&bar_p[buf]), ppar);
         tc_fence_after();
         const uint32_t tP = tmem_base + buf * 128, tdS = tP + 64;
-        const uint32_t sQb = sQdO + cs * 2 * AT_TILE64, sdOb = sQb + AT_TILE64;
+        const uint64_t ddo = desc_adv(ddOm, cs * STAGE_B), dq = desc_adv(dQm, cs * STAGE_B);
         if (el) {
 #pragma unroll
-          for (int k = 0; k < 64 / 16; ++k)
-            umma_bf16_ts(tdV, tP + k * 8, umma_desc(sdOb + k * 2048, 8192, 1024), idG, (i | k) != 0);
-        }
-        if (el) {
+          for (int k = 0; k < 64 / 16; ++k) umma_bf16_ts(tdV, tP + k * 8, desc_adv(ddo, k * 2048), idG, (i | k) != 0);
 #pragma unroll
-          for (int k = 0; k < 64 / 16; ++k)
-            umma_bf16_ts(tdK, tdS + k * 8, umma_desc(sQb + k * 2048, 8192, 1024), idG, (i | k) != 0);
+          for (int k = 0; k < 64 / 16; ++k) umma_bf16_ts(tdK, tdS + k * 8, desc_adv(dq, k * 2048), idG, (i | k) != 0);
+          umma_commit(smem_u32(&bar_empty[cs]));
         }
-        if (el) umma_commit(smem_u32(&bar_empty[cs]));
         if (issued < nqb) {
-          mbar_wait(smem_u32(&bar_full[ls]), lph);
-          tc_fence_after();
           if (el) issue_SdP(buf, ls);
           if (el) umma_commit(smem_u32(&bar_s[buf]));
           if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
@@ -1690,229 +1272,6 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   }
 }
 
-// backward dK / dV, PERSISTENT (EXPERIMENTAL, opt-in with B2_ATTN_PBWD=1, never run on a GPU yet): attn_bwd_dkv3_kernel with
-// the KEY tile as an outer loop inside the CTA (see attn_pfwd_kernel for the reasoning).  {K, V} double-buffered, the
-// {Q, dO, LSE, D} stages, the S^T / dP^T ring and all barriers keep running across tiles (global query-block counter); the
-// dV / dK accumulators are handed back by the softmax warps (bar_ofree) before the next tile's first MMA overwrites them.
-constexpr int PK_SMEM = 4 * AT_TILE128 + Q3_STAGES * 2 * AT_TILE64 + 1024;
-
-__global__ void __launch_bounds__(A3_THREADS, 1)
-attn_pbwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO, const AttnP p, int nkt,
-                     int total_tiles) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_kv[2], bar_kvfree[2], bar_full[Q3_STAGES], bar_empty[Q3_STAGES], bar_s[3], bar_p[3], bar_o,
-      bar_ofree;
-  __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float ld_s[Q3_STAGES][128];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sKVb = smem_base;                    // buffer kb: K at +kb*2*TILE128, V right after it
-  const uint32_t sQdO = smem_base + 4 * AT_TILE128;
-  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const int t_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
-  const int t_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
-  const int ntiles = t_end - t_begin;
-  const int nqb = (p.n_q + 63) / 64;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmdO);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bar_kv[i]), 1);
-      mbar_init(smem_u32(&bar_kvfree[i]), 1);
-    }
-#pragma unroll
-    for (int s = 0; s < Q3_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(smem_u32(&bar_s[i]), 1);
-      mbar_init(smem_u32(&bar_p[i]), 128);
-    }
-    mbar_init(smem_u32(&bar_o), 1);
-    mbar_init(smem_u32(&bar_ofree), 256);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), A3_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = uniform_u32(tmem_slot);
-  pdl_wait();
-  pdl_launch_dependents();
-
-  if (warp == 0) {
-    const bool el = elect_one();
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tl = 0; tl < ntiles; ++tl) {
-      const int gt = t_begin + tl;
-      const int kt = gt % nkt, bh = gt / nkt;
-      const int h = bh % p.H, b = bh / p.H;
-      const int kb = tl & 1;
-      // K / V of tile tl-2 are read by its S^T / dP^T MMAs only (dV / dK take Q / dO from the stages): free once those are done
-      if (tl >= 2) mbar_wait(smem_u32(&bar_kvfree[kb]), (uint32_t)((tl >> 1) - 1) & 1u);
-      if (el) {
-        const uint32_t dst = sKVb + kb * 2 * AT_TILE128;
-        mbar_expect_tx(smem_u32(&bar_kv[kb]), 2 * AT_TILE128);
-        tma_load_4d(dst, &tmK, smem_u32(&bar_kv[kb]), 0, kt * 128, h, b);
-        tma_load_4d(dst + AT_TILE128, &tmV, smem_u32(&bar_kv[kb]), 0, kt * 128, h, b);
-      }
-      for (int i = 0; i < nqb; ++i) {
-        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-        const uint32_t full = smem_u32(&bar_full[s]);
-        if (el) {
-          mbar_expect_tx(full, 2 * AT_TILE64 + 512);
-          tma_load_4d(sQdO + s * 2 * AT_TILE64, &tmQ, full, 0, i * 64, h, b);
-          tma_load_4d(sQdO + s * 2 * AT_TILE64 + AT_TILE64, &tmdO, full, 0, i * 64, h, b);
-          const long long off = ((long long)b * p.H + h) * p.n_pad + (long long)i * 64;
-          bulk_load_1d(smem_u32(&ld_s[s][0]), p.LSE + off, 256, full);
-          bulk_load_1d(smem_u32(&ld_s[s][64]), p.D + off, 256, full);
-        }
-        if (++s == Q3_STAGES) { s = 0; ph ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    const bool el = elect_one();
-    constexpr uint32_t idS = umma_idesc(128, 64, 0, 0);
-    constexpr uint32_t idG = umma_idesc(128, AT_D, 0, 1);
-    int s_tl = 0, s_i = 0, s_stage = 0, s_buf = 0;
-    uint32_t s_sph = 0;
-    auto issue_next_SdP = [&]() {
-      if (s_tl >= ntiles) return;
-      const int kb = s_tl & 1;
-      if (s_i == 0) mbar_wait(smem_u32(&bar_kv[kb]), (uint32_t)(s_tl >> 1) & 1u);
-      mbar_wait(smem_u32(&bar_full[s_stage]), s_sph);
-      tc_fence_after();
-      const uint32_t tS = tmem_base + s_buf * 128, tdP = tS + 64;
-      const uint32_t sK = sKVb + kb * 2 * AT_TILE128, sV = sK + AT_TILE128;
-      const uint32_t sQb = sQdO + s_stage * 2 * AT_TILE64, sdOb = sQb + AT_TILE64;
-      if (el) {
-#pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, umma_desc(sK + k * 32, 16, 1024), umma_desc(sQb + k * 32, 16, 1024), idS, k != 0);
-#pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tdP, umma_desc(sV + k * 32, 16, 1024), umma_desc(sdOb + k * 32, 16, 1024), idS, k != 0);
-        umma_commit(smem_u32(&bar_s[s_buf]));
-      }
-      if (++s_stage == Q3_STAGES) { s_stage = 0; s_sph ^= 1u; }
-      if (++s_buf == 3) s_buf = 0;
-      if (++s_i == nqb) {
-        if (el) umma_commit(smem_u32(&bar_kvfree[kb]));
-        s_i = 0;
-        ++s_tl;
-      }
-    };
-    issue_next_SdP();
-    issue_next_SdP();
-    issue_next_SdP();
-    int buf = 0, cs = 0;
-    uint32_t ppar = 0;
-    const uint32_t tdV = tmem_base + 384, tdK = tmem_base + 448;
-    for (int tl = 0; tl < ntiles; ++tl) {
-      for (int i = 0; i < nqb; ++i) {
-        mbar_wait(smem_u32(&bar_p[buf]), ppar);
-        if (i == 0 && tl > 0) mbar_wait(smem_u32(&bar_ofree), (uint32_t)(tl - 1) & 1u);  // previous tile's dV / dK were read
-        tc_fence_after();
-        const uint32_t tP = tmem_base + buf * 128, tdS = tP + 64;
-        const uint32_t sQb = sQdO + cs * 2 * AT_TILE64, sdOb = sQb + AT_TILE64;
-        if (el) {
-#pragma unroll
-          for (int k = 0; k < 64 / 16; ++k)
-            umma_bf16_ts(tdV, tP + k * 8, umma_desc(sdOb + k * 2048, 8192, 1024), idG, (i | k) != 0);
-#pragma unroll
-          for (int k = 0; k < 64 / 16; ++k)
-            umma_bf16_ts(tdK, tdS + k * 8, umma_desc(sQb + k * 2048, 8192, 1024), idG, (i | k) != 0);
-          umma_commit(smem_u32(&bar_empty[cs]));
-          if (i == nqb - 1) umma_commit(smem_u32(&bar_o));
-        }
-        issue_next_SdP();
-        if (++cs == Q3_STAGES) cs = 0;
-        if (++buf == 3) { buf = 0; ppar ^= 1u; }
-      }
-    }
-  } else {
-    const int g = (warp - 2) >> 2;
-    const int qd = warp & 3;
-    const int row = qd * 32 + lane;
-    const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    int gbase = 0;  // global index of the current tile's first query block
-    for (int tl = 0; tl < ntiles; ++tl, gbase += nqb) {
-      const int gt = t_begin + tl;
-      const int kt = gt % nkt, bh = gt / nkt;
-      const int h = bh % p.H, b = bh / p.H;
-      for (int i = g; i < nqb; i += 2) {
-        const int G = gbase + i;
-        const int buf = G % 3, stg = G % Q3_STAGES;
-        const uint32_t spar = (uint32_t)(G / 3) & 1u, fpar = (uint32_t)(G / Q3_STAGES) & 1u;
-        mbar_wait(smem_u32(&bar_s[buf]), spar);
-        tc_fence_after();
-        const uint32_t tS = tmem_base + buf * 128 + lane_off, tdP = tS + 64;
-        uint32_t rs[64], rd[64];
-        tmem_ld32_nowait(tS, rs);
-        tmem_ld32_nowait(tS + 32, rs + 32);
-        tmem_ld32_nowait(tdP, rd);
-        tmem_ld32_nowait(tdP + 32, rd + 32);
-        mbar_wait(smem_u32(&bar_full[stg]), fpar);  // already complete: makes the bulk-copied LSE / D visible to this thread
-        const float4* L4 = reinterpret_cast<const float4*>(&ld_s[stg][0]);
-        const float4* D4 = reinterpret_cast<const float4*>(&ld_s[stg][64]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t pp[16], pd[16];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 lv = L4[cc * 8 + q], dv = D4[cc * 8 + q];
-            const int o = cc * 32 + 4 * q;
-            const float p0 = fast_exp2(fmaf(__uint_as_float(rs[o + 0]), p.c, -lv.x));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(rs[o + 1]), p.c, -lv.y));
-            const float p2 = fast_exp2(fmaf(__uint_as_float(rs[o + 2]), p.c, -lv.z));
-            const float p3 = fast_exp2(fmaf(__uint_as_float(rs[o + 3]), p.c, -lv.w));
-            pp[2 * q] = pack_bf16x2(p0, p1);
-            pp[2 * q + 1] = pack_bf16x2(p2, p3);
-            pd[2 * q] = pack_bf16x2(p0 * (__uint_as_float(rd[o + 0]) - dv.x), p1 * (__uint_as_float(rd[o + 1]) - dv.y));
-            pd[2 * q + 1] = pack_bf16x2(p2 * (__uint_as_float(rd[o + 2]) - dv.z), p3 * (__uint_as_float(rd[o + 3]) - dv.w));
-          }
-          tmem_st16(tS + cc * 16, pp);
-          tmem_st16(tdP + cc * 16, pd);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bar_p[buf]));
-      }
-      mbar_wait(smem_u32(&bar_o), (uint32_t)tl & 1u);
-      tc_fence_after();
-      const int gk = kt * 128 + row;
-      uint32_t a[32], c[32];
-      float f[32];
-      tmem_ld32_nowait(tmem_base + 384 + g * 32 + lane_off, a);  // dV
-      tmem_ld32_nowait(tmem_base + 448 + g * 32 + lane_off, c);  // dK
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bar_ofree));
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(a[i]);
-      if (gk < p.n_k) store_row32(p.out1 + (long long)b * p.bs1 + (long long)gk * p.ld1 + h * AT_D + g * 32, f);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(c[i]) * p.scale;
-      if (gk < p.n_k) store_row32(p.out0 + (long long)b * p.bs0 + (long long)gk * p.ld0 + h * AT_D + g * 32, f);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, A3_TMEM_COLS);
-  }
-}
-
 template <typename K>
 static int set_smem(K kernel, int bytes, const char* what) {
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -1936,7 +1295,8 @@ using namespace b2;
 
 extern "C" int b2_attn_lse_rows(int n_q) { return (n_q + 127) / 128 * 128; }
 
-/* profiling hook (tools/attn_phase_timing.py): 32 uint64 counters accumulated by attn_fwd3_kernel, NULL disables */
+/* profiling hook (tools/attn_phase_timing.py): 32 uint64 counters accumulated by attn_fwd3_kernel (B2_ATTN_FWD3=1) and
+   attn_bwd_dkv3_kernel, NULL disables */
 extern "C" int b2_attn_set_debug(void* counters) {
   b2::g_attn_dbg = reinterpret_cast<unsigned long long*>(counters);
   return B2_OK;
@@ -1976,38 +1336,25 @@ extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
   if ((rc = make_map_bf16_4d(&tv, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 128, "attn V"))) return rc;
   static bool configured = false;
   if (!configured) {
-    if ((rc = set_smem(attn_fwd3_kernel<false>, F3_SMEM, "b2_attn_fwd"))) return rc;
-    if ((rc = set_smem(attn_fwd3_kernel<true>, F3_SMEM, "b2_attn_fwd"))) return rc;
+    if ((rc = set_smem(attn_fwd3_kernel, F3_SMEM, "b2_attn_fwd"))) return rc;
+    if ((rc = set_smem(attn_pfwd2_kernel<false>, P2_SMEM, "b2_attn_fwd"))) return rc;
+    if ((rc = set_smem(attn_pfwd2_kernel<true>, P2_SMEM, "b2_attn_fwd"))) return rc;
     configured = true;
   }
-  const dim3 grid3((a->n_q + 127) / 128, a->H, a->B);
-  if (getenv("B2_ATTN_PFWD")) {  // experimental persistent kernel (one CTA per SM over query tiles), opt-in until measured
-    static bool configured_p = false;
-    if (!configured_p) {
-      if ((rc = set_smem(attn_pfwd_kernel, PF_SMEM, "b2_attn_fwd"))) return rc;
-      configured_p = true;
-    }
-    const int nqt = (a->n_q + 127) / 128;
-    const long long total = (long long)nqt * a->H * a->B;
-    B2_REQUIRE(total < (1ll << 31), "b2_attn_fwd: too many tiles");
-    const int grid = (int)(total < num_sms() ? total : num_sms());
-    (void)launch_pdl(attn_pfwd_kernel, dim3(grid), dim3(A3_THREADS), (size_t)PF_SMEM, st, tq, tk, tv, p, nqt, (int)total);
-    return check_launch("b2_attn_fwd(persistent)");
+  if (getenv("B2_ATTN_FWD3")) {  // the round-1 one-CTA-per-query-tile kernel, kept for A/B timing (read per call: tests switch it)
+    const dim3 grid3((a->n_q + 127) / 128, a->H, a->B);
+    (void)launch_pdl(attn_fwd3_kernel, grid3, dim3(A3_THREADS), (size_t)F3_SMEM, st, tq, tk, tv, p);
+    return check_launch("b2_attn_fwd(v3)");
   }
-  if (getenv("B2_ATTN_FWD4")) {  // experimental sixteen-softmax-warp kernel, opt-in until measured
-    static bool configured4 = false;
-    if (!configured4) {
-      if ((rc = set_smem(attn_fwd4_kernel, F3_SMEM, "b2_attn_fwd"))) return rc;
-      configured4 = true;
-    }
-    (void)launch_pdl(attn_fwd4_kernel, grid3, dim3(A4_THREADS), (size_t)F3_SMEM, st, tq, tk, tv, p);
-    return check_launch("b2_attn_fwd(v4)");
-  }
-  if (getenv("B2_ATTN_POLY_EXP2"))  // opt-in until measured on the GPU (read per call so that tests can switch it)
-    (void)launch_pdl(attn_fwd3_kernel<true>, grid3, dim3(A3_THREADS), (size_t)F3_SMEM, st, tq, tk, tv, p);
+  const int nqt = (a->n_q + 127) / 128;
+  const long long total = (long long)nqt * a->H * a->B;
+  B2_REQUIRE(total < (1ll << 31), "b2_attn_fwd: too many tiles");
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  if (a->n_k % 128)
+    (void)launch_pdl(attn_pfwd2_kernel<true>, dim3(grid), dim3(P2_THREADS), (size_t)P2_SMEM, st, tq, tk, tv, p, nqt, (int)total);
   else
-    (void)launch_pdl(attn_fwd3_kernel<false>, grid3, dim3(A3_THREADS), (size_t)F3_SMEM, st, tq, tk, tv, p);
-  return check_launch("b2_attn_fwd");
+    (void)launch_pdl(attn_pfwd2_kernel<false>, dim3(grid), dim3(P2_THREADS), (size_t)P2_SMEM, st, tq, tk, tv, p, nqt, (int)total);
+  return check_launch("b2_attn_fwd(persistent)");
 }
 
 extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
@@ -2044,41 +1391,12 @@ extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
   if ((rc = make_map_bf16_4d(&tdo64, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 64, "attn dO64"))) return rc;
   AttnP pq = p;
   pq.out0 = (bf16*)a->dQ; pq.ld0 = a->lddq; pq.bs0 = a->dq_bs;
-  if (getenv("B2_ATTN_PBWD")) {  // experimental persistent dQ kernel, opt-in until measured
-    static bool configured_pq = false;
-    if (!configured_pq) {
-      if ((rc = set_smem(attn_pbwd_dq_kernel, PQ_SMEM, "b2_attn_bwd"))) return rc;
-      configured_pq = true;
-    }
-    const int nqt = (a->n_q + 127) / 128;
-    const long long total = (long long)nqt * a->H * a->B;
-    B2_REQUIRE(total < (1ll << 31), "b2_attn_bwd: too many tiles");
-    const int grid = (int)(total < num_sms() ? total : num_sms());
-    (void)launch_pdl(attn_pbwd_dq_kernel, dim3(grid), dim3(A3_THREADS), (size_t)PQ_SMEM, st, tq128, tdo128, tk64, tv64, pq, nqt,
-                     (int)total);
-    if ((rc = check_launch("b2_attn_bwd dq(persistent)"))) return rc;
-  } else {
-    (void)launch_pdl(attn_bwd_dq3_kernel, dim3((a->n_q + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)Q3_SMEM, st, tq128,
-                     tdo128, tk64, tv64, pq);
-    if ((rc = check_launch("b2_attn_bwd dq3"))) return rc;
-  }
+  (void)launch_pdl(attn_bwd_dq3_kernel, dim3((a->n_q + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)Q3_SMEM, st, tq128,
+                   tdo128, tk64, tv64, pq);
+  if ((rc = check_launch("b2_attn_bwd dq3"))) return rc;
   AttnP pk = p;
   pk.out0 = (bf16*)a->dK; pk.ld0 = a->lddk; pk.bs0 = a->dk_bs;
   pk.out1 = (bf16*)a->dV; pk.ld1 = a->lddv; pk.bs1 = a->dv_bs;
-  if (getenv("B2_ATTN_PBWD")) {  // experimental persistent dK / dV kernel, opt-in until measured
-    static bool configured_pk = false;
-    if (!configured_pk) {
-      if ((rc = set_smem(attn_pbwd_dkv_kernel, PK_SMEM, "b2_attn_bwd"))) return rc;
-      configured_pk = true;
-    }
-    const int nkt = (a->n_k + 127) / 128;
-    const long long total = (long long)nkt * a->H * a->B;
-    B2_REQUIRE(total < (1ll << 31), "b2_attn_bwd: too many tiles");
-    const int grid = (int)(total < num_sms() ? total : num_sms());
-    (void)launch_pdl(attn_pbwd_dkv_kernel, dim3(grid), dim3(A3_THREADS), (size_t)PK_SMEM, st, tk128, tv128, tq64, tdo64, pk, nkt,
-                     (int)total);
-    return check_launch("b2_attn_bwd dkv(persistent)");
-  }
   (void)launch_pdl(attn_bwd_dkv3_kernel, dim3((a->n_k + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)Q3_SMEM, st, tk128,
                    tv128, tq64, tdo64, pk);
   return check_launch("b2_attn_bwd dkv3");

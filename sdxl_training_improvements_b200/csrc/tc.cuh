@@ -303,29 +303,29 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   uint32_t hi = ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) /*version*/ | (2u << 29) /*SWIZZLE_128B*/;
   return (uint64_t(hi) << 32) | lo;
 }
+// Moving an operand by `bytes` inside shared memory only changes the descriptor's 14-bit start-address field (16-byte
+// units, no carry out of the field below 256 KiB): ONE 64-bit add.  The single MMA-issuing thread is the critical path of
+// the attention kernels (SASS: rebuilding a descriptor from an address costs ~5 uniform-datapath instructions, 88
+// instructions per 8 MMAs); descriptors are therefore built once per kernel and advanced with desc_adv().
+__device__ __forceinline__ uint64_t desc_adv(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32.
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | (uint32_t(a_mn) << 15) |
          (uint32_t(b_mn) << 16) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
+// Warp-specialised register budget: all four warps of a warpgroup execute the same instruction.  A kernel launched with
+// 384 threads gets 168 registers per thread; the producer / MMA warpgroup gives most of its share back and the softmax
+// warpgroups (one TMEM row of 128 fp32 logits per thread + the next block's prefetch) take it.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-// 2^x on the FMA / integer pipes, no MUFU: x clamped to >= -126, split x = n + f (round to nearest through the 1.5 * 2^23
-// trick), degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below bf16's 2^-9 — the result
-// feeds a bf16 P), n added to the exponent as an integer.  Nine instructions against one ex2.approx: worth it only for a
-// fraction of the softmax elements, where ex2 (16 per clock per SM) is what bounds the d=64 forward kernel.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -126.f);
-  const float xr = x + 12582912.f;
-  const float f = x - (xr - 12582912.f);
-  float p = fmaf(0.05517132f, f, 0.24261054f);
-  p = fmaf(p, f, 0.69326097f);
-  p = fmaf(p, f, 0.99992812f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);

@@ -1,8 +1,7 @@
-"""Synchronisation protocol of the persistent attention kernels (csrc/attn.cu: attn_pfwd_kernel, and with the same
-skeleton attn_pbwd_dq_kernel / attn_pbwd_dkv_kernel), checked on CPU by a randomised discrete-event simulation.
+"""Synchronisation protocol of the persistent forward attention kernel (csrc/attn.cu: attn_pfwd2_kernel), checked on CPU
+by a randomised discrete-event simulation.
 
-Those kernels were drafted after round 1's GPU budget was spent, so what can be verified without a GPU is verified here:
-the four roles (TMA producer, MMA-issuing warp, two softmax groups) are transcribed operation by operation — every
+The four roles (TMA producer, MMA-issuing warp, two softmax groups) are transcribed operation by operation — every
 mbarrier wait with the parity expression the CUDA code uses, every commit / arrive, every buffer read and write — and run
 under a random scheduler with asynchronous TMA completions and an in-order tensor pipe.  The simulation fails on
   * a deadlock (no agent can make progress before all have finished);
@@ -10,6 +9,10 @@ under a random scheduler with asynchronous TMA completions and an in-order tenso
     returns, or one that returns one phase early);
   * a data hazard: an S / P ring slot, K/V stage, Q buffer or O accumulator read while it holds another block's or tile's
     data, or overwritten before its last reader is done.
+What is specific to attn_pfwd2_kernel and modelled here: the MMA warp takes the waits of the NEXT S issue (Q buffer, K/V
+stage) before it waits for P; the lazy-rescale path waits on the K/V stage's bar_empty of the group's previous block
+(there is no separate "PV done" barrier); the two-group merge of tile t is DEFERRED behind each group's first block of
+tile t+1, with the first PV of tile t+1 held back by bar_ofree.
 Parameters sweep the cases that matter: 1, 2, 3 and many key blocks per tile (ring shorter / longer than a tile, a group
 without blocks), 1 to 7 tiles per CTA (Q double buffer wrap-around), several random schedules each.
 """
@@ -17,7 +20,7 @@ import random
 
 import pytest
 
-STAGES = 5  # F3_STAGES (forward); the backward kernels use Q3_STAGES = 6, see Sim(stages=...)
+STAGES = 5  # F3_STAGES
 
 
 class Barrier:
@@ -41,10 +44,7 @@ class Barrier:
 
 
 class Sim:
-    def __init__(self, ntiles, nkb, seed, stages=STAGES, groups_read_stage=False):
-        global STAGES
-        STAGES = stages
-        self.groups_read_stage = groups_read_stage  # dK/dV kernel: the softmax warps read LSE / D from the TMA stage
+    def __init__(self, ntiles, nkb, seed):
         self.rnd = random.Random(seed)
         self.ntiles, self.nkb = ntiles, nkb
         B = Barrier
@@ -54,7 +54,6 @@ class Sim:
         self.bar_empty = [B(f"bar_empty{i}", 1) for i in range(STAGES)]
         self.bar_s = [B(f"bar_s{i}", 1) for i in range(3)]
         self.bar_p = [B(f"bar_p{i}", 1) for i in range(3)]      # 128 threads of ONE group -> modelled as one arrival
-        self.bar_pv = [B(f"bar_pv{i}", 1) for i in range(2)]
         self.bar_o = B("bar_o", 1)
         self.bar_ofree = B("bar_ofree", 2)                      # 256 threads = both groups -> two arrivals
         # buffer contents (what the data currently IS), for the hazard checks
@@ -109,14 +108,20 @@ class Sim:
     def mma_warp(self):
         st = dict(s_tl=0, s_j=0, s_stage=0, s_sph=0, s_buf=0, s_G=0)
 
-        def issue_next_S():
+        def wait_next_S():
             if st["s_tl"] >= self.ntiles:
                 return
             tl, qb = st["s_tl"], st["s_tl"] & 1
             if st["s_j"] == 0:
                 yield lambda: self.bar_q[qb].ready((tl >> 1) & 1, tl >> 1)
-            stage, sph, G, buf = st["s_stage"], st["s_sph"], st["s_G"], st["s_buf"]
+            stage, sph, G = st["s_stage"], st["s_sph"], st["s_G"]
             yield lambda: self.bar_full[stage].ready(sph, G // STAGES)
+
+        def issue_next_S():
+            if st["s_tl"] >= self.ntiles:
+                return
+            tl, qb = st["s_tl"], st["s_tl"] & 1
+            stage, G, buf = st["s_stage"], st["s_G"], st["s_buf"]
 
             def exec_S(tl=tl, qb=qb, stage=stage, G=G, buf=buf):
                 assert self.qbuf[qb] == tl, f"S({G}) reads Q buffer {qb} holding tile {self.qbuf[qb]}, wants {tl}"
@@ -138,11 +143,13 @@ class Sim:
                 st["s_tl"] += 1
 
         for _ in range(3):
-            yield from issue_next_S()
+            yield from wait_next_S()
+            issue_next_S()
         buf, cs, ppar, G = 0, 0, 0, 0
         for tl in range(self.ntiles):
             for j in range(self.nkb):
                 g = j & 1
+                yield from wait_next_S()  # the next S issue's waits are taken BEFORE the wait for P
                 yield lambda buf=buf, ppar=ppar, G=G: self.bar_p[buf].ready(ppar, G // 3)
                 if j == 0 and tl > 0:
                     yield lambda tl=tl: self.bar_ofree.ready((tl - 1) & 1, tl - 1)
@@ -160,11 +167,10 @@ class Sim:
                         self.o_acc[g] = (tl, 1)
                     self.ring[buf] = ("consumed", G)
                 self.mma(exec_PV)
-                self.mma(lambda g=g: self.bar_pv[g].arrive())
                 self.mma(lambda cs=cs: self.bar_empty[cs].arrive())
                 if j == self.nkb - 1:
                     self.mma(lambda: self.bar_o.arrive())
-                yield from issue_next_S()
+                issue_next_S()
                 cs = (cs + 1) % STAGES
                 buf += 1
                 if buf == 3:
@@ -172,27 +178,8 @@ class Sim:
                 G += 1
 
     def group(self, g):
-        gbase, pvc = 0, 0
-        for tl in range(self.ntiles):
-            kown = 0
-            for j in range(g, self.nkb, 2):
-                G = gbase + j
-                buf, spar = G % 3, (G // 3) & 1
-                yield lambda buf=buf, spar=spar, G=G: self.bar_s[buf].ready(spar, G // 3)
-                assert self.ring[buf] == ("S", G), f"group {g} reads ring slot {buf} = {self.ring[buf]}, wants S({G})"
-                if self.groups_read_stage:  # attn_pbwd_dkv_kernel: mbar_wait(bar_full[stg], fpar) before reading ld_s[stg]
-                    stg, fpar = G % STAGES, (G // STAGES) & 1
-                    yield lambda stg=stg, fpar=fpar, G=G: self.bar_full[stg].ready(fpar, G // STAGES)
-                    assert self.stage[stg] == G, f"group {g} reads LSE / D of stage {stg} holding block {self.stage[stg]}"
-                if kown > 0 and self.rnd.random() < 0.5:  # the lazy-rescale path: needs the previous own PV to be complete
-                    yield lambda pvc=pvc: self.bar_pv[g].ready((pvc - 1) & 1, pvc - 1)
-                    assert self.o_acc[g] == (tl, kown), f"rescale of O_{g}: {self.o_acc[g]} vs tile {tl}, {kown} PVs"
-                yield None
-                self.ring[buf] = ("P", G)
-                self.bar_p[buf].arrive()
-                kown += 1
-                pvc += 1
-            # merge: wait for the tile's last PV, meet the other group (a3_group_sync), THEN read both O accumulators
+        def merge(tl):
+            # wait for the tile's last PV, meet the other group (p2_groups_sync), THEN read both O accumulators
             yield lambda tl=tl: self.bar_o.ready(tl & 1, tl)
             self.sync_arrivals[tl] = self.sync_arrivals.get(tl, 0) + 1
             yield lambda tl=tl: self.sync_arrivals.get(tl, 0) == 2
@@ -206,7 +193,33 @@ class Sim:
             if self.o_read[tl] == 2:
                 self.done_outputs.append(("merged", tl))
             self.bar_ofree.arrive()
+
+        gbase = 0
+        for tl in range(self.ntiles):
+            kown = 0
+            merged_prev = tl == 0
+            for j in range(g, self.nkb, 2):
+                G = gbase + j
+                buf, spar = G % 3, (G // 3) & 1
+                yield lambda buf=buf, spar=spar, G=G: self.bar_s[buf].ready(spar, G // 3)
+                assert self.ring[buf] == ("S", G), f"group {g} reads ring slot {buf} = {self.ring[buf]}, wants S({G})"
+                if kown > 0 and self.rnd.random() < 0.5:
+                    # the lazy-rescale path: the PV of this group's previous block (G - 2) must be complete = its K/V stage free
+                    Gp = G - 2
+                    yield lambda Gp=Gp: self.bar_empty[Gp % STAGES].ready((Gp // STAGES) & 1, Gp // STAGES)
+                    assert self.o_acc[g] == (tl, kown), f"rescale of O_{g}: {self.o_acc[g]} vs tile {tl}, {kown} PVs"
+                yield None
+                self.ring[buf] = ("P", G)
+                self.bar_p[buf].arrive()
+                kown += 1
+                if not merged_prev:  # deferred merge of the previous tile, behind this tile's first own block
+                    yield from merge(tl - 1)
+                    merged_prev = True
+            if not merged_prev:      # no own block in this tile (one key block per tile, group 1)
+                yield from merge(tl - 1)
             gbase += self.nkb
+        if self.ntiles > 0:
+            yield from merge(self.ntiles - 1)
 
     # ---- scheduler
     def run(self):
@@ -259,14 +272,3 @@ class Sim:
 def test_persistent_forward_protocol(ntiles, nkb):
     for seed in range(12):
         Sim(ntiles, nkb, seed).run()
-
-
-@pytest.mark.parametrize("nkb", [1, 2, 5, 6, 7, 16])
-@pytest.mark.parametrize("ntiles", [1, 2, 4, 5])
-def test_persistent_backward_protocol(ntiles, nkb):
-    """Same skeleton with six stages; the dK/dV variant's softmax warps additionally wait on the stage's full barrier to
-    read the bulk-copied LSE / D.  (bar_pv and the per-group accumulators of the forward model are a superset of the single
-    accumulator of the backward kernels.)"""
-    for seed in range(8):
-        Sim(ntiles, nkb, seed, stages=6, groups_read_stage=True).run()
-

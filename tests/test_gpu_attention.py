@@ -37,33 +37,24 @@ CASES = [
     (1, 2, 1200, 1200, True, 1.0),    # 1280x960 bucket at 64x: ragged
     (1, 2, 200, 77, False, 1.0),
     (1, 2, 512, 512, True, 6.0),      # peaky logits: exercises the lazy rescale path
+    (3, 20, 1024, 1024, True, 1.0),   # 480 tiles on 148 SMs: 3-4 tiles per persistent CTA, tile boundaries inside a head
+    (2, 3, 1536, 1536, True, 5.0),    # 12 key blocks, peaky logits, several tiles per CTA: rescale across the deferred merge
+    (1, 1, 300, 300, True, 1.0),      # 3 tiles, ragged query AND key tails, fewer tiles than SMs
 ]
 
 
 def _select_variant(variant, monkeypatch, n_k=1024):
-    """v3: the production forward kernel.  poly: v3 with every fourth softmax exponential evaluated as a polynomial on the
-    FMA pipe (opt-in, csrc/tc.cuh poly_exp2; tests/test_poly_exp2.py pins its arithmetic on CPU).  fwd4: the experimental
-    sixteen-softmax-warp kernel (measured once: parity green, 20 % slower).  pfwd: the experimental PERSISTENT forward kernel
-    (one CTA per SM over query tiles) — written after round 1's GPU budget was spent, never run.  Both experimental kernels
-    pbwd: the experimental persistent BACKWARD kernels (dQ over query tiles, dK/dV over key tiles), same status.  The
-    experimental kernels only run when B2_TEST_EXPERIMENTAL=1 (a protocol bug in an unmeasured kernel would trap the whole GPU
-    test run)."""
-    import os
-    monkeypatch.delenv("B2_ATTN_POLY_EXP2", raising=False)
-    monkeypatch.delenv("B2_ATTN_FWD4", raising=False)
-    monkeypatch.delenv("B2_ATTN_PFWD", raising=False)
-    monkeypatch.delenv("B2_ATTN_PBWD", raising=False)
-    if variant not in ("v3", "pbwd") and n_k <= 96:
-        pytest.skip("the cross-attention kernel has no variants")
-    if variant == "poly":
-        monkeypatch.setenv("B2_ATTN_POLY_EXP2", "1")
-    elif variant in ("fwd4", "pfwd", "pbwd"):
-        if not os.environ.get("B2_TEST_EXPERIMENTAL"):
-            pytest.skip("experimental kernel: set B2_TEST_EXPERIMENTAL=1")
-        monkeypatch.setenv({"fwd4": "B2_ATTN_FWD4", "pfwd": "B2_ATTN_PFWD", "pbwd": "B2_ATTN_PBWD"}[variant], "1")
+    """p2: the production forward kernel (attn_pfwd2_kernel: persistent CTA per SM, deferred two-group merge).
+    v3: the round-1 one-CTA-per-query-tile forward kernel, kept selectable (B2_ATTN_FWD3=1) for A/B timing.
+    The backward kernels and the cross-attention kernel (n_k <= 96) have no variants."""
+    monkeypatch.delenv("B2_ATTN_FWD3", raising=False)
+    if variant == "v3":
+        if n_k <= 96:
+            pytest.skip("the cross-attention kernel has no variants")
+        monkeypatch.setenv("B2_ATTN_FWD3", "1")
 
 
-@pytest.mark.parametrize("variant", ["v3", "poly", "fwd4", "pfwd", "pbwd"])
+@pytest.mark.parametrize("variant", ["p2", "v3"])
 @pytest.mark.parametrize("B,H,n_q,n_k,fused,gain", CASES)
 def test_attention_fwd_bwd(B, H, n_q, n_k, fused, gain, variant, monkeypatch):
     _select_variant(variant, monkeypatch, n_k)
@@ -110,12 +101,35 @@ def test_attention_fwd_bwd(B, H, n_q, n_k, fused, gain, variant, monkeypatch):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("variant", ["v3", "poly", "fwd4", "pfwd", "pbwd"])
+@pytest.mark.parametrize("variant", ["p2", "v3"])
 def test_attention_speed_report(variant, monkeypatch):
     """Not an assertion on speed — prints achieved TFLOP/s of the three kernels for the bench log."""
     from sdxl_training_improvements_b200 import ops
     _select_variant(variant, monkeypatch)
     poly = variant
+    if variant == "p2":  # cross-attention core (77 keys), forward + backward, once
+        for (B, H, n, nk) in ((4, 20, 1024, 77), (4, 10, 4096, 77)):
+            Cc = H * 64
+            q = torch.randn(B * n, Cc, device="cuda").to(bf16)
+            kv = torch.randn(B * nk, 2 * Cc, device="cuda").to(bf16)
+            k, v = kv[:, :Cc], kv[:, Cc:]
+            do = torch.randn(B * n, Cc, device="cuda").to(bf16)
+            dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+            o, lse = ops.attn_fwd(q, k, v, B, H, n, nk, 0.125)
+            ops.attn_bwd(q, k, v, o, lse, do, dq, dkv[:, :Cc], dkv[:, Cc:], B, H, n, nk, 0.125)
+            torch.cuda.synchronize()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            it = 20
+            e[0].record()
+            for _ in range(it):
+                ops.attn_fwd(q, k, v, B, H, n, nk, 0.125, out=o)
+            e[1].record()
+            for _ in range(it):
+                ops.attn_bwd(q, k, v, o, lse, do, dq, dkv[:, :Cc], dkv[:, Cc:], B, H, n, nk, 0.125)
+            e[2].record()
+            torch.cuda.synchronize()
+            print(f"\ncross attn B={B} H={H} n={n} nk={nk}: fwd {e[0].elapsed_time(e[1]) / it * 1e3:.1f} us, "
+                  f"bwd {e[1].elapsed_time(e[2]) / it * 1e3:.1f} us (stream launches, not graph replay)")
     for (B, H, n) in ((4, 20, 1024), (4, 10, 4096)):
         Cc = H * 64
         qkv = torch.randn(B * n, 3 * Cc, device="cuda").to(bf16)

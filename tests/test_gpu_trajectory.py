@@ -13,6 +13,7 @@ kernel path must track the exact curve at least as well as the reference's own p
 (pure forward parity, no optimizer drift) must be within 1e-3 * max(1, loss).
 Reduced-width UNet (same topology) so that the oracles run in seconds; flow matching and ddpm/v-prediction.
 """
+import os
 from types import SimpleNamespace
 
 import pytest
@@ -158,7 +159,6 @@ def _oracle_adamw_bf16_step(params, state, step, lr, wd_state, gen):
 def test_mid_size_loss_curve_100_steps(method, optname):
     import copy
     import json
-    import os
     from oracle import schedule as S
     from oracle.unet_sdxl import OracleUNet, seeded_init_
     from sdxl_training_improvements_b200.trainer import B200AdamW, B200AdamWBF16, create_trainer
@@ -173,7 +173,11 @@ def test_mid_size_loss_curve_100_steps(method, optname):
     net = B200UNet(cfg, device="cuda")
     net.store.flat.copy_(host.store.flat)
     del host
-    lr = 1e-4 if optname == "adamw_fp32_master" else 2e-5
+    # lr: the reference ships 4e-7 (src/config.yaml:17).  At 1e-4 a random-init 0.85 B-parameter UNet on 10 batches is in a
+    # chaotic regime where ANY two precisions diverge by 0.1-0.7 in loss within 100 steps (measured: bf16 eager vs fp32
+    # 0.15 / 0.23 / 0.66, profiles/r2_trajectory_lr1e-4_chaotic.json) — the yardstick bar still holds there but the north
+    # star's 1e-3 is meaningless.  5e-6 (12x the shipped value) keeps the curves smooth while the loss still goes down.
+    lr = float(os.environ.get("B2_TRAJ_LR", "5e-6"))
     if optname == "adamw_fp32_master":
         opt_k = B200AdamW(net, lr=lr, weight_decay=1e-2, master_weights=True)
     else:
@@ -231,24 +235,39 @@ def test_mid_size_loss_curve_100_steps(method, optname):
         lk.append(float(out["loss"].detach())); lo.append(float(o["loss"].detach())); l16.append(float(o16["loss"].detach()))
     d = [abs(a - b_) for a, b_ in zip(lk, lo)]
     d16 = [abs(a - b_) for a, b_ in zip(l16, lo)]
+    # THE north-star comparison: the reference casts the whole UNet to bf16 (sdxl_trainer.py:52-55), so "the reference's loss
+    # curve" is the bf16-eager arm; the fp32 arm shows how far BOTH bf16 paths sit from exact arithmetic (the weights they
+    # train are rounded to bf16 after every update, the fp32 arm's are not — that, not the kernels, is the 1e-2 gap)
+    dkr = [abs(a - b_) for a, b_ in zip(lk, l16)]
+    rel_kr = max(x / max(1.0, abs(r)) for x, r in zip(dkr, l16))
     rec = {"method": method, "optimizer": optname, "steps": STEPS, "lr": lr,
            "config": "widths 320/640/1280, heads 5/10/20, depth 0/1/2, cross dim 2048, latent 32x32, B=2, 10 batches cycled",
            "params": int(net.store.numel),
            "loss_first": {"kernel": lk[0], "oracle_fp32": lo[0], "oracle_bf16_eager": l16[0]},
            "loss_last": {"kernel": lk[-1], "oracle_fp32": lo[-1], "oracle_bf16_eager": l16[-1]},
+           "kernel_vs_reference_bf16_eager": {"max_abs": max(dkr), "mean_abs": sum(dkr) / STEPS,
+                                              "argmax_step": dkr.index(max(dkr)), "max_rel_to_max1loss": rel_kr},
            "kernel_vs_fp32": {"max_abs": max(d), "mean_abs": sum(d) / STEPS, "argmax_step": d.index(max(d))},
            "bf16_eager_vs_fp32_yardstick": {"max_abs": max(d16), "mean_abs": sum(d16) / STEPS},
-           "north_star_1e-3_met_by_kernel": max(d) <= 1e-3, "north_star_1e-3_met_by_bf16_eager": max(d16) <= 1e-3,
+           "north_star_1e-3_vs_reference_met": rel_kr <= 1e-3,
            "curves": {"kernel": lk, "oracle_fp32": lo, "oracle_bf16_eager": l16}}
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
-    with open(os.path.join(out_dir, f"r2_trajectory_{method}_{optname}.json"), "w") as f:
+    with open(os.path.join(out_dir, f"r2_trajectory_{method}_{optname}_lr{lr:g}.json"), "w") as f:
         json.dump(rec, f, indent=1)
-    print(f"\n{method}/{optname}: loss {lo[0]:.4f} -> {lo[-1]:.4f} (fp32 oracle); kernel vs fp32 max |d| {max(d):.3e} mean "
-          f"{sum(d) / STEPS:.3e}; bf16-eager vs fp32 max |d| {max(d16):.3e} mean {sum(d16) / STEPS:.3e}")
+    print(f"\n{method}/{optname} lr {lr:g}: loss {lo[0]:.4f} -> {lo[-1]:.4f} (fp32 oracle); kernel vs REFERENCE (bf16 eager) max |d| "
+          f"{max(dkr):.3e} (rel {rel_kr:.2e}) mean {sum(dkr) / STEPS:.3e}; kernel vs fp32 max |d| {max(d):.3e}; "
+          f"bf16-eager vs fp32 max |d| {max(d16):.3e}")
     assert sum(lo[-10:]) < sum(lo[:10]), "the oracle's loss did not go down: the trajectory is not exercising learning"
     assert d[0] <= max(1e-3 * max(1.0, lo[0]), 1.5 * d16[0]), f"first-step loss differs: {d[0]:.3e} (bf16 eager: {d16[0]:.3e})"
-    # north star: 1e-3 on the curve wherever the reference's own precision (bf16 eager) meets it; otherwise the kernel path
-    # must track the exact curve at least as closely as 1.5 x the reference's own numerics do
+    # (1) north star: within 1e-3 (relative to max(1, loss)) of the reference's own numerics — or, where stochastic rounding /
+    #     a larger lr make two bf16 runs drift, at most a quarter of the distance between the reference and exact arithmetic
+    #     (AdamWBF16: the kernel's Philox stream and the oracle's torch.randint stream round every update differently, so the
+    #     two bf16 runs are two independent samples of the same stochastic process: they may sit as far from each other as
+    #     each sits from the exact curve — factor 1.5 instead of 0.25)
+    fac = 0.25 if optname == "adamw_fp32_master" else 1.5
+    assert rel_kr <= 1e-3 or max(dkr) <= fac * max(d16), \
+        f"kernel vs reference (bf16 eager): max |d| {max(dkr):.3e}, rel {rel_kr:.2e}; reference vs fp32 {max(d16):.3e}"
+    # (2) and it tracks the exact curve as well as the reference's precision does
     bar = max(1e-3, 1.5 * max(d16))
     assert max(d) <= bar, f"loss curves diverge: max |d| {max(d):.3e} > {bar:.3e}"
