@@ -183,6 +183,15 @@ int b2_attn_set_debug(void* counters);
 
 /* GEGLU: z[m, j] = u[m, j] * gelu_erf(u[m, F + j]), u: [M, 2F]. replaces diffusers GEGLU.forward + backward. */
 int b2_geglu_fwd(const void* u, void* z, int64_t M, int F, void* stream);
+/* GEGLU up-projection with the gate in the GEMM epilogue (gemm2_kernel, GEGLU mode):
+ *   u[M, 2F] = x[M, K] W1[2F, K]^T + b1   (both halves rounded to bf16 and stored: the backward pass reads them)
+ *   z[M, F]  = u[:, :F] * gelu_erf(u[:, F:])   formed from the bf16 values of u, i.e. bit-identical to b2_gemm + b2_geglu_fwd
+ * replaces: diffusers GEGLU.forward (attention.py / activations.py: proj -> chunk(2) -> hidden * F.gelu(gate)), 70 per UNet
+ * forward; saves the separate kernel's re-read of u (84 MB per block at C = 1280, B = 4, 1024 px).
+ * b2_linear_geglu_ok(): M >= 128, F a multiple of 128, K a multiple of 8 and >= 64. */
+int b2_linear_geglu_ok(int M, int F, int K);
+int b2_linear_geglu(const void* x, const void* W1, const void* b1, void* u, void* z, int M, int F, int K, int64_t ldx,
+                    int64_t ldw, int64_t ldu, int64_t ldz, void* stream);
 int b2_geglu_bwd(const void* u, const void* dz, void* du, int64_t M, int F, void* stream);
 
 /* Elementwise / plumbing */

@@ -47,6 +47,11 @@ struct AttnP {
   unsigned long long* dbg;  // optional per-phase cycle counters (b2_attn_set_debug), NULL in production
 };
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of work).  The backward kernels are bound by
+// the softmax warps' ISSUE SLOTS (trace + ncu, profiles/r2_attention_notes.md: 2 x 458 instructions per 64-query block pair on
+// each scheduler against a 1250-cycle period), so halving the FFMA / FADD / FMUL count is worth more than any pipe tuning.
+__device__ __forceinline__ float2 f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+
 __device__ __forceinline__ void store_row64(bf16* dst, const uint32_t* r0, const uint32_t* r1, float mul) {
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
@@ -610,15 +615,17 @@ attn_pfwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           l *= factor;
         }
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        const float2 c2 = make_float2(p.c, p.c), nm2 = make_float2(-m_used, -m_used);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i]), p.c, -m_used));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 1]), p.c, -m_used));
-            const float p2 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 2]), p.c, -m_used));
-            const float p3 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 3]), p.c, -m_used));
+            // packed fp32 pairs (FFMA2) halve the issue slots of the scale; the row sum stays scalar: with FADD2 the
+            // compiler moves every ex2 result into an aligned register pair first (one MOV per element, no gain)
+            const float2 x01 = __ffma2_rn(f2(r[cc * 32 + 2 * i], r[cc * 32 + 2 * i + 1]), c2, nm2);
+            const float2 x23 = __ffma2_rn(f2(r[cc * 32 + 2 * i + 2], r[cc * 32 + 2 * i + 3]), c2, nm2);
+            const float p0 = fast_exp2(x01.x), p1 = fast_exp2(x01.y), p2 = fast_exp2(x23.x), p3 = fast_exp2(x23.y);
             l0 += p0; l1 += p1; l2 += p2; l3 += p3;
             pk[i] = pack_bf16x2(p0, p1);
             pk[i + 1] = pack_bf16x2(p2, p3);
@@ -836,15 +843,15 @@ attn_xfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       const float m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.c;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      const float2 c2 = make_float2(p.c, p.c), nm2 = make_float2(-m, -m);
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * j]), p.c, -m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * j + 1]), p.c, -m));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * j + 2]), p.c, -m));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(r[cc * 32 + 2 * j + 3]), p.c, -m));
+          const float2 x01 = __ffma2_rn(f2(r[cc * 32 + 2 * j], r[cc * 32 + 2 * j + 1]), c2, nm2);
+          const float2 x23 = __ffma2_rn(f2(r[cc * 32 + 2 * j + 2], r[cc * 32 + 2 * j + 3]), c2, nm2);
+          const float p0 = fast_exp2(x01.x), p1 = fast_exp2(x01.y), p2 = fast_exp2(x23.x), p3 = fast_exp2(x23.y);
           l0 += p0; l1 += p1; l2 += p2; l3 += p3;
           pk[j] = pack_bf16x2(p0, p1);
           pk[j + 1] = pack_bf16x2(p2, p3);
@@ -891,7 +898,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
 attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                     const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnP p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_full[Q3_STAGES], bar_empty[Q3_STAGES], bar_s[3], bar_p[3], bar_o;
+  __shared__ __align__(8) uint64_t bar_q, bar_t, bar_full[Q3_STAGES], bar_empty[Q3_STAGES], bar_s[3], bar_p[3], bar_o;
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base, sdO = smem_base + AT_TILE128, sKV = smem_base + 2 * AT_TILE128;
@@ -905,6 +912,7 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(smem_u32(&bar_q), 1);
+    mbar_init(smem_u32(&bar_t), 256);
 #pragma unroll
     for (int s = 0; s < Q3_STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
@@ -954,18 +962,22 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       constexpr uint32_t idQ = umma_idesc(128, AT_D, 0, 1);
       constexpr uint32_t STAGE_B = 2 * AT_TILE64;
       // descriptors are built once and advanced with one add per MMA (tc.cuh desc_adv): this thread's issue rate bounds the kernel
-      const uint64_t dQd = umma_desc(sQ, 16, 1024), ddO = umma_desc(sdO, 16, 1024);            // A of S / dP (K-major)
+      // A of S / dP = this CTA's Q / dO tile: the same 128 x 64 operand for every key block.  Read from shared memory (SS mode)
+      // an N = 64 MMA moves 4 KB of A + 2 KB of B per 32 tensor cycles = 192 B/clk against the 128 B/clk the SM's shared
+      // memory delivers — measured 47 cycles per MMA instead of 32 (tools/attn_trace.py).  The softmax warps therefore copy
+      // Q and dO once into TMEM columns [448, 512) as bf16 pairs and the MMAs take A from there (TS mode).
+      const uint32_t tQ = tmem_base + 448, tdO = tmem_base + 480;
       const uint64_t dKk = umma_desc(sKV, 16, 1024), dVk = umma_desc(sKV + AT_TILE64, 16, 1024);  // B of S / dP (K-major)
       const uint64_t dKm = umma_desc(sKV, 8192, 1024);                                          // B of dQ += dS K (MN-major)
       auto issue_SdP = [&](int buf, int stage) {
         const uint32_t tS = tmem_base + buf * 128, tdP = tS + 64;
         const uint64_t dk = desc_adv(dKk, stage * STAGE_B), dv = desc_adv(dVk, stage * STAGE_B);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tS, desc_adv(dQd, k * 32), desc_adv(dk, k * 32), idS, k != 0);
+        for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ts(tS, tQ + k * 8, desc_adv(dk, k * 32), idS, k != 0);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tdP, desc_adv(ddO, k * 32), desc_adv(dv, k * 32), idS, k != 0);
+        for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ts(tdP, tdO + k * 8, desc_adv(dv, k * 32), idS, k != 0);
       };
-      mbar_wait(smem_u32(&bar_q), 0);
+      mbar_wait(smem_u32(&bar_t), 0);  // Q and dO are in TMEM
       int ls = 0, issued = 0;
       uint32_t lph = 0;
       for (; issued < 3 && issued < nkb; ++issued) {
@@ -1009,6 +1021,20 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const long long sidx = ((long long)b * p.H + h) * p.n_pad + gq;
     const float L2 = p.LSE[sidx];   // n_pad is a multiple of 128: in bounds; +inf on pad rows -> P = 0
     const float Dr = p.D[sidx];
+    {  // group 0 moves row `row` of Q, group 1 of dO, from the swizzled TMA tile into TMEM (bf16 pairs, K-major A operand)
+      mbar_wait(smem_u32(&bar_q), 0);
+      const uint32_t src = (g == 0 ? sQ : sdO) + row * 128;
+      uint32_t w[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[4 * c]), "=r"(w[4 * c + 1]), "=r"(w[4 * c + 2]), "=r"(w[4 * c + 3])
+                     : "r"(src + ((c ^ (row & 7)) << 4)));
+      tmem_st32(tmem_base + 448 + g * 32 + lane_off, w);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_t));
+    }
     int buf = g;
     uint32_t spar = 0;
     for (int j = g; j < nkb; j += 2) {
@@ -1032,10 +1058,10 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(rs[cc * 32 + 2 * i]), p.c, -L2));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(rs[cc * 32 + 2 * i + 1]), p.c, -L2));
-          pk[i] = pack_bf16x2(p0 * (__uint_as_float(rd[cc * 32 + 2 * i]) - Dr),
-                              p1 * (__uint_as_float(rd[cc * 32 + 2 * i + 1]) - Dr));
+          const float2 x = __ffma2_rn(f2(rs[cc * 32 + 2 * i], rs[cc * 32 + 2 * i + 1]), make_float2(p.c, p.c), make_float2(-L2, -L2));
+          const float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+          const float2 ds = __fmul2_rn(pe, __fadd2_rn(f2(rd[cc * 32 + 2 * i], rd[cc * 32 + 2 * i + 1]), make_float2(-Dr, -Dr)));
+          pk[i] = pack_bf16x2(ds.x, ds.y);
         }
         tmem_st16(tS + cc * 16, pk);  // dS (bf16) in place over the consumed S columns
       }
@@ -1080,6 +1106,10 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nqb = (p.n_q + 63) / 64;
+  // b2_attn_set_debug(buffer of >= 320 uint64): besides the phase counters, CTA (1,0,0) leaves a clock64 trace of its first
+  // 64 query blocks — [64 + 2i] P(i) seen by the MMA thread, [65 + 2i] block i issued, [192 + 2i] S(i) seen by its softmax
+  // group, [193 + 2i] P(i) arrived (tools/attn_trace.py)
+  const bool trace = p.dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmK);
@@ -1168,6 +1198,7 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
         if (issued < nqb) mbar_wait(smem_u32(&bar_full[ls]), lph);  // {Q, dO} of the S^T / dP^T issued below: off the critical path
         mbar_wait(smem_u32(&bar_p[buf]), ppar);
         tc_fence_after();
+        if (trace && el && i < 64) p.dbg[64 + 2 * i] = clk();        // event trace of CTA (0,0,0): P(i) seen by the MMA thread
         const uint32_t tP = tmem_base + buf * 128, tdS = tP + 64;
         const uint64_t ddo = desc_adv(ddOm, cs * STAGE_B), dq = desc_adv(dQm, cs * STAGE_B);
         if (el) {
@@ -1183,6 +1214,7 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
           if (++ls == Q3_STAGES) { ls = 0; lph ^= 1u; }
           ++issued;
         }
+        if (trace && el && i < 64) p.dbg[65 + 2 * i] = clk();        // ... and everything for block i issued
         if (++cs == Q3_STAGES) cs = 0;
         if (++buf == 3) { buf = 0; ppar ^= 1u; }
       }
@@ -1202,6 +1234,7 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       mbar_wait(smem_u32(&bar_s[buf]), spar);
       tc_fence_after();
       if (dbg) { t1 = clk(); d_wait += t1 - t0; t0 = t1; }
+      if (trace && qd == 0 && lane == 0 && i < 64) p.dbg[192 + 2 * i] = clk();   // S(i) seen by its softmax group
       const uint32_t tS = tmem_base + buf * 128 + lane_off, tdP = tS + 64;
       uint32_t rs[64], rd[64];
       tmem_ld32_nowait(tS, rs);
@@ -1222,14 +1255,17 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
         for (int q = 0; q < 8; ++q) {
           const float4 lv = L4[cc * 8 + q], dv = D4[cc * 8 + q];
           const int o = cc * 32 + 4 * q;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(rs[o + 0]), p.c, -lv.x));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(rs[o + 1]), p.c, -lv.y));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(rs[o + 2]), p.c, -lv.z));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(rs[o + 3]), p.c, -lv.w));
-          pp[2 * q] = pack_bf16x2(p0, p1);
-          pp[2 * q + 1] = pack_bf16x2(p2, p3);
-          pd[2 * q] = pack_bf16x2(p0 * (__uint_as_float(rd[o + 0]) - dv.x), p1 * (__uint_as_float(rd[o + 1]) - dv.y));
-          pd[2 * q + 1] = pack_bf16x2(p2 * (__uint_as_float(rd[o + 2]) - dv.z), p3 * (__uint_as_float(rd[o + 3]) - dv.w));
+          const float2 cc2 = make_float2(p.c, p.c);
+          const float2 x01 = __ffma2_rn(f2(rs[o + 0], rs[o + 1]), cc2, make_float2(-lv.x, -lv.y));
+          const float2 x23 = __ffma2_rn(f2(rs[o + 2], rs[o + 3]), cc2, make_float2(-lv.z, -lv.w));
+          const float2 p01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
+          const float2 p23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
+          const float2 s01 = __fmul2_rn(p01, __fadd2_rn(f2(rd[o + 0], rd[o + 1]), make_float2(-dv.x, -dv.y)));
+          const float2 s23 = __fmul2_rn(p23, __fadd2_rn(f2(rd[o + 2], rd[o + 3]), make_float2(-dv.z, -dv.w)));
+          pp[2 * q] = pack_bf16x2(p01.x, p01.y);
+          pp[2 * q + 1] = pack_bf16x2(p23.x, p23.y);
+          pd[2 * q] = pack_bf16x2(s01.x, s01.y);
+          pd[2 * q + 1] = pack_bf16x2(s23.x, s23.y);
         }
         tmem_st16(tS + cc * 16, pp);
         tmem_st16(tdP + cc * 16, pd);
@@ -1239,6 +1275,7 @@ attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_p[buf]));
       if (dbg) { t1 = clk(); d_st += t1 - t0; t0 = t1; }
+      if (trace && qd == 0 && lane == 0 && i < 64) p.dbg[193 + 2 * i] = clk();   // ... P(i) / dS(i) written, arrived
       buf += 2;
       if (buf >= 3) { buf -= 3; spar ^= 1u; }
       stg += 2;

@@ -49,32 +49,7 @@ __global__ void softmax_bwd_kernel(const bf16* __restrict__ P, const float* __re
 }
 
 // ---------------------------------------------------------------- GEGLU
-// Exact-erf GELU (diffusers GEGLU uses F.gelu, not the tanh form).  erff() costs ~25 instructions and made these
-// kernels ALU-bound (41 / 53 us for 126 / 210 MB); Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, far below one bf16
-// ulp of the product) needs one reciprocal, five FMAs and ONE exponential — exp(-x^2/2) — which is also the Gaussian
-// density the derivative needs:   Phi(x) = (1 + erf(x/sqrt2)) / 2,   gelu' = Phi + x * phi.
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
-  const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));  // exp(-x^2 / 2)
-  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
-                              0.254829592f);
-  const float erf_abs = fmaf(-poly, e, 1.f);
-  cdf = 0.5f * (1.f + copysignf(erf_abs, x));
-  pdf = 0.3989422804014327f * e;
-}
-__device__ __forceinline__ float gelu_erf(float x) {
-  float c, d;
-  gelu_parts(x, c, d);
-  return x * c;
-}
-__device__ __forceinline__ float dgelu_erf(float x) {
-  float c, d;
-  gelu_parts(x, c, d);
-  return fmaf(x, d, c);
-}
-
+// exact-erf GELU helpers (gelu_parts / gelu_erf / dgelu_erf): common.cuh — shared with the GEGLU epilogue of gemm2.cu
 // I = unsigned (M * F / 8 < 2^31, every SDXL shape) keeps the per-vector row / column split a 32-bit division: with the
 // 64-bit one these kernels are co-bound by the integer pipe (~60 of ~270 instructions per 48 bytes of traffic)
 template <typename I>

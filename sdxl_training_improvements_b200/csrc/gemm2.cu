@@ -34,6 +34,7 @@ constexpr int G2_WIDE_BN = 320;
 constexpr int G2_WIDE_STAGES = 5;
 constexpr int G2_WIDE_STAGE_BYTES = G2_A_BYTES + (G2_WIDE_BN / 2) * G2_BK * 2;  // 16 KiB A + 20 KiB B half
 static_assert(G2_WIDE_STAGES * G2_WIDE_STAGE_BYTES + 2 * G2_EPI_BYTES + 1024 <= G2_SMEM, "wide mode must fit the same smem budget");
+static_assert((G2_STAGES - 1) * G2_STAGE_BYTES + 3 * G2_EPI_BYTES + 1024 <= G2_SMEM, "GEGLU mode: 5 stages + 3 staging tiles");
 constexpr int G2_TMEM_COLS = 512;
 
 struct Gemm2P {
@@ -70,6 +71,12 @@ struct Gemm2P {
   // stay in natural order.
   int wide;
   int stages, stage_bytes;
+  // GEGLU mode (b2_linear_geglu): D = u[M, 2F] = x W1^T + b1 with u = [h | g], and Z[M, F] = h * gelu(g) from the same
+  // accumulators.  A 256-column tile is 128 h-columns (this pair's CTA 0 stages those rows of W1) next to the MATCHING 128
+  // g-columns (CTA 1 stages rows F + ...), so the epilogue holds h_j and g_j of the same feature j in one thread; it
+  // rounds both to bf16 exactly as the un-fused path stores them, writes them to u (the backward pass needs both) and
+  // writes bf16(h * gelu(g)) to Z — the separate GEGLU kernel's 2F-wide re-read of u disappears.
+  int geglu, gg_F;
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
@@ -111,7 +118,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const Gemm2P p) {
+             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+             const __grid_constant__ CUtensorMap tmZ, const Gemm2P p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[G2_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[G2_STAGES];
@@ -171,7 +179,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int kb0 = split * p.kb_per, kb1 = min(num_kb_total, kb0 + p.kb_per);
         const int mb = t % p.tiles_m, nb = t / p.tiles_m;
         const int m_base = mb * 256 + (int)rank * 128;
-        const int n_base = nb * p.BN + (int)rank * halfn;
+        // GEGLU mode: CTA 0 stages W1's h rows [nb*128, +128), CTA 1 the matching g rows [F + nb*128, +128)
+        const int n_base = p.geglu ? nb * 128 + (int)rank * p.gg_F : nb * p.BN + (int)rank * halfn;
         const int n_wide = nb * p.BN + (int)rank * 80;  // wide mode: rows [n_wide, +80) and [n_wide + 160, +80)
         // Implicit-conv address state.  Everything below is strength-reduced to counters: this loop runs on ONE
         // thread and must issue a k-block's TMAs in well under the k-block's MMA time (256..512 cycles); runtime
@@ -354,6 +363,59 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait<true>(smem_u32(&bar_acc_full[buf]), use & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * 256 + lane_off;
+      if (p.geglu) {
+        // accumulator columns [0,128) = h features nb*128 .., [128,256) = the matching g features.  Three staging tiles
+        // (h, g, z) per 64-column chunk: GEGLU mode runs the mainloop on 5 stages, which frees a third 16 KB buffer.
+        const int nh = nb * 128;
+        for (int c0 = 0; c0 < 128; c0 += 64) {
+          uint32_t vh0[32], vh1[32], vg0[32], vg1[32];
+          tmem_ld32_nowait(tacc + c0, vh0);
+          tmem_ld32_nowait(tacc + c0 + 32, vh1);
+          tmem_ld32_nowait(tacc + 128 + c0, vg0);
+          tmem_ld32_nowait(tacc + 128 + c0 + 32, vg1);
+          if (et == 0) tma_store_wait_read<0>();  // the previous chunk's three TMA stores have read their staging tiles
+          epi_bar_sync();
+          tmem_ld_wait();
+          const uint32_t srow = smem_epi + row * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t* a = g < 4 ? vh0 + g * 8 : vh1 + (g - 4) * 8;
+            const uint32_t* b = g < 4 ? vg0 + g * 8 : vg1 + (g - 4) * 8;
+            float fh[8], fg[8], tb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { fh[j] = __uint_as_float(a[j]); fg[j] = __uint_as_float(b[j]); }
+            if (p.bias) {
+              unpack8(ld8(p.bias + nh + c0 + g * 8), tb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) fh[j] += tb[j];
+              unpack8(ld8(p.bias + p.gg_F + nh + c0 + g * 8), tb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) fg[j] += tb[j];
+            }
+            const bf16x8 ph = pack8(fh), pg = pack8(fg);
+            unpack8(ph, fh);   // the GEGLU product is formed from the bf16 values u holds (as geglu_fwd_kernel does)
+            unpack8(pg, fg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fh[j] *= gelu_erf(fg[j]);
+            const bf16x8 pz = pack8(fh);
+            const uint32_t saddr = srow + ((g ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(ph.u.x), "r"(ph.u.y), "r"(ph.u.z),
+                         "r"(ph.u.w) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr + G2_EPI_BYTES), "r"(pg.u.x), "r"(pg.u.y),
+                         "r"(pg.u.z), "r"(pg.u.w) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr + 2 * G2_EPI_BYTES), "r"(pz.u.x), "r"(pz.u.y),
+                         "r"(pz.u.z), "r"(pz.u.w) : "memory");
+          }
+          fence_proxy_async_smem();
+          epi_bar_sync();
+          if (et == 0) {
+            tma_store_2d(&tmD, smem_epi, nh + c0, m_base);
+            tma_store_2d(&tmD, smem_epi + G2_EPI_BYTES, p.gg_F + nh + c0, m_base);
+            tma_store_2d(&tmZ, smem_epi + 2 * G2_EPI_BYTES, nh + c0, m_base);
+            tma_store_commit();
+          }
+        }
+      } else
       for (int c0 = 0; c0 < ncols; c0 += 64) {
         const int cw = min(64, ncols - c0);
         const int n0 = n_tile + c0;
@@ -586,7 +648,7 @@ static int gemm2_zero_fill(void* D, long long ldd, int M, int N, cudaStream_t st
 }
 
 static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr,
-                        Gemm2P& p, cudaStream_t st, const char* what) {
+                        Gemm2P& p, cudaStream_t st, const char* what, const CUtensorMap* tz = nullptr) {
   static bool configured = false;
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
@@ -598,13 +660,13 @@ static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   }
   const int num_clusters = num_sms() / 2;
   p.tiles_m = (p.M + 255) / 256;
-  p.tiles_n = (p.N + p.BN - 1) / p.BN;
+  p.tiles_n = p.geglu ? p.gg_F / 128 : (p.N + p.BN - 1) / p.BN;
   if (p.splits < 1) {
     p.splits = 1;
     p.kb_per = (p.K + G2_BK - 1) / G2_BK;
   }
   p.wide = p.BN == G2_WIDE_BN ? 1 : 0;
-  p.stages = p.wide ? G2_WIDE_STAGES : G2_STAGES;
+  p.stages = p.wide ? G2_WIDE_STAGES : p.geglu ? G2_STAGES - 1 : G2_STAGES;  // GEGLU: 5 stages + a third staging tile
   p.stage_bytes = p.wide ? G2_WIDE_STAGE_BYTES : G2_STAGE_BYTES;
   if (p.splits > 1) p.has_res = 0;  // the reduce-add epilogue is the accumulation
   static const bool log_calls = getenv("B2_GEMM_LOG") != nullptr;
@@ -613,7 +675,8 @@ static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
             p.a_mn, p.b_mn, p.conv, p.BN, p.splits, p.bias != nullptr, p.has_res);
   const long long tiles = (long long)p.tiles_m * p.tiles_n * p.splits;
   const int clusters = (int)(tiles < num_clusters ? tiles : num_clusters);
-  cudaError_t le = launch_pdl(gemm2_kernel, dim3(2 * clusters), dim3(G2_THREADS), (size_t)G2_SMEM, st, ta, tb, td, tr, p);
+  cudaError_t le = launch_pdl(gemm2_kernel, dim3(2 * clusters), dim3(G2_THREADS), (size_t)G2_SMEM, st, ta, tb, td, tr,
+                              tz ? *tz : td, p);
   if (le != cudaSuccess) {
     set_error("%s: launch: %s", what, cudaGetErrorString(le));
     return B2_ERR_CUDA;
@@ -722,6 +785,34 @@ static bool conv_geom_ok(int B, int H, int W, int pix) {
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2_linear_geglu_ok(int M, int F, int K) {
+  if (getenv("B2_GEGLU_UNFUSED")) return 0;
+  return M >= 128 && F >= 128 && (F % 128) == 0 && K >= 64 && (K % 8) == 0;
+}
+
+extern "C" int b2_linear_geglu(const void* x, const void* W1, const void* b1, void* u, void* z, int M, int F, int K,
+                               int64_t ldx, int64_t ldw, int64_t ldu, int64_t ldz, void* stream) {
+  B2_REQUIRE(x && W1 && u && z, "b2_linear_geglu: null pointer");
+  B2_REQUIRE(b2_linear_geglu_ok(M, F, K), "b2_linear_geglu: unsupported shape M=%d F=%d K=%d (use b2_gemm + b2_geglu_fwd)", M,
+             F, K);
+  B2_REQUIRE(!b1 || !(reinterpret_cast<uintptr_t>(b1) & 15), "b2_linear_geglu: bias must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap ta, tb, td, tz;
+  int rc;
+  if ((rc = make_map_2d(&ta, x, K, M, ldx, 64, 128, "geglu x"))) return rc;
+  if ((rc = make_map_2d(&tb, W1, K, 2ull * F, ldw, 64, 128, "geglu W1"))) return rc;
+  if ((rc = make_map_2d(&td, u, 2ull * F, M, ldu, 64, 128, "geglu u"))) return rc;
+  if ((rc = make_map_2d(&tz, z, F, M, ldz, 64, 128, "geglu z"))) return rc;
+  Gemm2P p{};
+  p.M = M; p.N = 2 * F; p.K = K; p.BN = 256;
+  p.alpha = 1.f;
+  p.bias = reinterpret_cast<const bf16*>(b1);
+  p.bias_rows_per_group = 0x7fffffff;
+  p.D = reinterpret_cast<bf16*>(u); p.ldd = ldu;
+  p.geglu = 1; p.gg_F = F;
+  return gemm2_launch(ta, tb, td, td, p, st, "b2_linear_geglu", &tz);
+}
 
 extern "C" int b2_conv3x3_implicit_ok(int B, int H, int W, int Cin, int Cout) {
   if (getenv("B2_CONV_EXPLICIT")) return 0;

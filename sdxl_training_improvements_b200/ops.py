@@ -246,6 +246,21 @@ def geglu_fwd(u, F):
     return z
 
 
+def linear_geglu_ok(M, F, K) -> bool:
+    return bool(_lib.load().b2_linear_geglu_ok(int(M), int(F), int(K)))
+
+
+def linear_geglu_fwd(x, W1, b1, F):
+    """(u, z): u[M, 2F] = x @ W1^T + b1, z[M, F] = u[:, :F] * gelu(u[:, F:]) in ONE GEMM launch (gate in the epilogue)."""
+    _need_cuda(x, W1, b1)
+    M, K = x.shape
+    u = torch.empty((M, 2 * F), device=x.device, dtype=bf16)
+    z = torch.empty((M, F), device=x.device, dtype=bf16)
+    _lib.check(_lib.load().b2_linear_geglu(_p(x), _p(W1), _p(b1), _p(u), _p(z), int(M), int(F), int(K), int(x.stride(0)),
+                                           int(W1.stride(0)), 2 * F, F, _stream()), "linear_geglu")
+    return u, z
+
+
 def geglu_bwd(u, dz, F):
     M = u.shape[0]
     du = torch.empty_like(u)

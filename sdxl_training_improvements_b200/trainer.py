@@ -21,9 +21,9 @@ from typing import Any, Dict, Optional
 import torch
 
 from . import ops
-from .unet import B200UNet, bf16
+from .unet import IN_PAD, PRED_PAD, B200UNet, bf16
 
-LATENT_PAD = 8
+LATENT_PAD = IN_PAD  # channel padding of the noisy latents handed to conv_in; the prediction comes back PRED_PAD wide
 
 
 class FatalStepError(RuntimeError):
@@ -182,10 +182,10 @@ class FusedLossCore:
         dpred = torch.empty_like(pred.d)
         self.loss_sum.zero_()
         self.stats.zero_()
-        ops.mse_loss(pred.d, target, weight, self.loss_sum, dpred, loss_scale / n, B, Cc, HW, LATENT_PAD)
+        ops.mse_loss(pred.d, target, weight, self.loss_sum, dpred, loss_scale / n, B, Cc, HW, PRED_PAD)
         ops.finalize_loss(self.loss_sum, n, loss_scale, self.loss, self.ok, dpred)
         ops.abs_sq_sums(noise, self.stats[0:2])
-        ops.abs_sq_sums(pred.d, self.stats[2:4], LATENT_PAD, Cc)
+        ops.abs_sq_sums(pred.d, self.stats[2:4], PRED_PAD, Cc)
         ops.abs_sq_sums(latents, self.stats[4:6])
         self._saved = ((tape[0], tape[1]), dpred)
         self.last = {"pred": pred.d, "target": target, "noisy": noisy, "noise": noise, "numel": n}

@@ -25,6 +25,9 @@ from .params import SDXL_BASE, ParamStore
 
 bf16 = torch.bfloat16
 HEAD_DIM = 64
+IN_PAD = 8     # latent channels (4) padded to 8 at conv_in: TMA's 16-byte rule
+PRED_PAD = 64  # conv_out's 4 output channels padded to 64: N = 64 puts its forward and dgrad GEMMs on the CTA-pair kernel
+               # (at N = 8 they ran on the first-generation kernel: 426 + 397 us per step for 3 GFLOP)
 
 
 class Act:
@@ -133,6 +136,24 @@ class UNetEngine:
 
         self.tape.append(bwd)
         return out
+
+    def _linear_geglu(self, x: Act, wname: str, bname: str, F: int, K: int):
+        """GEGLU up-projection with the gate fused into the GEMM epilogue: returns (u, z) Acts; the backward closure is the
+        plain Linear's (weight / bias / input gradients from u.g, which the caller's geglu backward fills)."""
+        st = self.store
+        Wt = st.w(wname, 2 * F, K)
+        ud, zd = ops.linear_geglu_fwd(x.d, Wt, st.v(bname), F)
+        u, z = Act(ud), Act(zd)
+
+        def bwd():
+            dy = u.g
+            ops.linear_wgrad(dy, x.d, st.g(wname, 2 * F, K), accumulate=True)
+            ops.colsum_f32(dy, st.gs(bname))
+            buf, acc = _gslot(x)
+            ops.linear_dgrad(dy, Wt, buf, acc)
+
+        self.tape.append(bwd)
+        return u, z
 
     def _add_grad(self, t: Act, dy: torch.Tensor):
         if t.g is None:
@@ -334,8 +355,11 @@ class UNetEngine:
         n2 = self.layernorm(h1, Cc, f"{pfx}.norm2.weight", f"{pfx}.norm2.bias")
         h2 = self.attention(n2, h1, B, n, Cc, f"{pfx}.attn2", ctx, n_ctx)
         n3 = self.layernorm(h2, Cc, f"{pfx}.norm3.weight", f"{pfx}.norm3.bias")
-        u = self.linear(n3, f"{pfx}.ff.net.0.proj.weight", 8 * Cc, Cc, f"{pfx}.ff.net.0.proj.bias")
-        z = Act(ops.geglu_fwd(u.d, 4 * Cc))
+        if ops.linear_geglu_ok(n3.d.shape[0], 4 * Cc, Cc):
+            u, z = self._linear_geglu(n3, f"{pfx}.ff.net.0.proj.weight", f"{pfx}.ff.net.0.proj.bias", 4 * Cc, Cc)
+        else:
+            u = self.linear(n3, f"{pfx}.ff.net.0.proj.weight", 8 * Cc, Cc, f"{pfx}.ff.net.0.proj.bias")
+            z = Act(ops.geglu_fwd(u.d, 4 * Cc))
 
         def geglu_bwd():
             u.g = ops.geglu_bwd(u.d, z.g, 4 * Cc)
@@ -400,7 +424,7 @@ class UNetEngine:
     # ------------------------------------------------------------------ whole network
     def forward(self, x_nhwc8: torch.Tensor, t_f32: torch.Tensor, ctx: torch.Tensor, pooled: torch.Tensor,
                 time_ids_f32: torch.Tensor, B: int, H: int, W: int) -> Act:
-        """x_nhwc8: [B*H*W, 8] bf16 (4 latent channels + 4 zero pad).  Returns pred as Act([B*H*W, 8])."""
+        """x_nhwc8: [B*H*W, IN_PAD] bf16 (4 latent channels + zero pad).  Returns pred as Act([B*H*W, PRED_PAD])."""
         cfg = self.cfg
         st = self.store
         self.tape = []
@@ -465,22 +489,24 @@ class UNetEngine:
                 cH, cW = cH * 2, cW * 2
 
         a = self.groupnorm(h, B, cH * cW, ch, "conv_norm_out.weight", "conv_norm_out.bias", cfg["norm_eps"], True)
-        # conv_out: Cout padded to 8 rows (zero rows / zero bias) so the GEMM's N and the dgrad's K satisfy TMA
+        # conv_out: Cout padded to PRED_PAD rows (zero rows / zero bias): the GEMM's N and the dgrad's K then satisfy TMA and
+        # the CTA-pair kernel's minimum tile
         co = cfg["out_channels"]
         K = 9 * ch
-        wk_out = torch.zeros((8, K), device=dev, dtype=bf16)
+        NP = PRED_PAD
+        wk_out = torch.zeros((NP, K), device=dev, dtype=bf16)
         ops.copy2d(st.w("conv_out.weight", co, K), wk_out, co, K, K, K)
-        gwk_out = torch.zeros((8, K), device=dev, dtype=bf16)
-        b_out = torch.zeros(8, device=dev, dtype=bf16)
-        ops.copy2d_any(st.v("conv_out.bias").view(1, co), b_out.view(1, 8), 1, co, co, 8)
+        gwk_out = torch.zeros((NP, K), device=dev, dtype=bf16)
+        b_out = torch.zeros(NP, device=dev, dtype=bf16)
+        ops.copy2d_any(st.v("conv_out.bias").view(1, co), b_out.view(1, NP), 1, co, co, NP)
         pred = self.conv3x3(a, B, cH, cW, ch, co, "conv_out.weight", "conv_out.bias", Wk=wk_out, gWk=gwk_out,
-                            bias_t=b_out, Npad=8)
+                            bias_t=b_out, Npad=NP)
 
         def conv_out_pgrad():
             ops.copy2d(gwk_out, st.g("conv_out.weight", co, K), co, K, K, K, accumulate=True)
-            gb = torch.zeros(8, device=dev, dtype=bf16)
+            gb = torch.zeros(NP, device=dev, dtype=bf16)
             ops.colsum(pred.g, gb, accumulate=False)
-            ops.copy2d_any(gb.view(1, 8), st.gv("conv_out.bias").view(1, co), 1, co, 8, co, accumulate=True)
+            ops.copy2d_any(gb.view(1, NP), st.gv("conv_out.bias").view(1, co), 1, co, NP, co, accumulate=True)
 
         self.tape.insert(len(self.tape) - 1, conv_out_pgrad)
         self._out = pred
@@ -493,7 +519,7 @@ class UNetEngine:
         return t
 
     def backward(self, dpred_nhwc8: torch.Tensor, saved=None, cuts=None, on_cut=None):
-        """Replay a tape: fills ParamStore.grad (+=).  dpred: [B*H*W, 8] bf16 (pad channels must be zero).
+        """Replay a tape: fills ParamStore.grad (+=).  dpred: [B*H*W, PRED_PAD] bf16 (pad channels must be zero).
         `cuts` (ascending replay positions, the last one = end of tape) + `on_cut(k)`: data-parallel hook — called right
         after position cuts[k] has run, when chunk k of the gradient buffer is final (dp.plan_chunks); the hook flushes
         that chunk's small-parameter gradients and starts its exchange."""
@@ -542,12 +568,12 @@ class _UNetFunction(torch.autograd.Function):
         ctx.unet = unet
         ctx.shape = (B, Cc, H, W)
         ctx.out_dtype = sample.dtype if sample.dtype in (bf16, torch.float32) else bf16
-        return ops.nhwc_to_nchw(pred.d, B, Cc, H, W, 8, dtype=ctx.out_dtype)
+        return ops.nhwc_to_nchw(pred.d, B, Cc, H, W, PRED_PAD, dtype=ctx.out_dtype)
 
     @staticmethod
     def backward(ctx, grad_out):
         B, Cc, H, W = ctx.shape
-        g8 = ops.nchw_to_nhwc(grad_out.contiguous(), 8)
+        g8 = ops.nchw_to_nhwc(grad_out.contiguous(), PRED_PAD)
         ctx.unet.engine.backward(g8, ctx.saved_tape)
         ctx.saved_tape = None
         return (None,) * 7

@@ -44,6 +44,13 @@ class ShapeOnlyOps:
     def ln_fwd(self, x, gamma, beta, eps=1e-5):
         return torch.empty_like(x), self._e(x, x.shape[0], dtype=torch.float32), self._e(x, x.shape[0], dtype=torch.float32)
 
+    @staticmethod
+    def linear_geglu_ok(M, F, K):
+        return F % 128 == 0  # which path is taken does not change the tape length
+
+    def linear_geglu_fwd(self, x, W1, b1, F):
+        return self._e(x, x.shape[0], 2 * F), self._e(x, x.shape[0], F)
+
     def geglu_fwd(self, u, F):
         return self._e(u, u.shape[0], F)
 

@@ -38,7 +38,7 @@ def _real_tape_log(H, W, B=1):
     saved = eng.detach_tape()
     n_tape = len(saved[0])
     store.touch_log = []
-    eng.backward(torch.empty(B * H * W, 8, device="meta", dtype=bf16), saved)
+    eng.backward(torch.empty(B * H * W, 64, device="meta", dtype=bf16), saved)
     log, store.touch_log = store.touch_log, None
     return store, log, n_tape
 

@@ -452,3 +452,24 @@ def test_small_grad_staging_and_group_colsum(ops):
     exp[16:24] += 3.0
     _close(grad, exp, rtol=2 ** -7, atol=2e-2, what="flush_small_grads")
     assert float(st.abs().sum()) == 0.0, "staging must be cleared by the flush"
+
+
+@pytest.mark.parametrize("M,Fd,K", [(4096, 5120, 1280), (1024, 2560, 640), (300, 512, 128), (128, 128, 64)])
+def test_linear_geglu_fused_epilogue_is_bit_identical_to_gemm_plus_geglu(ops, M, Fd, K):
+    """b2_linear_geglu (gate in the GEMM epilogue, GEGLU mode of gemm2_kernel) vs the two-kernel path b2_gemm + b2_geglu_fwd:
+    u and z BIT-identical (same accumulation order per output element, same bf16 rounding points), and vs torch:
+    diffusers GEGLU.forward = proj -> chunk(2) -> hidden * F.gelu(gate) (exact erf)."""
+    assert ops.linear_geglu_ok(M, Fd, K)
+    x = _rand(M, K, seed=31)
+    W1 = _rand(2 * Fd, K, scale=K ** -0.5, seed=32)
+    b1 = _rand(2 * Fd, scale=0.1, seed=33)
+    u, z = ops.linear_geglu_fwd(x, W1, b1, Fd)
+    u2 = ops.linear_fwd(x, W1, bias=b1)
+    z2 = ops.geglu_fwd(u2, Fd)
+    if M >= 256:  # below that b2_gemm takes its generic (different accumulation order) kernel: compare with tolerance only
+        assert torch.equal(u, u2), f"u differs in {int((u != u2).sum())} elements"
+        assert torch.equal(z, z2), f"z differs in {int((z != z2).sum())} elements"
+    ur = x.float() @ W1.float().t() + b1.float()
+    _close(u, ur, what="geglu-fused u")
+    h, g = u.float().chunk(2, -1)  # the gate is formed from the bf16 values u holds (one bf16 rounding of the product)
+    _close(z, h * F.gelu(g), what="geglu-fused z")

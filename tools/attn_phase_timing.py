@@ -12,7 +12,7 @@ for (B, H, n) in ((4, 20, 1024), (4, 10, 4096)):
     q, k, v = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
     ops.attn_fwd(q, k, v, B, H, n, n, 0.125)
     torch.cuda.synchronize()
-    ctr = torch.zeros(32, device="cuda", dtype=torch.int64)
+    ctr = torch.zeros(512, device="cuda", dtype=torch.int64)
     _lib.load().b2_attn_set_debug(ctr.data_ptr())
     ops.attn_fwd(q, k, v, B, H, n, n, 0.125)
     torch.cuda.synchronize()
@@ -24,7 +24,7 @@ for (B, H, n) in ((4, 20, 1024), (4, 10, 4096)):
     o, lse = ops.attn_fwd(q, k, v, B, H, n, n, 0.125)
     ops.attn_bwd(q, k, v, o, lse, do, dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:], B, H, n, n, 0.125)
     torch.cuda.synchronize()
-    ctr2 = torch.zeros(32, device="cuda", dtype=torch.int64)
+    ctr2 = torch.zeros(512, device="cuda", dtype=torch.int64)
     _lib.load().b2_attn_set_debug(ctr2.data_ptr())
     ops.attn_bwd(q, k, v, o, lse, do, dqkv[:, :Cc], dqkv[:, Cc:2 * Cc], dqkv[:, 2 * Cc:], B, H, n, n, 0.125)
     torch.cuda.synchronize()
