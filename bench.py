@@ -455,8 +455,32 @@ def run_ours(args):
     if args.no_grad_exchange and world > 1:
         trainer.core.dp = None
         trainer.world_size = 1
-    batch = _synthetic_batch(B, H, W, seed=77 + rank)
+    # BASELINE configs[4] (--mixed-buckets): aspect buckets {768^2, 1024^2, 1280x960}, the bucket of every GLOBAL micro-step
+    # drawn by data.BucketBatchSampler (rank-sharded, identical order on every rank: all ranks run the same shape)
+    mixed = bool(args.mixed_buckets)
+    shapes = [(96, 96), (128, 128), (120, 160)] if mixed else [(H, W)]
+    batches = {s_: _synthetic_batch(B, s_[0], s_[1], seed=77 + rank + 13 * i_) for i_, s_ in enumerate(shapes)}
+    batch = batches[shapes[-1] if not mixed else (128, 128)]
     h2d = sum(v.numel() * v.element_size() for k, v in batch.items() if torch.is_tensor(v))
+    n_micro = (args.steps + max(args.warmup, 3) + 4) * A
+    if mixed:
+        from sdxl_training_improvements_b200.data import BucketBatchSampler
+        per_bucket = B * world * ((n_micro + len(shapes) - 1) // len(shapes) + 2)
+        idx, shape_of = {}, {}
+        for i_, s_ in enumerate(shapes):
+            idx[s_] = list(range(i_ * per_bucket, (i_ + 1) * per_bucket))
+            shape_of.update({j_: s_ for j_ in idx[s_]})
+        sampler_b = BucketBatchSampler(idx, B, rank=rank, world_size=world, seed=11)
+        seq = [shape_of[b_[0]] for b_ in sampler_b][:n_micro]
+        assert len(seq) == n_micro
+    else:
+        seq = [shapes[0]] * n_micro
+    seq_pos = [0]
+
+    def next_shape():
+        s_ = seq[seq_pos[0] % len(seq)]
+        seq_pos[0] += 1
+        return s_
 
     def barrier():
         if world > 1:
@@ -464,18 +488,22 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up through the public plugin API (also JITs nothing: all kernels are prebuilt) ----
-    def api_step():
+    def api_step(fixed=None):
         for a in range(A):
-            loss, metrics = trainer._execute_training_step(batch, accumulate=A > 1, is_last_accumulation_step=a == A - 1)
+            s_ = fixed or next_shape()
+            loss, metrics = trainer._execute_training_step(batches[s_], accumulate=A > 1, is_last_accumulation_step=a == A - 1)
         return loss, metrics
 
+    if mixed:  # every bucket shape is first seen at an optimizer-step boundary, so its CUDA graph is captured there
+        for s_ in shapes:
+            api_step(fixed=s_)
     for _ in range(max(args.warmup, 3)):
         api_step()
     barrier()
 
     # ---- (1) device-resident timing: `value` ----
     from sdxl_training_improvements_b200.trainer import _prep_batch, allreduce_gradients
-    dev_batch = _prep_batch(batch, unet.device)
+    dev_batches = {s_: _prep_batch(batches[s_], unet.device) for s_ in shapes}
     K = args.steps
     sched = trainer.noise_scheduler if args.method == "ddpm" else None
     gen = torch.Generator().manual_seed(5 + rank)
@@ -489,8 +517,10 @@ def run_ours(args):
         t_embed = [t.float().cuda() for t in ts]
         sig = t_embed
     core = trainer.core
-    gm = next(iter(trainer._micro_graphs.values())) if use_graph else None
+    gms = {s_: trainer._micro_graphs[(B, s_[0], s_[1], 77)] for s_ in shapes} if use_graph else {}
+    gm = gms[shapes[0]] if use_graph else None
     og = trainer._opt_graph if use_graph else None
+    timed_seq = [next_shape() for _ in range(K * A)]
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = _lib.launch_count()
@@ -500,10 +530,12 @@ def run_ours(args):
     for i in range(K):
         for a in range(A):
             core.dp_last = a == A - 1  # N>1: the last micro-step's backward hands finished gradient chunks to the exchange
+            s_ = timed_seq[i * A + a]
+            dev_batch = dev_batches[s_]
             if use_graph:  # one graph launch per micro-step (N>1: per exchange chunk); inputs already resident in HBM
-                gm.load(dev_batch["latents"], dev_batch["ctx"], dev_batch["pooled"], dev_batch["time_ids"],
-                        t_embed[i * A + a], sig[i * A + a], None, 1.0 / A)
-                gm.replay(last=core.dp_last)
+                gms[s_].load(dev_batch["latents"], dev_batch["ctx"], dev_batch["pooled"], dev_batch["time_ids"],
+                             t_embed[i * A + a], sig[i * A + a], None, 1.0 / A)
+                gms[s_].replay(last=core.dp_last)
             else:
                 core.step_no_autograd(grad_scale=1.0 / A, latents=dev_batch["latents"], ctx=dev_batch["ctx"],
                                       pooled=dev_batch["pooled"], time_ids=dev_batch["time_ids"], t_embed=t_embed[i * A + a],
@@ -514,7 +546,7 @@ def run_ours(args):
     barrier()
     launches = _lib.launch_count() - launches0
     if use_graph:
-        launches = K * (A * gm.launches_per_replay + og.launches_per_replay)
+        launches = sum(gms[s_].launches_per_replay for s_ in timed_seq) + K * og.launches_per_replay
     ms_dev = e0.elapsed_time(e1) / K
 
     # ---- (2) end-to-end through the plugin API with host buffers: `e2e` ----
@@ -548,6 +580,7 @@ def run_ours(args):
             return torch.stack([a, b])
 
         sums = [checksum(unet.store.flat)]
+        dev_batch = dev_batches[shapes[0]]
         core.dp_last = True
         if use_graph:
             gm.load(dev_batch["latents"], dev_batch["ctx"], dev_batch["pooled"], dev_batch["time_ids"], t_embed[0], sig[0],
@@ -586,7 +619,7 @@ def run_ours(args):
     if rank == 0 and core.dp is not None and core.dp.plan is not None:
         print(core.dp.plan.describe(), file=sys.stderr, flush=True)
     if rank == 0:
-        step_flops = train_step_flops(None, H, W) * B * A
+        step_flops = sum(train_step_flops(None, s_[0], s_[1]) * B for s_ in timed_seq) / K
         value = world * B * A / (ms_dev * 1e-3)
         e2e_v = world * B * A / (ms_e2e * 1e-3)
         roof = _time_gemm_roofline(ops, peaks)
@@ -599,8 +632,16 @@ def run_ours(args):
         out = {"metric": METRIC, "value": round(value, 4), "unit": "images/s", "n_gpus": world, "steps": K,
                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev, 2), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-               "config": {"workload": WORKLOAD_FMT.format(method=args.method, W=8 * W, H=8 * H, h=H, w=W,
-                                                          accum=(f"grad-accum {A}, " if A > 1 else ""), opt=args.optimizer),
+               "config": {"workload": (WORKLOAD_FMT.format(method=args.method, W=8 * W, H=8 * H, h=H, w=W,
+                                                           accum=(f"grad-accum {A}, " if A > 1 else ""), opt=args.optimizer)
+                                       if not mixed else
+                                       f"SDXL-base UNet, {args.method}, bs=4/GPU, mixed-AR buckets 768^2 / 1024^2 / 1280x960 (one "
+                                       f"bucket per global micro-step, data.BucketBatchSampler), grad-accum {A}, bf16, full "
+                                       f"fwd+bwd+loss+clip+{args.optimizer} (configs[4])"),
+                          **({"bucket_counts": {f"{8 * s_[1]}x{8 * s_[0]}": timed_seq.count(s_) for s_ in shapes},
+                              "images_1024eq_per_s": round(world * step_flops / train_step_flops(None, 128, 128)
+                                                           / (ms_dev * 1e-3), 3),
+                              "uncaptured_micro_steps": trainer.uncaptured_micro_steps} if mixed else {}),
                           "cuda_graph": use_graph,
                           "global_batch": B * world * A, "parallelism": f"dp{world}",
                           "grad_exchange": ("none (1 GPU)" if world == 1 else "DISABLED (diagnostic)" if args.no_grad_exchange else
@@ -717,6 +758,9 @@ def main():
     ap.add_argument("--latent-h", type=int, default=128, help="latent height (image / 8); default 128 = 1024 px")
     ap.add_argument("--latent-w", type=int, default=128)
     ap.add_argument("--accum", type=int, default=1, help="gradient-accumulation micro-steps per optimizer step")
+    ap.add_argument("--mixed-buckets", action="store_true",
+                    help="BASELINE configs[4]: aspect buckets {768^2, 1024^2, 1280x960}, one bucket per global micro-step "
+                         "(use with --method flow_matching --accum 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU oracle timing")
     ap.add_argument("--optimizer", default="adamw_bf16", choices=["adamw_bf16", "adamw_fp32"])

@@ -181,6 +181,20 @@ int b2_attn_bwd(const b2_attn_args* args, void* stream);
 /* Profiling hook: device buffer of 32 uint64 per-phase cycle counters accumulated by the forward kernel (NULL = off). */
 int b2_attn_set_debug(void* counters);
 
+/* Cross-attention query projection fused with the 77-key attention core (xattn.cu; the north-star kernel of SURVEY.md 8d):
+ *   Q[M, C] = xn[M, C] Wq[C, C]^T          (M = B * n_q; written once for the backward pass, never read back here)
+ *   O[:, h*64:(h+1)*64] = softmax(Q_h K_h^T * scale) V_h   per head, keys = the sample's n_k text tokens
+ *   LSE[B, H, n_pad] (log2 domain, as b2_attn_fwd)
+ * replaces: diffusers Attention.to_q (Linear) + F.scaled_dot_product_attention of attn2 in BasicTransformerBlock (call site
+ * of the UNet forward: src/training/trainers/methods/ddpm_trainer.py:320-325) — two launches and the HBM round trip of Q.
+ * K / V: [B * n_k, ld] row-major views (head h = columns h*64..), sample stride k_bs / v_bs elements.
+ * b2_xattn_q_core_ok(): C a multiple of 320, n_q a multiple of 256, n_k <= 80; other shapes: b2_gemm + b2_attn_fwd. */
+int b2_xattn_q_core_ok(int B, int n_q, int n_k, int C);
+int b2_xattn_set_debug(void* stamps); /* profiling hook: >= 32 uint64 clock64 stamps of CTA 0's first tile; NULL = off */
+int b2_xattn_q_core(const void* xn, const void* Wq, const void* K, const void* V, void* Q, void* O, float* LSE, int B, int n_q,
+                    int n_k, int C, int64_t ldx, int64_t ldw, int64_t ldq, int64_t ldo, int64_t ldk, int64_t ldv, int64_t k_bs,
+                    int64_t v_bs, float scale, void* stream);
+
 /* GEGLU: z[m, j] = u[m, j] * gelu_erf(u[m, F + j]), u: [M, 2F]. replaces diffusers GEGLU.forward + backward. */
 int b2_geglu_fwd(const void* u, void* z, int64_t M, int F, void* stream);
 /* GEGLU up-projection with the gate in the GEMM epilogue (gemm2_kernel, GEGLU mode):

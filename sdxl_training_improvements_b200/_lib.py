@@ -57,6 +57,9 @@ SIGNATURES = {
     "b2_attn_fwd": [C.POINTER(AttnArgs), c_p],
     "b2_attn_bwd": [C.POINTER(AttnArgs), c_p],
     "b2_attn_set_debug": [c_p],
+    "b2_xattn_q_core_ok": [i32, i32, i32, i32],
+    "b2_xattn_set_debug": [c_p],
+    "b2_xattn_q_core": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, f32, c_p],
     "b2_conv3x3_implicit_ok": [i32, i32, i32, i32, i32],
     "b2_conv3x3": [C.POINTER(ConvArgs), c_p],
     "b2_im2col3x3": [c_p, c_p, i32, i32, i32, i32, i32, i32, i64, c_p],

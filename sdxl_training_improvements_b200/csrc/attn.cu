@@ -47,9 +47,11 @@ struct AttnP {
   unsigned long long* dbg;  // optional per-phase cycle counters (b2_attn_set_debug), NULL in production
 };
 
-// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of work).  The backward kernels are bound by
-// the softmax warps' ISSUE SLOTS (trace + ncu, profiles/r2_attention_notes.md: 2 x 458 instructions per 64-query block pair on
-// each scheduler against a 1250-cycle period), so halving the FFMA / FADD / FMUL count is worth more than any pipe tuning.
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one instruction for two lanes of work).  The softmax warps of the backward
+// kernels walk a dependent chain LDTM -> FFMA -> ex2 -> FADD -> FMUL -> F2FP -> STTM with one warp per scheduler per group;
+// fewer instructions on that chain shortened it measurably (458 -> 350 per 64-query block, backward 145 -> 138 us at n = 1024,
+// 777 -> 707 us at n = 4096; profiles/r2_attention_notes.md).  ncu: issue slots are only ~33 % busy — the chain's latency,
+// not its issue rate, is what the packing buys back.
 __device__ __forceinline__ float2 f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
 __device__ __forceinline__ void store_row64(bf16* dst, const uint32_t* r0, const uint32_t* r1, float mul) {
@@ -658,35 +660,6 @@ attn_pfwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
 
 // ---------------------------------------------------------------------------------------------
-// backward, part 0: D[i] = sum_d dO[i,d] * O[i,d]   (8 lanes per (row, head))
-// ---------------------------------------------------------------------------------------------
-__global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ D, int B,
-                                     int H, int n_q, int n_pad, long long ldo, long long o_bs, long long lddo,
-                                     long long do_bs) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long item = gid >> 3;
-  const int sub = (int)(gid & 7);
-  const long long total = (long long)B * n_pad * H;
-  const bool live = item < total;
-  const int h = (int)(item % H);
-  const long long t = item / H;
-  const int i = (int)(t % n_pad);
-  const int b = (int)(t / n_pad);
-  float acc = 0.f;
-  if (live && i < n_q) {
-    float a[8], g[8];
-    unpack8(ld8(O + (long long)b * o_bs + (long long)i * ldo + h * AT_D + sub * 8), a);
-    unpack8(ld8(dO + (long long)b * do_bs + (long long)i * lddo + h * AT_D + sub * 8), g);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc += a[j] * g[j];
-  }
-  acc += __shfl_xor_sync(AT_FULL, acc, 1);
-  acc += __shfl_xor_sync(AT_FULL, acc, 2);
-  acc += __shfl_xor_sync(AT_FULL, acc, 4);
-  if (live && sub == 0) D[((long long)b * H + h) * n_pad + i] = acc;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Cross-attention kernels (n_k <= 96 keys: SDXL's 77 text tokens = ONE key block).
 //   With a single key block the v3 kernels spend their time in per-CTA set-up (640 CTAs x {TMEM alloc, barrier init, one
 //   128x128 tile}): 29 us per layer call for 1.6 GFLOP / 22.6 MB (HBM floor 3.5 us).  Here the loop dimension is the
@@ -893,15 +866,19 @@ attn_xfwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // LSE and D), so no merge is needed.
 constexpr int Q3_STAGES = 6;
 constexpr int Q3_SMEM = 2 * AT_TILE128 + Q3_STAGES * 2 * AT_TILE64 + 1024;
+constexpr int DQ3_SMEM = Q3_SMEM + AT_TILE128;  // + the O tile: D = rowsum(dO * O) is computed here, not by a separate kernel
 
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnP p) {
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnP p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_q, bar_t, bar_full[Q3_STAGES], bar_empty[Q3_STAGES], bar_s[3], bar_p[3], bar_o;
   __shared__ uint32_t tmem_slot;
+  __shared__ float d_row[128];  // D[i] = sum_d dO[i,d] * O[i,d] of this CTA's 128 queries (was: attn_bwd_prep_kernel)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base, sdO = smem_base + AT_TILE128, sKV = smem_base + 2 * AT_TILE128;
+  const uint32_t sO = sKV + Q3_STAGES * 2 * AT_TILE64;
   const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nkb = (p.n_k + 63) / 64;
@@ -909,6 +886,7 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmO);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(smem_u32(&bar_q), 1);
@@ -938,9 +916,10 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool el = elect_one();  // warp-uniform loop, elected lane issues (see tc.cuh)
     {
       if (el) {
-      mbar_expect_tx(smem_u32(&bar_q), 2 * AT_TILE128);
+      mbar_expect_tx(smem_u32(&bar_q), 3 * AT_TILE128);
         tma_load_4d(sQ, &tmQ, smem_u32(&bar_q), 0, q0, h, b);
         tma_load_4d(sdO, &tmdO, smem_u32(&bar_q), 0, q0, h, b);
+        tma_load_4d(sO, &tmO, smem_u32(&bar_q), 0, q0, h, b);
       }
       int s = 0;
       uint32_t ph = 0;
@@ -1020,8 +999,9 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int gq = q0 + row;
     const long long sidx = ((long long)b * p.H + h) * p.n_pad + gq;
     const float L2 = p.LSE[sidx];   // n_pad is a multiple of 128: in bounds; +inf on pad rows -> P = 0
-    const float Dr = p.D[sidx];
-    {  // group 0 moves row `row` of Q, group 1 of dO, from the swizzled TMA tile into TMEM (bf16 pairs, K-major A operand)
+    {  // group 0 moves row `row` of Q, group 1 of dO, from the swizzled TMA tile into TMEM (bf16 pairs, K-major A operand);
+       // group 1 also forms D[row] = sum_d dO * O from the row it is holding and publishes it (smem for this CTA, global
+       // for the dK / dV kernel that runs next on this stream).  Pad rows are TMA zero fill: D = 0.
       mbar_wait(smem_u32(&bar_q), 0);
       const uint32_t src = (g == 0 ? sQ : sdO) + row * 128;
       uint32_t w[32];
@@ -1030,11 +1010,33 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(w[4 * c]), "=r"(w[4 * c + 1]), "=r"(w[4 * c + 2]), "=r"(w[4 * c + 3])
                      : "r"(src + ((c ^ (row & 7)) << 4)));
+      if (g == 1) {
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t o4[4];
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(o4[0]), "=r"(o4[1]), "=r"(o4[2]), "=r"(o4[3])
+                       : "r"(sO + row * 128 + ((c ^ (row & 7)) << 4)));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[4 * c + e]));
+            const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o4[e]));
+            acc0 = fmaf(a2.x, b2.x, acc0);
+            acc1 = fmaf(a2.y, b2.y, acc1);
+          }
+        }
+        const float dsum = acc0 + acc1;
+        d_row[row] = dsum;
+        if (gq < p.n_pad) p.D[sidx] = dsum;
+      }
       tmem_st32(tmem_base + 448 + g * 32 + lane_off, w);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_t));
     }
+    a3_group_sync();  // d_row[] written by group 1 is visible to group 0
+    const float Dr = d_row[row];
     int buf = g;
     uint32_t spar = 0;
     for (int j = g; j < nkb; j += 2) {
@@ -1400,15 +1402,11 @@ extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
   B2_REQUIRE(a->dO && a->D && a->dQ && a->dK && a->dV, "b2_attn_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int n_pad = b2_attn_lse_rows(a->n_q);
-  {
-    const long long threads = (long long)a->B * n_pad * a->H * 8;
-    attn_bwd_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-        (const bf16*)a->O, (const bf16*)a->dO, a->D, a->B, a->H, a->n_q, n_pad, a->ldo, a->o_bs, a->lddo, a->do_bs);
-    if ((rc = check_launch("b2_attn_bwd prep"))) return rc;
-  }
+  // D = rowsum(dO * O) is formed inside the dQ kernel (which owns whole query tiles) and written to a->D for the dK / dV
+  // kernel: the separate attn_bwd_prep_kernel launch (140 per step, 1.1 ms in profiles/r1_step_launches_v8_final.txt) is gone
   static bool configured = false;
   if (!configured) {
-    if ((rc = set_smem(attn_bwd_dq3_kernel, Q3_SMEM, "b2_attn_bwd"))) return rc;
+    if ((rc = set_smem(attn_bwd_dq3_kernel, DQ3_SMEM, "b2_attn_bwd"))) return rc;
     if ((rc = set_smem(attn_bwd_dkv3_kernel, Q3_SMEM, "b2_attn_bwd"))) return rc;
     configured = true;
   }
@@ -1417,9 +1415,10 @@ extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
   p.scale = a->scale; p.c = a->scale * 1.4426950408889634f;
   p.LSE = a->LSE; p.D = a->D;
   p.dbg = g_attn_dbg;
-  CUtensorMap tq128, tdo128, tk64, tv64, tk128, tv128, tq64, tdo64;
+  CUtensorMap tq128, tdo128, to128, tk64, tv64, tk128, tv128, tq64, tdo64;
   if ((rc = make_map_bf16_4d(&tq128, a->Q, AT_D, a->n_q, a->H, a->B, a->ldq, AT_D, a->q_bs, 64, 128, "attn Q"))) return rc;
   if ((rc = make_map_bf16_4d(&tdo128, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 128, "attn dO"))) return rc;
+  if ((rc = make_map_bf16_4d(&to128, a->O, AT_D, a->n_q, a->H, a->B, a->ldo, AT_D, a->o_bs, 64, 128, "attn O"))) return rc;
   if ((rc = make_map_bf16_4d(&tk64, a->K, AT_D, a->n_k, a->H, a->B, a->ldk, AT_D, a->k_bs, 64, 64, "attn K64"))) return rc;
   if ((rc = make_map_bf16_4d(&tv64, a->V, AT_D, a->n_k, a->H, a->B, a->ldv, AT_D, a->v_bs, 64, 64, "attn V64"))) return rc;
   if ((rc = make_map_bf16_4d(&tk128, a->K, AT_D, a->n_k, a->H, a->B, a->ldk, AT_D, a->k_bs, 64, 128, "attn K"))) return rc;
@@ -1428,8 +1427,8 @@ extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
   if ((rc = make_map_bf16_4d(&tdo64, a->dO, AT_D, a->n_q, a->H, a->B, a->lddo, AT_D, a->do_bs, 64, 64, "attn dO64"))) return rc;
   AttnP pq = p;
   pq.out0 = (bf16*)a->dQ; pq.ld0 = a->lddq; pq.bs0 = a->dq_bs;
-  (void)launch_pdl(attn_bwd_dq3_kernel, dim3((a->n_q + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)Q3_SMEM, st, tq128,
-                   tdo128, tk64, tv64, pq);
+  (void)launch_pdl(attn_bwd_dq3_kernel, dim3((a->n_q + 127) / 128, a->H, a->B), dim3(A3_THREADS), (size_t)DQ3_SMEM, st, tq128,
+                   tdo128, to128, tk64, tv64, pq);
   if ((rc = check_launch("b2_attn_bwd dq3"))) return rc;
   AttnP pk = p;
   pk.out0 = (bf16*)a->dK; pk.ld0 = a->lddk; pk.bs0 = a->dk_bs;

@@ -172,6 +172,42 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -233,6 +269,18 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, u
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// CTA-pair MMA with the A operand in TMEM (each CTA's own 128 lanes), B halves from both CTAs' shared memory
+__device__ __forceinline__ void umma_bf16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -377,6 +425,33 @@ inline int make_map_bf16_4d(CUtensorMap* tm, const void* ptr, uint64_t d0, uint6
               (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
               (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
               (unsigned long long)strides[2]);
+    return B2_ERR_TMAP;
+  }
+  return B2_OK;
+}
+
+// bf16 2-D tiled map (rank 2: the .2d TMA instructions fault on a higher-rank descriptor), SWIZZLE_128B, zero OOB fill
+inline int make_map_2d(CUtensorMap* tm, const void* ptr, uint64_t d0, uint64_t d1, long long ld, uint32_t b0, uint32_t b1,
+                       const char* name) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return B2_ERR_TMAP;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 7)) {
+    set_error("b2_gemm: operand %s violates TMA alignment (ptr %p ld %lld)", name, ptr, ld);
+    return B2_ERR_ARG;
+  }
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed: CUresult %d (dims %llu %llu, stride %llu, box %u %u)", name, (int)r,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)strides[0], b0, b1);
     return B2_ERR_TMAP;
   }
   return B2_OK;

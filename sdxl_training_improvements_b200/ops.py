@@ -246,6 +246,27 @@ def geglu_fwd(u, F):
     return z
 
 
+def xattn_q_core_ok(B, n_q, n_k, C) -> bool:
+    return bool(_lib.load().b2_xattn_q_core_ok(int(B), int(n_q), int(n_k), int(C)))
+
+
+def xattn_q_core(xn, Wq, k, v, B, n_q, n_k, scale):
+    """(Q, O, LSE) of a cross-attention: Q = xn @ Wq^T and O = softmax(Q K^T * scale) V per 64-channel head in ONE launch.
+    k, v: [B * n_k, C] column views of the grouped K / V projection (row stride = k.stride(0))."""
+    _need_cuda(xn, Wq, k, v)
+    M, Cc = xn.shape
+    H = Cc // 64
+    q = torch.empty((M, Cc), device=xn.device, dtype=bf16)
+    o = torch.empty((M, Cc), device=xn.device, dtype=bf16)
+    n_pad = int(_lib.load().b2_attn_lse_rows(int(n_q)))
+    lse = torch.empty((B, H, n_pad), device=xn.device, dtype=torch.float32)
+    _lib.check(_lib.load().b2_xattn_q_core(_p(xn), _p(Wq), _p(k), _p(v), _p(q), _p(o), _p(lse), int(B), int(n_q), int(n_k),
+                                           int(Cc), int(xn.stride(0)), int(Wq.stride(0)), Cc, Cc, int(k.stride(0)),
+                                           int(v.stride(0)), int(n_k * k.stride(0)), int(n_k * v.stride(0)), float(scale),
+                                           _stream()), "xattn_q_core")
+    return q, o, lse
+
+
 def linear_geglu_ok(M, F, K) -> bool:
     return bool(_lib.load().b2_linear_geglu_ok(int(M), int(F), int(K)))
 

@@ -318,10 +318,17 @@ class UNetEngine:
             if kv_bwd is not None:
                 self.tape.append(kv_bwd)
             Wq = st.w(f"{pfx}.to_q.weight", Cc, Cc)
-            q = ops.linear_fwd(xn.d, Wq)
             kv, dkv = self._kv_slices[pfx]  # [B*77, 2C] views of the grouped projection (computed once per forward)
-            q_t, k_t, v_t = q, kv[:, :Cc], kv[:, Cc:]
-        O, lse = ops.attn_fwd(q_t, k_t, v_t, B, heads, n, nk, scale)
+            k_t, v_t = kv[:, :Cc], kv[:, Cc:]
+            if ops.xattn_q_core_ok(B, n, nk, Cc):
+                # ONE launch: to_q GEMM with the 77-key attention core in its epilogue (csrc/xattn.cu); Q is written for the
+                # backward pass but never read back
+                q, O, lse = ops.xattn_q_core(xn.d, Wq, k_t, v_t, B, n, nk, scale)
+            else:
+                q = ops.linear_fwd(xn.d, Wq)
+            q_t = q
+        if is_self or not ops.xattn_q_core_ok(B, n, nk, Cc):
+            O, lse = ops.attn_fwd(q_t, k_t, v_t, B, heads, n, nk, scale)
         Oa = Act(O)
         out = self.linear(Oa, f"{pfx}.to_out.0.weight", Cc, Cc, f"{pfx}.to_out.0.bias", residual=res)
 

@@ -45,6 +45,10 @@ class ShapeOnlyOps:
         return torch.empty_like(x), self._e(x, x.shape[0], dtype=torch.float32), self._e(x, x.shape[0], dtype=torch.float32)
 
     @staticmethod
+    def xattn_q_core_ok(B, n_q, n_k, C):
+        return False  # the fused and the two-launch cross-attention record the same tape
+
+    @staticmethod
     def linear_geglu_ok(M, F, K):
         return F % 128 == 0  # which path is taken does not change the tape length
 
