@@ -134,6 +134,10 @@ int b2_ln_fwd(const void* x, void* y, const void* gamma, const void* beta, float
 int b2_ln_bwd(const void* x, const void* dy, void* dx, const void* gamma, const float* mean,
               const float* rstd, float* dgb /* float[2*C], accumulated */, int M, int C, int accumulate_dx,
               void* stream);
+/* The same in two independently launchable halves (parts: 1 = dx, 2 = dgamma / dbeta accumulation, 3 = both): the host runs
+ * them on two streams (they read the same x / dy). */
+int b2_ln_bwd_parts(const void* x, const void* dy, void* dx, const void* gamma, const float* mean, const float* rstd,
+                    float* dgb, int M, int C, int accumulate_dx, int parts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attention softmax over materialised logits (round-1 path; the fused flash kernel supersedes it).
@@ -178,6 +182,11 @@ typedef struct b2_attn_args {
 int b2_attn_lse_rows(int n_q);
 int b2_attn_fwd(const b2_attn_args* args, void* stream);
 int b2_attn_bwd(const b2_attn_args* args, void* stream);
+/* Cross-attention backward (n_k <= 80 keys) in one pass: dQ, dK, dV from a single recomputation of P; b2_attn_bwd routes to it
+ * when b2_xattn_bwd_ok().  Same argument struct and semantics as b2_attn_bwd (D is not used).  B2_XATTN_BWD_GENERIC=1 forces the
+ * generic two-kernel path. */
+int b2_xattn_bwd_ok(int B, int H, int n_q, int n_k);
+int b2_xattn_bwd(const b2_attn_args* args, void* stream);
 /* Profiling hook: device buffer of 32 uint64 per-phase cycle counters accumulated by the forward kernel (NULL = off). */
 int b2_attn_set_debug(void* counters);
 

@@ -57,6 +57,8 @@ SIGNATURES = {
     "b2_attn_fwd": [C.POINTER(AttnArgs), c_p],
     "b2_attn_bwd": [C.POINTER(AttnArgs), c_p],
     "b2_attn_set_debug": [c_p],
+    "b2_xattn_bwd_ok": [i32, i32, i32, i32],
+    "b2_xattn_bwd": [C.POINTER(AttnArgs), c_p],
     "b2_xattn_q_core_ok": [i32, i32, i32, i32],
     "b2_xattn_set_debug": [c_p],
     "b2_xattn_q_core": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, f32, c_p],
@@ -69,6 +71,7 @@ SIGNATURES = {
     "b2_gn_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, c_p, c_p, i32, c_p],
     "b2_ln_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, f32, c_p],
     "b2_ln_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, i32, c_p],
+    "b2_ln_bwd_parts": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, i32, i32, c_p],
     "b2_softmax_fwd": [c_p, c_p, i64, i32, i64, i64, c_p],
     "b2_softmax_bwd": [c_p, c_p, c_p, i64, i32, i64, i64, f32, c_p],
     "b2_geglu_fwd": [c_p, c_p, i64, i32, c_p],

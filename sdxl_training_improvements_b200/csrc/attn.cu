@@ -1396,10 +1396,14 @@ extern "C" int b2_attn_fwd(const b2_attn_args* a, void* stream) {
   return check_launch("b2_attn_fwd(persistent)");
 }
 
+extern "C" int b2_xattn_bwd_ok(int B, int H, int n_q, int n_k);
+extern "C" int b2_xattn_bwd(const b2_attn_args* a, void* stream);
+
 extern "C" int b2_attn_bwd(const b2_attn_args* a, void* stream) {
   int rc = check_common(a, "b2_attn_bwd");
   if (rc) return rc;
   B2_REQUIRE(a->dO && a->D && a->dQ && a->dK && a->dV, "b2_attn_bwd: null pointer");
+  if (b2_xattn_bwd_ok(a->B, a->H, a->n_q, a->n_k)) return b2_xattn_bwd(a, stream);  // cross-attention: one-pass kernel (xattn_bwd.cu)
   cudaStream_t st = (cudaStream_t)stream;
   const int n_pad = b2_attn_lse_rows(a->n_q);
   // D = rowsum(dO * O) is formed inside the dQ kernel (which owns whole query tiles) and written to a->D for the dK / dV

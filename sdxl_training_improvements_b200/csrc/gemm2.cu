@@ -77,6 +77,7 @@ struct Gemm2P {
   // rounds both to bf16 exactly as the un-fused path stores them, writes them to u (the backward pass needs both) and
   // writes bf16(h * gelu(g)) to Z — the separate GEGLU kernel's 2F-wide re-read of u disappears.
   int geglu, gg_F;
+  int res_prefetch;  // 1: residual tiles travel one chunk ahead (default); B2_GEMM_NO_RES_PREFETCH=1 restores the per-chunk load
 };
 
 // 2-D TMA load / store / reduce, cluster address mapping and the epilogue named barrier: tc.cuh (shared with xattn.cu)
@@ -325,6 +326,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool row_ok = gm < p.M;
       const bf16* bias_row =
           p.bias ? p.bias + (long long)((row_ok ? gm : 0) / p.bias_rows_per_group) * p.bias_group_stride : nullptr;
+      // Residual / accumulate operand: its 16 KB tile per 64-column chunk comes in by TMA.  Issued at the chunk's own start, the
+      // load's latency (L2 hit ~0.4 us, HBM ~0.8 us) was exposed once per chunk — five times per 256 x 320 tile, on every
+      // "+= gradient" GEMM and every Linear with a fused residual.  Now the first chunk's load leaves BEFORE the wait for the
+      // accumulator and each chunk prefetches the next one's tile into the other staging buffer.
+      auto chunk_full = [&](int c0) { return (min(64, ncols - c0) == 64) || (n_tile + p.BN >= p.N); };
+      if (p.has_res && p.res_prefetch && !p.geglu && et == 0 && chunk_full(0)) {
+        const uint32_t sb = chunk_i & 1;
+        tma_store_wait_read<1>();  // the store that last read this staging buffer (two chunks ago) has drained
+        mbar_expect_tx(smem_u32(&bar_res[sb]), G2_EPI_BYTES);
+        tma_load_2d(smem_epi + sb * G2_EPI_BYTES, &tmR, smem_u32(&bar_res[sb]), n_tile, m_base);
+      }
       mbar_wait<true>(smem_u32(&bar_acc_full[buf]), use & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * 256 + lane_off;
@@ -391,12 +403,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (full_chunk) {
           const uint32_t sbuf = chunk_i & 1;
           const uint32_t stage = smem_epi + sbuf * G2_EPI_BYTES;
-          // the previous TMA store that read this staging buffer must have drained
           if (et == 0) {
-            tma_store_wait_read<1>();
-            if (p.has_res) {
+            if (p.has_res && !p.res_prefetch) {
+              tma_store_wait_read<1>();
               mbar_expect_tx(smem_u32(&bar_res[sbuf]), G2_EPI_BYTES);
               tma_load_2d(stage, &tmR, smem_u32(&bar_res[sbuf]), n0, m_base);
+            } else if (p.has_res) {
+              // this chunk's residual tile is already in flight (tile start / previous chunk); send the next chunk's after
+              // the store that last read the OTHER staging buffer (the previous chunk's) has drained
+              if (c0 + 64 < ncols && chunk_full(c0 + 64)) {
+                tma_store_wait_read<0>();
+                mbar_expect_tx(smem_u32(&bar_res[sbuf ^ 1]), G2_EPI_BYTES);
+                tma_load_2d(smem_epi + (sbuf ^ 1) * G2_EPI_BYTES, &tmR, smem_u32(&bar_res[sbuf ^ 1]), n0 + 64, m_base);
+              }
+            } else {
+              tma_store_wait_read<1>();  // the previous TMA store that read this staging buffer must have drained
             }
           }
           epi_bar_sync();
@@ -605,6 +626,8 @@ static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
     p.splits = 1;
     p.kb_per = (p.K + G2_BK - 1) / G2_BK;
   }
+  static const bool no_res_prefetch = getenv("B2_GEMM_NO_RES_PREFETCH") != nullptr;
+  p.res_prefetch = no_res_prefetch ? 0 : 1;
   p.wide = p.BN == G2_WIDE_BN ? 1 : 0;
   p.stages = p.wide ? G2_WIDE_STAGES : p.geglu ? G2_STAGES - 1 : G2_STAGES;  // GEGLU: 5 stages + a third staging tile
   p.stage_bytes = p.wide ? G2_WIDE_STAGE_BYTES : G2_STAGE_BYTES;

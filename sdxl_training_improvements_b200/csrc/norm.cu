@@ -684,16 +684,26 @@ extern "C" int b2_ln_fwd(const void* x, void* y, const void* gamma, const void* 
   return check_launch("ln_fwd");
 }
 
+extern "C" int b2_ln_bwd_parts(const void* x, const void* dy, void* dx, const void* gamma, const float* mean,
+                               const float* rstd, float* dgb, int M, int C, int accumulate_dx, int parts, void* stream);
 extern "C" int b2_ln_bwd(const void* x, const void* dy, void* dx, const void* gamma, const float* mean,
                          const float* rstd, float* dgb, int M, int C, int accumulate_dx, void* stream) {
-  B2_REQUIRE(x && dy && dx && gamma && mean && rstd && dgb, "b2_ln_bwd: null pointer");
+  return b2_ln_bwd_parts(x, dy, dx, gamma, mean, rstd, dgb, M, C, accumulate_dx, 3, stream);
+}
+
+// parts: 1 = dx only, 2 = dgamma / dbeta only, 3 = both.  The two halves are independent kernels over the same x / dy: the
+// host issues them on two streams so that they share their reads in L2 instead of running back to back (unet.py).
+extern "C" int b2_ln_bwd_parts(const void* x, const void* dy, void* dx, const void* gamma, const float* mean,
+                               const float* rstd, float* dgb, int M, int C, int accumulate_dx, int parts, void* stream) {
+  B2_REQUIRE(x && dy && gamma && mean && rstd && (dx || !(parts & 1)) && (dgb || !(parts & 2)) && (parts & 3),
+             "b2_ln_bwd: null pointer");
   B2_REQUIRE(C % 8 == 0, "b2_ln_bwd: C %% 8 != 0");
   cudaStream_t st = (cudaStream_t)stream;
   const int nv = (C / 8 + 31) / 32;
   // Opt-in (B2_LN_BWD_FUSED=1): one fused pass, one wave of CTAs.  Measured SLOWER inside the training step than the two
   // kernels below (130.9 vs 126.5 ms per step, profiles/r1_bench_n1_v8_notes.txt): at C = 1280 the column sums cost 80
   // more registers per thread, occupancy drops to 8 warps per SM and the row loop becomes latency-bound.
-  const bool fused = getenv("B2_LN_BWD_FUSED") != nullptr;
+  const bool fused = getenv("B2_LN_BWD_FUSED") != nullptr && parts == 3;
   if (nv <= 5 && fused) {
     const int per_sm = nv <= 3 ? 2 : 1;
     const int slots = num_sms() * per_sm;
@@ -712,15 +722,19 @@ extern "C" int b2_ln_bwd(const void* x, const void* dy, void* dx, const void* ga
 #define B2_LN_BWD(NV)                                                                                                 \
   ln_bwd_dx_reg_kernel<NV><<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, (const bf16*)gamma, \
                                                         mean, rstd, M, C, accumulate_dx)
-  if (nv <= 2) B2_LN_BWD(2);
-  else if (nv <= 3) B2_LN_BWD(3);
-  else if (nv <= 5) B2_LN_BWD(5);
-  else
-    ln_bwd_dx_kernel<<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, (const bf16*)gamma, mean,
-                                                  rstd, M, C, accumulate_dx);
+  if (parts & 1) {
+    if (nv <= 2) B2_LN_BWD(2);
+    else if (nv <= 3) B2_LN_BWD(3);
+    else if (nv <= 5) B2_LN_BWD(5);
+    else
+      ln_bwd_dx_kernel<<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, (const bf16*)gamma, mean,
+                                                    rstd, M, C, accumulate_dx);
+    int rc1 = check_launch("ln_bwd_dx");
+    if (rc1) return rc1;
+  }
 #undef B2_LN_BWD
-  int rc = check_launch("ln_bwd_dx");
-  if (rc) return rc;
+  if (!(parts & 2)) return B2_OK;
+  int rc = B2_OK;
   const int colblocks = (C + 63) / 64;
   int rows_per_cta = (int)(((long long)M * colblocks + 4LL * num_sms() - 1) / (4LL * num_sms()));
   if (rows_per_cta < 128) rows_per_cta = 128;

@@ -178,13 +178,14 @@ def ln_fwd(x, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def ln_bwd(x, dy, gamma, mean, rstd, dgb, dx=None, accumulate=False):
+def ln_bwd(x, dy, gamma, mean, rstd, dgb, dx=None, accumulate=False, parts=3):
+    """parts: 1 = dx only, 2 = dgamma / dbeta accumulation into `dgb` only, 3 = both (two kernels either way)."""
     M, Cc = x.shape
-    if dx is None:
+    if dx is None and parts & 1:
         dx = torch.empty_like(x)
         accumulate = False
-    _lib.check(_lib.load().b2_ln_bwd(_p(x), _p(dy), _p(dx), _p(gamma), _p(mean), _p(rstd), _p(dgb), M, Cc,
-                                    int(accumulate), _stream()), "ln_bwd")
+    _lib.check(_lib.load().b2_ln_bwd_parts(_p(x), _p(dy), _p(dx), _p(gamma), _p(mean), _p(rstd), _p(dgb), M, Cc,
+                                          int(accumulate), int(parts), _stream()), "ln_bwd")
     return dx
 
 

@@ -15,6 +15,8 @@ accumulation and the single NCCL all-reduce operate on.
 from __future__ import annotations
 
 import math
+import os
+from contextlib import contextmanager
 from types import SimpleNamespace
 from typing import Callable, Dict, List, Optional
 
@@ -60,6 +62,12 @@ class UNetEngine:
         self.tape: List[Callable[[], None]] = []
         self._ws: Dict[str, torch.Tensor] = {}
         self._ws_retired: List[torch.Tensor] = []
+        # Backward pass: the weight-gradient GEMM (+ bias column sum) of a layer and its input-gradient GEMM are independent.
+        # They are issued on two streams (fork after dy, join right after the pair), so that inside the captured CUDA graph
+        # they are parallel branches: the second persistent kernel's CTAs take over SMs as the first one's retire — no launch
+        # gap between the two, the tail of one filled by the head of the other.  B2_BWD_OVERLAP=0 issues them back to back.
+        self._overlap = os.environ.get("B2_BWD_OVERLAP", "1") != "0" and store.flat.is_cuda
+        self._side: Optional[torch.cuda.Stream] = None
         st = store
         for pfx in self._attn_prefixes():
             assert st.adjacent(f"{pfx}.attn1.to_q.weight", f"{pfx}.attn1.to_k.weight", f"{pfx}.attn1.to_v.weight")
@@ -67,6 +75,24 @@ class UNetEngine:
 
     def _attn_prefixes(self):
         return sorted({n.rsplit(".attn1.", 1)[0] for n, _ in self.store.specs if ".attn1.to_q." in n})
+
+    @contextmanager
+    def _side_branch(self):
+        """`with self._side_branch():` — the enclosed launches run on the side stream, ordered after everything issued so far
+        on the current stream; `self._join()` makes the current stream wait for them."""
+        if not self._overlap:
+            yield
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.store.flat.device)
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            yield
+
+    def _join(self):
+        if self._overlap and self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
 
     # ------------------------------------------------------------------ workspaces
     def ws(self, key: str, numel: int, dtype) -> torch.Tensor:
@@ -125,12 +151,16 @@ class UNetEngine:
 
         def bwd():
             dy = out.g
-            ops.linear_wgrad(dy, x.d, st.g(wname, N, K), accumulate=True)
-            if bname:
-                ops.colsum_f32(dy, st.gs(bname))
+            gW = st.g(wname, N, K)
+            gb = st.gs(bname) if bname else None
+            with self._side_branch():  # weight + bias gradients beside the input gradient
+                ops.linear_wgrad(dy, x.d, gW, accumulate=True)
+                if bname:
+                    ops.colsum_f32(dy, gb)
             if need_dx:
                 buf, acc = _gslot(x)
                 ops.linear_dgrad(dy, Wt, buf, acc)
+            self._join()
             if residual is not None:
                 self._add_grad(residual, dy)
 
@@ -147,10 +177,13 @@ class UNetEngine:
 
         def bwd():
             dy = u.g
-            ops.linear_wgrad(dy, x.d, st.g(wname, 2 * F, K), accumulate=True)
-            ops.colsum_f32(dy, st.gs(bname))
+            gW, gb = st.g(wname, 2 * F, K), st.gs(bname)
+            with self._side_branch():
+                ops.linear_wgrad(dy, x.d, gW, accumulate=True)
+                ops.colsum_f32(dy, gb)
             buf, acc = _gslot(x)
             ops.linear_dgrad(dy, Wt, buf, acc)
+            self._join()
 
         self.tape.append(bwd)
         return u, z
@@ -183,7 +216,11 @@ class UNetEngine:
 
         def bwd():
             buf, acc = _gslot(x)
-            ops.ln_bwd(x.d, out.g, gamma, mean, rstd, self._norm_dgb(wname, bname, Cc), buf, acc)
+            dgb = self._norm_dgb(wname, bname, Cc)
+            with self._side_branch():  # dgamma / dbeta beside dx: two kernels over the same x / dy
+                ops.ln_bwd(x.d, out.g, gamma, mean, rstd, dgb, None, False, parts=2)
+            ops.ln_bwd(x.d, out.g, gamma, mean, rstd, dgb, buf, acc, parts=1)
+            self._join()
 
         self.tape.append(bwd)
         return out
@@ -224,7 +261,8 @@ class UNetEngine:
             # the gradient view is taken HERE, not in forward: ParamStore logs when each gradient is written (dp.py)
             gWk = st.g(wname, Cout, K) if gWk_given is None else gWk_given
             if implicit:
-                ops.conv3x3_wgrad(dy, x.d, gWk, B, H, W, Cin, Cout, accumulate=True)
+                with self._side_branch():  # joined at the end of this closure
+                    ops.conv3x3_wgrad(dy, x.d, gWk, B, H, W, Cin, Cout, accumulate=True)
             else:
                 colb = ops.im2col3x3(x.d, B, H, W, Cin, stride, up, out=self.ws("col", M * K, bf16).view(M, K))
                 ops.gemm_raw(dy, colb, gWk, N, K, M, a_mn=True, b_mn=True, lda=N, ldb=K, ldd=K, accumulate=True,
@@ -246,6 +284,8 @@ class UNetEngine:
                     dcol = self.ws("dcol", M * K, bf16).view(M, K)
                     ops.gemm_raw(dy, Wk, dcol, M, K, N, b_mn=True, lda=N, ldb=K, ldd=K)
                     ops.col2im3x3(dcol, buf, B, H, W, Cin, stride, up, accumulate=acc)
+            if implicit:
+                self._join()
             if residual is not None:
                 self._add_grad(residual, dy)
 
@@ -343,11 +383,16 @@ class UNetEngine:
             ops.attn_bwd(q_t, k_t, v_t, O, lse, dO, dq_t, dk_t, dv_t, B, heads, n, nk, scale)
             buf, acc = _gslot(xn)
             if is_self:
-                ops.linear_wgrad(dqkv, xn.d, st.g(f"{pfx}.to_q.weight", 3 * Cc, Cc), accumulate=True)
+                gW = st.g(f"{pfx}.to_q.weight", 3 * Cc, Cc)
+                with self._side_branch():
+                    ops.linear_wgrad(dqkv, xn.d, gW, accumulate=True)
                 ops.linear_dgrad(dqkv, Wqkv, buf, acc)
             else:
-                ops.linear_wgrad(dq, xn.d, st.g(f"{pfx}.to_q.weight", Cc, Cc), accumulate=True)
+                gW = st.g(f"{pfx}.to_q.weight", Cc, Cc)
+                with self._side_branch():
+                    ops.linear_wgrad(dq, xn.d, gW, accumulate=True)
                 ops.linear_dgrad(dq, Wq, buf, acc)
+            self._join()
                 # the K/V projection weight gradients of all blocks run as ONE GEMM per width (see _project_context)
 
         # attention-core backward must run after to_out's backward (already on the tape) -> append
