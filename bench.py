@@ -520,6 +520,7 @@ def run_ours(args):
     gms = {s_: trainer._micro_graphs[(B, s_[0], s_[1], 77)] for s_ in shapes} if use_graph else {}
     gm = gms[shapes[0]] if use_graph else None
     og = trainer._opt_graph if use_graph else None
+    timed_pos0 = seq_pos[0]
     timed_seq = [next_shape() for _ in range(K * A)]
     sampler = ClockSampler(local)
     sampler.start()
@@ -553,6 +554,11 @@ def run_ours(args):
     for _ in range(2):  # untimed: bring the host-side path (pinned copies, RNG, graph launch) back into cache after loop (1)
         api_step()
     barrier()
+    # same timestep / bucket sequence as loop (1): under the power cap a step whose loss hits the reference's clamp (zero
+    # gradients through the backward GEMMs) draws less power and runs at higher clocks, so the two loops must see the same mix
+    torch.manual_seed(5 + rank)
+    if mixed:
+        seq_pos[0] = timed_pos0
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     last_loss = None

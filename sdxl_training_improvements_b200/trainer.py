@@ -233,6 +233,8 @@ class GraphedMicroStep:
         self.loss: Optional[torch.Tensor] = None
         self.static_last: Dict[str, torch.Tensor] = {}
         self.launches_per_replay = 0
+        self._pin: Optional[torch.Tensor] = None
+        self._pin_i = 0
 
     def _run(self):
         return self.core.step_no_autograd(grad_scale_dev=self.grad_scale, latents=self.latents, ctx=self.ctx,
@@ -297,17 +299,32 @@ class GraphedMicroStep:
         torch.cuda.synchronize()
         return self
 
+    def _h2d(self, dst: torch.Tensor, src: torch.Tensor):
+        """dst <- src without stalling the host: an async copy from PAGEABLE host memory makes the driver synchronise the
+        stream first (the host then sits behind the 11 ms optimizer graph and the GPU idles while the next micro-step is
+        being enqueued: measured ~2 ms per step end to end).  Small host tensors (timesteps, sigmas, weights) therefore go
+        through a pinned staging row; two rows alternate so that a row is never rewritten while its copy may be in flight."""
+        if src.is_cuda or src.is_pinned():
+            dst.copy_(src, non_blocking=True)
+            return
+        if self._pin is None or self._pin.shape[1] < dst.numel():
+            self._pin = torch.zeros(8, max(16, dst.numel()), dtype=torch.float32).pin_memory()
+        row = self._pin[self._pin_i % 8, :dst.numel()].view(dst.shape)
+        self._pin_i += 1
+        row.copy_(src)
+        dst.copy_(row, non_blocking=True)
+
     def load(self, latents, ctx, pooled, time_ids, t_embed, sig_or_t, weight=None, grad_scale: float = 1.0):
         self.latents.copy_(latents, non_blocking=True)
         self.ctx.copy_(ctx, non_blocking=True)
         self.pooled.copy_(pooled, non_blocking=True)
         self.time_ids.copy_(time_ids, non_blocking=True)
-        self.t_embed.copy_(t_embed, non_blocking=True)
-        self.sig_or_t.copy_(sig_or_t, non_blocking=True)
+        self._h2d(self.t_embed, t_embed)
+        self._h2d(self.sig_or_t, sig_or_t)
         if weight is None:
             self.weight.fill_(1.0)
         else:
-            self.weight.copy_(weight, non_blocking=True)
+            self._h2d(self.weight, weight)
         self.grad_scale.fill_(float(grad_scale))
 
     def replay(self, last: bool = False) -> torch.Tensor:
@@ -422,6 +439,13 @@ class _StepBase:
         self._graph_pool = None                      # shared by all captured shapes
         self.max_graphed_shapes = int(kwargs.get("max_graphed_shapes", 8))
         self.uncaptured_micro_steps = 0              # micro-steps cuda_graph mode ran un-captured (new shape mid-window / cap)
+        # graph mode driven by _execute_training_step: the optimizer graph is enqueued right behind the last micro-step's
+        # graph, BEFORE the host reads the step's loss / metrics (which travel through a pinned buffer + an event) — the GPU
+        # does not idle while Python builds the metrics dict and walks the (no-op) autograd backward
+        self._opt_after_micro = False
+        self._opt_done_early = False
+        self._host_vals: Optional[torch.Tensor] = None   # pinned [7] float64: loss, stats[0:6]
+        self._host_event: Optional[torch.cuda.Event] = None
         self._opt_graph: Optional[GraphedOptimizerStep] = None
         self._pending_grad_scale = 1.0
 
@@ -436,6 +460,9 @@ class _StepBase:
         self._pending_grad_scale = 1.0 / self.gradient_accumulation_steps if accumulate else 1.0
         # the backward pass of the last micro-step hands finished gradient chunks to the data-parallel exchange
         self.core.dp_last = (not accumulate) or is_last_accumulation_step
+        self._opt_after_micro = (self.cuda_graph and hasattr(self.optimizer, "fused_step")
+                                 and ((not accumulate) or is_last_accumulation_step))
+        self._opt_done_early = False
         try:
             out = self.compute_loss(batch) if not isinstance(self, B200FlowMatchingTrainer) else self.compute_loss(self.model, batch)
             loss = out["loss"]
@@ -451,8 +478,10 @@ class _StepBase:
             raise
         finally:
             self.core.dp_last = False
-        if not accumulate or is_last_accumulation_step:
+            self._opt_after_micro = False
+        if (not accumulate or is_last_accumulation_step) and not self._opt_done_early:
             self.optimizer_step()
+        self._opt_done_early = False
         return out["loss"].detach(), out["metrics"]
 
     def _graphed_loss(self, t: Dict[str, torch.Tensor], t_embed, sig_or_t, weight) -> torch.Tensor:
@@ -476,7 +505,8 @@ class _StepBase:
                 loss = self.core.step_no_autograd(grad_scale=self._pending_grad_scale, latents=t["latents"], ctx=t["ctx"],
                                                   pooled=t["pooled"], time_ids=t["time_ids"],
                                                   t_embed=t_embed.to(self.unet.device), sig_or_t=sig_or_t.to(self.unet.device),
-                                                  weight=weight, loss_scale=1.0)
+                                                  weight=None if weight is None else weight.to(self.unet.device),
+                                                  loss_scale=1.0)
                 return _PrecomputedBackward.apply(loss.reshape(()), self.core._anchor)
             torch.cuda.empty_cache()
             if self._graph_pool is None:
@@ -491,7 +521,30 @@ class _StepBase:
         gm.load(t["latents"], t["ctx"], t["pooled"], t["time_ids"], t_embed, sig_or_t, weight, self._pending_grad_scale)
         loss = gm.replay(last=self.core.dp_last)
         self.core.last = {"numel": t["latents"].numel()}
-        return _PrecomputedBackward.apply(loss.reshape(()), self.core._anchor)
+        out = _PrecomputedBackward.apply(loss.reshape(()), self.core._anchor)
+        if self._opt_after_micro:
+            # loss + metric sums -> pinned host memory behind the micro-step, then the optimizer graph right away
+            if self._host_vals is None:
+                self._host_vals = torch.zeros(7, dtype=torch.float64).pin_memory()
+                self._host_event = torch.cuda.Event()
+                self._dev_vals = torch.zeros(7, device=self.unet.device, dtype=torch.float64)
+            self._dev_vals[0:1].copy_(out.detach().reshape(1))
+            self._dev_vals[1:7].copy_(self.core.stats)
+            self._host_vals.copy_(self._dev_vals, non_blocking=True)
+            self._host_event.record()
+            self.optimizer_step()
+            self._opt_done_early = True
+        return out
+
+    def _read_loss_and_stats(self, loss: torch.Tensor):
+        """(python float loss, list of the six metric sums): ONE host read per micro-step.  After _graphed_loss() enqueued the
+        optimizer graph early the values come from the pinned buffer (waiting only for the micro-step, not the update)."""
+        if self._opt_done_early and self._host_event is not None:
+            self._host_event.synchronize()
+            v = self._host_vals.tolist()
+            return v[0], v[1:]
+        st = self.core.stats.tolist()
+        return float(loss.detach()), st
 
     def _init_dp(self):
         """Data parallel: gradients are exchanged over NVSwitch peer memory beside the backward pass (dp.py); if that
@@ -573,19 +626,20 @@ class B200DDPMTrainer(_StepBase):
         weight = None
         if self.min_snr_gamma is not None:  # B3: intended per-sample broadcast
             snr = (self.noise_scheduler.sigma_data / sig) ** 2
-            weight = torch.minimum(snr, torch.ones_like(snr) * float(self.min_snr_gamma)).float().to(dev)
+            weight = torch.minimum(snr, torch.ones_like(snr) * float(self.min_snr_gamma)).float()  # host; staged below
         tw = _tag_weight_mean(batch)
         if self.cuda_graph and noise is None and tw is None:
             loss = self._graphed_loss(t, timesteps.float(), sig, weight)
         else:
             loss = self.core.loss_fn(latents=t["latents"], ctx=t["ctx"], pooled=t["pooled"], time_ids=t["time_ids"],
-                                     t_embed=timesteps.float().to(dev), sig_or_t=sig.to(dev), weight=weight,
+                                     t_embed=timesteps.float().to(dev), sig_or_t=sig.to(dev),
+                                     weight=None if weight is None else weight.to(dev),
                                      loss_scale=1.0 if tw is None else tw,
                                      noise=None if noise is None else noise.to(dev).to(bf16).float().reshape(-1).contiguous())
-        st = self.core.stats.tolist()  # one D2H for all metrics (the reference does 5 .item() syncs)
+        loss_f, st = self._read_loss_and_stats(loss)  # one D2H for all metrics (the reference does 5 .item() syncs)
         n = self.core.last["numel"]
         metrics = {
-            "loss": float(loss.detach()),
+            "loss": loss_f,
             "lr": self._lr(),
             "timestep_mean": float(timesteps.float().mean()),
             "noise_scale": st[0] / n,
@@ -620,16 +674,17 @@ class B200FlowMatchingTrainer(_StepBase):
         loss_scale = 1.0
         if "tag_weights" in batch:  # flow_matching_trainer.py:326-328
             loss_scale = float(batch["tag_weights"].to(bf16).float().mean())
-        tf = t.float().to(dev)
         if self.cuda_graph and x0 is None and loss_scale == 1.0:
-            loss = self._graphed_loss(tb, tf, tf, weight)
+            th = t.float()  # host tensor: the graph path stages it through pinned memory (no stream-synchronising copy)
+            loss = self._graphed_loss(tb, th, th, weight)
         else:
+            tf = t.float().to(dev)
             loss = self.core.loss_fn(latents=tb["latents"], ctx=tb["ctx"], pooled=tb["pooled"], time_ids=tb["time_ids"],
                                      t_embed=tf, sig_or_t=tf, weight=weight, loss_scale=loss_scale,
                                      noise=None if x0 is None else x0.to(dev).to(bf16).float().reshape(-1).contiguous())
-        st = self.core.stats.tolist()
+        loss_f, st = self._read_loss_and_stats(loss)
         metrics = {
-            "loss": float(loss.detach()),
+            "loss": loss_f,
             "x0_norm": math.sqrt(st[1]),
             "x1_norm": math.sqrt(st[5]),
             "time_mean": float(t.float().mean()),

@@ -149,7 +149,7 @@ def test_ddpm_tag_weights_scale_the_loss():
     assert abs(lk / float(r1.out["loss"]) - TAG_MEAN) < 1e-3  # same inputs, same noise: the ratio is the weight
     g_w = dict(r.net.named_parameters())[PROBE].grad.float()
     g_1 = dict(r1.net.named_parameters())[PROBE].grad.float()
-    assert float((g_w - TAG_MEAN * g_1).norm() / g_w.norm()) < 2e-2
+    assert float((g_w - TAG_MEAN * g_1).norm() / g_w.norm()) < 4e-2  # two bf16 backward passes with differently scaled dL/dpred
 
 
 def test_ddpm_tag_weights_under_cuda_graph_mode_use_the_eager_kernels():
