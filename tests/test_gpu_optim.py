@@ -49,7 +49,7 @@ def test_adamw_bf16_bit_exact_vs_reference_golden(ops, mode, rng_mode):
     assert torch.equal(p.cpu(), case["decay_state"]["p"])
 
 
-def test_adamw_bf16_philox_rounding_is_neighbouring_and_unbiased(ops):
+def test_adamw_bf16_hash_rounding_is_neighbouring_and_unbiased(ops):
     from oracle import adamw_bf16 as O
     n = 1 << 20
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -81,6 +81,41 @@ def test_adamw_bf16_philox_rounding_is_neighbouring_and_unbiased(ops):
     p3, m3, v3, s3 = p0.clone(), m0.clone(), v0.clone(), s0.clone()
     ops.adamw_bf16(p3, gr, m3, v3, s3, lr=1e-3, step=6, seed_offset=so)
     assert not torch.equal(m3, m)
+    # the parameter rounding draws from the SECOND random word: with g = 0 and exp_avg = 0 the update is p <- SR(p + shift)
+    # exactly (shift passes through its own rounding unchanged), so its bias is measurable from the outputs alone
+    z = torch.zeros(n, device="cuda", dtype=bf16)
+    s_big = (torch.randn(n, device="cuda", generator=g) * 3e-4).to(bf16)
+    p4, m4, v4, s4 = p0.clone(), z.clone(), v0.clone(), s_big.clone()
+    ops.adamw_bf16(p4, z, m4, v4, s4, lr=1e-3, step=5, seed_offset=so)
+    exact_p = p0.float() + s_big.float()
+    down = (exact_p.view(torch.int32) & -65536).view(torch.float32)
+    ulp = (((exact_p.view(torch.int32) & -65536) + 65536).view(torch.float32) - down).abs()
+    err = (p4.float() - exact_p).double()
+    assert bool(((p4.float() == down) | ((p4.float() - down).abs() == ulp)).all()), "p is not a bf16 neighbour of p + shift"
+    assert abs(float(err.mean())) < 0.02 * float(ulp.double().mean()), f"p rounding biased: {float(err.mean()):.3e}"
+    # and the two words are not the same draw: rounding direction of exp_avg and of p must be (nearly) uncorrelated
+    up_m = (mk != lo[1]).double()
+    up_p = (p4.float().cpu() != down.cpu()).double()
+    corr = float(((up_m - up_m.mean()) * (up_p - up_p.mean())).mean() / (up_m.std() * up_p.std() + 1e-12))
+    assert abs(corr) < 0.01, f"rounding directions of exp_avg and p correlate: {corr:.4f}"
+
+
+def test_adamw_denominator_all_bf16_patterns(ops):
+    """optim.cu computes bf16(bf16(sqrt v) + eps) with `sqrt.approx.f32`; the result must equal the IEEE statement for
+    EVERY bf16 input (adamw_bfloat16/__init__.py:176 `exp_avg_sq.sqrt().add_(eps)` on bf16 tensors)."""
+    from sdxl_training_improvements_b200 import _lib
+    allv = torch.arange(65536, dtype=torch.int32).to(torch.int16).cuda().view(bf16)
+    for eps in (1e-8, 1e-6, 1e-3):
+        fast, ieee = torch.empty_like(allv), torch.empty_like(allv)
+        _lib.check(_lib.load().b2_adamw_denom_test(allv.data_ptr(), fast.data_ptr(), ieee.data_ptr(), allv.numel(), eps, None),
+                   "denom_test")
+        torch.cuda.synchronize()
+        a, b = fast.view(torch.int16), ieee.view(torch.int16)
+        nan = torch.isnan(fast) & torch.isnan(ieee)
+        assert bool(((a == b) | nan).all()), f"eps={eps}: {(~((a == b) | nan)).sum().item()} bf16 patterns differ"
+        ref = (allv.float().sqrt().to(bf16).float() + eps).to(bf16)
+        ok = (ref.view(torch.int16) == b) | (torch.isnan(ref) & torch.isnan(ieee))
+        assert bool(ok.all()), "IEEE leg disagrees with torch"
 
 
 def test_adamw_bf16_optimizer_class_on_tiny_unet(ops):
