@@ -290,12 +290,14 @@ int b2_adamw(void* p, float* master /* fp32 master weights or NULL */, const voi
  * torch.nn.utils.clip_grad_norm_).  18 bytes of HBM traffic per parameter.
  *   as_written = 1 keeps add_stochastic_'s operand order as the reference wrote it (exp_avg <- SR(g + (1-b1) b1 m)).
  *   rng_mode: 0 counter hash of (element, seed_offset[0], step); 1/2/3 deterministic patterns for parity tests (3: int32 [4,n] buffer).
+ *   zero_grad = 1: g is overwritten with zeros after it has been read (optimizer.zero_grad() in the same pass).
  *   step <= 0: the step is read from seed_offset[1] on the device (CUDA-graph replays; advance with b2_philox_advance).
  * b2_axpy_bf16: y <- bf16(y + alpha x) — the deferred weight decay `shift.add_(p, alpha=-decay)` (:191-192).
  * b2_adamw_denom_test: test hook — the kernel's denominator bf16(bf16(sqrt v) + eps) as computed (fast) and as IEEE. */
-int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shift, int64_t n, double lr, double beta1, double beta2,
+int b2_adamw_bf16(void* p, void* g, void* m, void* v, void* shift, int64_t n, double lr, double beta1, double beta2,
                   double eps, int step, const double* gnorm_sq, float max_norm, float grad_scale,
-                  const uint64_t* seed_offset, int as_written, int rng_mode, const int32_t* test_rand16, void* stream);
+                  const uint64_t* seed_offset, int as_written, int rng_mode, const int32_t* test_rand16, int zero_grad,
+                  void* stream);
 int b2_axpy_bf16(void* y, const void* x, int64_t n, float alpha, void* stream);
 int b2_adamw_denom_test(const void* v, void* fast, void* ieee, int n, float eps, void* stream);
 

@@ -99,7 +99,7 @@ SIGNATURES = {
     "b2_abs_sq_sums": [c_p, i32, i64, i32, i32, c_p, c_p],
     "b2_scale_bf16": [c_p, i64, c_p, f32, c_p],
     "b2_sumsq": [c_p, i64, c_p, c_p],
-    "b2_adamw_bf16": [c_p, c_p, c_p, c_p, c_p, i64, f64, f64, f64, f64, i32, c_p, f32, f32, c_p, i32, i32, c_p, c_p],
+    "b2_adamw_bf16": [c_p, c_p, c_p, c_p, c_p, i64, f64, f64, f64, f64, i32, c_p, f32, f32, c_p, i32, i32, c_p, i32, c_p],
     "b2_axpy_bf16": [c_p, c_p, i64, f32, c_p],
     "b2_adamw_denom_test": [c_p, c_p, c_p, i32, f32, c_p],
     "b2_dpx_ipc_export": [c_p, c_p, C.POINTER(i64)],

@@ -9,7 +9,8 @@
 // selects the documented intent instead).  Each torch bf16 op rounds to nearest-even; the three `*_stochastic_`
 // helpers compute in fp32 and round with SR(x) = (bits(x) + rand16) & 0xFFFF0000.
 //
-// Traffic: reads p, g, m, v, shift and writes p, m, v, shift = 18 B / parameter (46 GB for the SDXL UNet), HBM-bound.
+// Traffic: reads p, g, m, v, shift and writes p, m, v, shift = 18 B / parameter (46 GB for the SDXL UNet), HBM-bound
+// (+2 B when the gradient is zeroed in the same pass).
 // Random bits: 64 per element (4 roundings x 16 bits) from a counter-based hash — two evaluations of the "triple32" integer
 // mixer (3 multiplies + 4 xor-shifts, avalanche bias 0.02 bits) of (element index, optimizer step, seed).  Round 1 used
 // Philox4x32-7 here: ~35 integer instructions per element out of ~80 in a kernel whose ALU time (5.7 ms at perfect issue)
@@ -54,6 +55,7 @@ struct AdamBF16P {
   int dev_step;
   float max_norm, grad_scale;
   int as_written;
+  int zero_grad;
   int rng_mode;     // 0: counter hash; 1: rand16 = 0 (truncate); 2: rand16 = 0xFFFF; 3: rand16 read from `test_rand16`
                     // (int32 [4, n]: test hooks for bit-exact parity with the reference's own functions)
 };
@@ -126,9 +128,11 @@ struct AdamVec { bf16x8 p, g, m, v, s; };
 // instantiation keeps the test hooks (fixed / supplied random words, documented-intent order) on the SAME arithmetic.
 template <bool FAST>
 __global__ void __launch_bounds__(256, 2)
-adamw_bf16_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __restrict__ m, bf16* __restrict__ v,
+adamw_bf16_kernel(bf16* __restrict__ p, bf16* __restrict__ g, bf16* __restrict__ m, bf16* __restrict__ v,
                   bf16* __restrict__ sh, long long n, AdamBF16P a, const double* __restrict__ gnorm_sq,
                   const uint64_t* __restrict__ seed_offset, uint64_t step, const int32_t* __restrict__ test_rand16) {
+  // a.zero_grad: the gradient vector is overwritten with zeros once it has been read (optimizer.zero_grad() folded in:
+  // +2 B / parameter of writes here instead of a separate 5 GB fill)
   float clip = a.grad_scale;
   if (gnorm_sq && a.max_norm > 0.f) {
     const float norm = (float)sqrt(*gnorm_sq) * a.grad_scale;
@@ -197,6 +201,7 @@ adamw_bf16_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __rest
     st8(m + q * 8, pack8(fm));
     st8(v + q * 8, pack8(fv));
     st8(sh + q * 8, pack8(fs));
+    if (a.zero_grad) st8(g + q * 8, zero8());
     cur = nxt;
   }
   // tail (n % 8 elements), one thread
@@ -221,6 +226,7 @@ adamw_bf16_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __rest
       m[i] = __float2bfloat16_rn(fm[0]);
       v[i] = __float2bfloat16_rn(fv[0]);
       sh[i] = __float2bfloat16_rn(fs[0]);
+      if (a.zero_grad) g[i] = __float2bfloat16_rn(0.f);
     }
   }
 }
@@ -247,10 +253,10 @@ __global__ void axpy_bf16_kernel(bf16* __restrict__ y, const bf16* __restrict__ 
 
 using namespace b2;
 
-extern "C" int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shift, int64_t n, double lr, double beta1,
+extern "C" int b2_adamw_bf16(void* p, void* g, void* m, void* v, void* shift, int64_t n, double lr, double beta1,
                              double beta2, double eps, int step, const double* gnorm_sq, float max_norm, float grad_scale,
                              const uint64_t* seed_offset, int as_written, int rng_mode, const int32_t* test_rand16,
-                             void* stream) {
+                             int zero_grad, void* stream) {
   B2_REQUIRE(p && g && m && v && shift && n > 0 && (step >= 1 || seed_offset), "b2_adamw_bf16: bad args");
   B2_REQUIRE(!((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                 reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(shift)) & 15),
@@ -265,13 +271,13 @@ extern "C" int b2_adamw_bf16(void* p, const void* g, void* m, void* v, void* shi
   a.step_size = (float)(-lr * sqrt(1.0 - pow(beta2, (double)step)));
   a.lr = lr; a.b2d = beta2; a.dev_step = step >= 1 ? 0 : 1;
   a.max_norm = max_norm; a.grad_scale = grad_scale;
-  a.as_written = as_written; a.rng_mode = rng_mode;
+  a.as_written = as_written; a.rng_mode = rng_mode; a.zero_grad = zero_grad;
   long long blocks = ((n >> 3) + 255) / 256;
   const long long cap = 2LL * num_sms();  // resident CTAs only: the prefetch pipeline runs across grid-stride iterations
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   auto kern = (rng_mode == 0 && as_written) ? adamw_bf16_kernel<true> : adamw_bf16_kernel<false>;
-  kern<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)p, (const bf16*)g, (bf16*)m, (bf16*)v, (bf16*)shift, n, a,
+  kern<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)p, (bf16*)g, (bf16*)m, (bf16*)v, (bf16*)shift, n, a,
                                                            gnorm_sq, seed_offset, (uint64_t)step, test_rand16);
   return check_launch("adamw_bf16");
 }

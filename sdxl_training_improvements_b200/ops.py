@@ -431,12 +431,14 @@ def adamw(p, master, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_de
 
 
 def adamw_bf16(p, g, m, v, shift, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, gnorm_sq=None, max_norm=0.0,
-               grad_scale=1.0, seed_offset=None, as_written=True, rng_mode=0, test_rand16=None):
-    """Fused AdamWBF16 step over flat bf16 buffers (reference: adamw_bfloat16/__init__.py:150-197)."""
+               grad_scale=1.0, seed_offset=None, as_written=True, rng_mode=0, test_rand16=None, zero_grad=False):
+    """Fused AdamWBF16 step over flat bf16 buffers (reference: adamw_bfloat16/__init__.py:150-197); `zero_grad` clears
+    `g` in the same pass (the `optimizer.zero_grad()` that follows every step)."""
     _need_cuda(p, g, m, v, shift)
     _lib.check(_lib.load().b2_adamw_bf16(_p(p), _p(g), _p(m), _p(v), _p(shift), p.numel(), lr, beta1, beta2, eps,
                                         int(step), _p(gnorm_sq), float(max_norm), float(grad_scale), _p(seed_offset),
-                                        int(as_written), int(rng_mode), _p(test_rand16), _stream()), "adamw_bf16")
+                                        int(as_written), int(rng_mode), _p(test_rand16), int(bool(zero_grad)), _stream()),
+               "adamw_bf16")
 
 
 def axpy_bf16(y, x, alpha):

@@ -368,8 +368,11 @@ class GraphedOptimizerStep:
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            opt.fused_step(max_norm=self.max_norm, grad_scale=self.gscale, _in_graph=True)
-            opt.zero_grad()
+            if isinstance(opt, B200AdamWBF16):  # zero_grad() folded into the optimizer kernel (no separate 5 GB fill)
+                opt.fused_step(max_norm=self.max_norm, grad_scale=self.gscale, _in_graph=True, zero_grad=True)
+            else:
+                opt.fused_step(max_norm=self.max_norm, grad_scale=self.gscale, _in_graph=True)
+                opt.zero_grad()
         self.launches_per_replay = _lib.launch_count() - n0
         torch.cuda.synchronize()
         return self
@@ -566,6 +569,9 @@ class _StepBase:
             if self._opt_graph is None:
                 self._opt_graph = GraphedOptimizerStep(self.optimizer, self.clip_grad_norm, 1.0 / self.world_size).capture()
             self._opt_graph.replay()
+            return
+        if isinstance(self.optimizer, B200AdamWBF16):
+            self.optimizer.fused_step(max_norm=self.clip_grad_norm, grad_scale=1.0 / self.world_size, zero_grad=True)
             return
         if hasattr(self.optimizer, "fused_step"):
             self.optimizer.fused_step(max_norm=self.clip_grad_norm, grad_scale=1.0 / self.world_size)
@@ -795,7 +801,7 @@ class B200AdamWBF16:
         self._min_headroom = 0.0  # steps can skip the per-tensor scan while no accumulator can reach the threshold
 
     def fused_step(self, max_norm: float = 0.0, grad_scale: float = 1.0, rng_mode: int = 0, test_rand16=None,
-                   _in_graph: bool = False):
+                   _in_graph: bool = False, zero_grad: bool = False):
         st = self.unet.store
         g = self.param_groups[0]
         gn = None
@@ -807,7 +813,7 @@ class B200AdamWBF16:
         ops.adamw_bf16(st.flat, st.grad, self.exp_avg, self.exp_avg_sq, self.shift, lr=g["lr"], beta1=g["betas"][0],
                        beta2=g["betas"][1], eps=g["eps"], step=0, gnorm_sq=gn, max_norm=max_norm or 0.0,
                        grad_scale=grad_scale, seed_offset=self.seed_offset, as_written=self.as_written,
-                       rng_mode=rng_mode, test_rand16=test_rand16)
+                       rng_mode=rng_mode, test_rand16=test_rand16, zero_grad=zero_grad)
         if not _in_graph:
             self.after_graph_step()
 
@@ -836,9 +842,7 @@ class B200AdamWBF16:
             self._min_headroom = self.decay_threshold - max(self.accumulated_decay.values())
 
     def step(self, zero_grad: bool = False):
-        self.fused_step()
-        if zero_grad:
-            self.zero_grad()
+        self.fused_step(zero_grad=zero_grad)  # the kernel clears the gradient vector behind its own read
 
     def zero_grad(self, set_to_none: bool = False):
         self.unet.store.grad.zero_()

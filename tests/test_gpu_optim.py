@@ -81,6 +81,14 @@ def test_adamw_bf16_hash_rounding_is_neighbouring_and_unbiased(ops):
     p3, m3, v3, s3 = p0.clone(), m0.clone(), v0.clone(), s0.clone()
     ops.adamw_bf16(p3, gr, m3, v3, s3, lr=1e-3, step=6, seed_offset=so)
     assert not torch.equal(m3, m)
+    # zero_grad folded into the kernel: same update, gradient vector cleared (odd length: the scalar tail too)
+    for cnt in (n, n - 3):
+        p5, m5, v5, s5, g5 = p0[:cnt].clone(), m0[:cnt].clone(), v0[:cnt].clone(), s0[:cnt].clone(), gr[:cnt].clone()
+        p6, m6, v6, s6 = p0[:cnt].clone(), m0[:cnt].clone(), v0[:cnt].clone(), s0[:cnt].clone()
+        ops.adamw_bf16(p5, g5, m5, v5, s5, lr=1e-3, step=5, seed_offset=so, zero_grad=True)
+        ops.adamw_bf16(p6, gr[:cnt].clone(), m6, v6, s6, lr=1e-3, step=5, seed_offset=so)
+        assert torch.equal(p5, p6) and torch.equal(m5, m6) and torch.equal(v5, v6) and torch.equal(s5, s6)
+        assert int(g5.view(torch.int16).count_nonzero()) == 0
     # the parameter rounding draws from the SECOND random word: with g = 0 and exp_avg = 0 the update is p <- SR(p + shift)
     # exactly (shift passes through its own rounding unchanged), so its bias is measurable from the outputs alone
     z = torch.zeros(n, device="cuda", dtype=bf16)

@@ -34,9 +34,12 @@ def timed(fn, reps=5):
     return min(ts), sum(ts) / reps
 
 
-for label, kw in (("no clip", dict()), ("clip active", dict(gnorm_sq=gn, max_norm=1.0))):
+for label, kw in (("no clip", dict()), ("clip active", dict(gnorm_sq=gn, max_norm=1.0)),
+                  ("no clip, zero_grad folded in: 20 B/param", dict(zero_grad=True))):
     best, avg = timed(lambda: ops.adamw_bf16(p, gr, m, v, sh, lr=1e-5, step=3, seed_offset=so, **kw))
     print(f"adamw_bf16 n={n} ({label}): best {best:.3f} ms avg {avg:.3f} ms = {18 * n / best / 1e6:.0f} GB/s")
 a = torch.empty(n, device="cuda", dtype=bf16)
+best, avg = timed(lambda: gr.zero_())
+print(f"torch zero_ of the gradient vector {2 * n / 1e9:.2f} GB: best {best:.3f} ms = {2 * n / best / 1e6:.0f} GB/s (write only)")
 best, avg = timed(lambda: a.copy_(p))
 print(f"torch copy {2 * n / 1e9:.2f} GB: best {best:.3f} ms = {4 * n / best / 1e6:.0f} GB/s (read + write)")
