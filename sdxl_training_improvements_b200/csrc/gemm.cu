@@ -266,6 +266,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
 }
 
 int gemm2_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc);  // gemm2.cu: persistent CTA-pair fast path
+bool smallm_try(const b2_gemm_args* a, cudaStream_t st, int* out_rc);  // smallm.cu: few-row linears on CUDA cores
 
 }  // namespace b2
 
@@ -276,6 +277,7 @@ extern "C" int b2_gemm(const b2_gemm_args* a, void* stream) {
   B2_REQUIRE(a->nb_lo >= 1 && a->nb_hi >= 1 && (long long)a->nb_lo * a->nb_hi <= 65535, "b2_gemm: bad batch");
   {
     int rc2 = 0;
+    if (smallm_try(a, reinterpret_cast<cudaStream_t>(stream), &rc2)) return rc2;
     if (gemm2_try(a, reinterpret_cast<cudaStream_t>(stream), &rc2)) return rc2;
   }
   int bn = a->tile_n;

@@ -119,7 +119,10 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  static const bool off = getenv("B2_PDL") == nullptr;  // opt-in: measured no gain inside CUDA graphs (130.5 vs 129.1 ms/step)
+  // on unless B2_PDL=0.  Same-box A/B inside the graphed step (round 2, gpurun_out/r2C_bench_pdl*.log): 118.26 / 117.75 ms off,
+  // 118.20 / 117.25 ms on — a few tenths of a millisecond: the step runs under the power cap, so hidden set-up time mostly
+  // comes back as a lower SM clock (1 860 -> 1 800 MHz in the same runs).
+  static const bool off = getenv("B2_PDL") != nullptr && atoi(getenv("B2_PDL")) == 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

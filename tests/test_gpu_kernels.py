@@ -82,6 +82,43 @@ def test_gemm_dgrad_wgrad(ops, M, N, K):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("M,N,K", [(4, 1280, 1280), (4, 320, 1280), (4, 1280, 2816), (1, 1280, 320), (8, 640, 1280), (3, 72, 64)])
+def test_few_row_linears(ops, M, N, K, monkeypatch):
+    """smallm.cu: the per-sample-row linears (time_embedding / add_embedding / time_emb_proj; diffusers
+    ResnetBlock2D.forward `self.time_emb_proj(self.nonlinearity(temb))`) forward, dgrad, wgrad on CUDA cores, every epilogue
+    option of b2_gemm, against fp32 torch and against the tensor-core GEMM path for the same call."""
+    x = _rand(M, K, seed=11)
+    W = _rand(N, K, scale=1 / math.sqrt(K), seed=12)
+    b = _rand(N, seed=13)
+    r = _rand(M, N, seed=14)
+    row = _rand(N, seed=15)
+    dy = _rand(M, N, seed=16)
+    ref = x.float() @ W.float().t()
+    _close(ops.linear_fwd(x, W), ref, what="fwd plain")
+    _close(ops.linear_fwd(x, W, bias=b, residual=r), ref + b.float() + r.float(), what="fwd bias+res")
+    y = torch.empty(M, N, device="cuda", dtype=bf16)
+    ops.gemm_raw(x, W, y, M, N, K, lda=K, ldb=K, ldd=N, bias=b, residual=row, ldr=0)  # broadcast row via ldr = 0
+    _close(y, ref + b.float() + row.float(), what="fwd broadcast residual row")
+    yf = torch.full((M, N), 0.5, device="cuda", dtype=torch.float32)
+    ops.gemm_raw(x, W, yf, M, N, K, lda=K, ldb=K, ldd=N, alpha=0.25, accumulate=True, out_fp32=True)
+    assert float((yf - (0.25 * ref + 0.5)).abs().max()) < 1e-3, "fwd alpha / accumulate / fp32 out"
+    # input gradient, plain and accumulated into an existing bf16 buffer
+    dref = dy.float() @ W.float()
+    _close(ops.linear_dgrad(dy, W), dref, atol=2e-2, what="dgrad")
+    dx = _rand(M, K, seed=17)
+    dx0 = dx.float().clone()
+    ops.linear_dgrad(dy, W, dx, accumulate=True)
+    _close(dx, dx0 + dref, atol=3e-2, what="dgrad accumulate")
+    # weight gradient
+    wref = dy.float().t() @ x.float()
+    dW = torch.zeros(N, K, device="cuda", dtype=bf16)
+    ops.linear_wgrad(dy, x, dW, accumulate=False)
+    _close(dW, wref, atol=2e-2, what="wgrad")
+    ops.linear_wgrad(dy, x, dW, accumulate=True)
+    _close(dW, 2 * wref, rtol=2 ** -6, atol=4e-2, what="wgrad accumulate")
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("tile_n", [64, 128, 256])
 def test_gemm_tile_variants(ops, tile_n):
     M, N, K = 512, 512, 448
