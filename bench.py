@@ -151,8 +151,16 @@ def _time_gemm_roofline(ops, peaks):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    agg = None  # all gemm2 launches of one training step, from the committed ncu launch list joined with the shape log
+    ap = os.path.join(ROOT, "profiles", "gemm_aggregate.json")
+    if os.path.exists(ap):
+        try:
+            agg = json.load(open(ap))
+            agg["frac_of_burst_peak"] = round(agg["tflops"] / peaks["burst"], 4)
+        except Exception:
+            agg = None
     return {"bound": "tensor", "achieved": round(ach, 1), "peak": peaks["burst"], "unit": "TFLOP/s",
-            "frac": round(ach / peaks["burst"], 4), "traffic": traffic,
+            "frac": round(ach / peaks["burst"], 4), "traffic": traffic, "aggregate_all_gemm_launches": agg,
             "kernel": "gemm2_kernel (cta_group::2, 256xBN tiles) on M=4096,N=10240,K=1280 (GEGLU up-projection), "
                       f"{flops / 1e9:.1f} GFLOP/launch, {ms * 1e3:.1f} us/launch, peak = {peaks['src']} burst bf16"}
 
@@ -200,7 +208,7 @@ def _extra_rooflines(ops, peaks):
             out[tag] = {"fwd_us": round(tf, 1), "fwd_tflops": round(ff / tf / 1e6, 1),
                         "fwd_frac_of_peak": round(ff / tf / 1e6 / peaks["burst"], 3),
                         "bwd_us": round(tb, 1), "bwd_tflops": round(2.5 * ff / tb / 1e6, 1),
-                        "bwd_frac_of_peak": round(2.5 * ff / tb / 1e6 / peaks["burst"], 3), "bound": "ex2 (XU pipe ~75 % busy inside the key-block loop) + per-CTA set-up / tear-down outside it (26-53 % of the kernel time), d=64"}
+                        "bwd_frac_of_peak": round(2.5 * ff / tb / 1e6 / peaks["burst"], 3), "bound": "d=64: ex2 (16 384 per 128x128 block = 1 024 XU cycles) and the S MMA's shared-memory operand reads (128 B/clk) both sit at ~1 000 cycles per block; measured block period ~1 450-1 600 (hand-off latency between softmax groups and the MMA thread) - profiles/r2_attention_notes.md"}
         # cross-attention, C=1280, n=1024, 77 keys: the core alone (HBM-bound) and the fused-block definition
         B, H, n, nk = 4, 20, 1024, 77
         Cc = H * 64
@@ -211,18 +219,30 @@ def _extra_rooflines(ops, peaks):
         bo = torch.zeros(Cc, device="cuda", dtype=bf)
         kv = torch.randn(B * nk, 2 * Cc, device="cuda").to(bf)
         kk, vv = kv[:, :Cc], kv[:, Cc:]
-        qb = torch.empty_like(x)
+        qb = torch.randn_like(x)
         ob = torch.empty_like(x)
         yb = torch.empty_like(x)
         tcore = _graph_time_us(lambda: ops.attn_fwd(qb, kk, vv, B, H, n, nk, 0.125, out=ob))
 
-        def block():
+        fused = bool(ops.xattn_q_core_ok(B, n, nk, Cc))
+
+        def block():  # what UNetEngine.attention() launches for one cross-attention layer call
             xn, _, _ = ops.ln_fwd(x, gamma, beta, 1e-5)
-            ops.linear_fwd(xn, Wq, out=qb)
-            ops.attn_fwd(qb, kk, vv, B, H, n, nk, 0.125, out=ob)
-            ops.linear_fwd(ob, Wo, bias=bo, residual=x, out=yb)
+            if fused:  # to_q GEMM + 77-key core in one launch (csrc/xattn.cu)
+                _, o_, _ = ops.xattn_q_core(xn, Wq, kk, vv, B, n, nk, 0.125)
+            else:
+                ops.linear_fwd(xn, Wq, out=qb)
+                o_ = ops.attn_fwd(qb, kk, vv, B, H, n, nk, 0.125, out=ob)[0]
+            ops.linear_fwd(o_, Wo, bias=bo, residual=x, out=yb)
 
         tblock = _graph_time_us(block)
+        tqcore = _graph_time_us(lambda: ops.xattn_q_core(x, Wq, kk, vv, B, n, nk, 0.125)) if fused else None
+        # backward of the core (dQ, dK, dV from dO): one pass, P / dS tiles in shared memory (csrc/xattn_bwd.cu)
+        ob2, lse2 = ops.attn_fwd(qb, kk, vv, B, H, n, nk, 0.125)
+        dob = torch.randn_like(x)
+        dqb, dkvb = torch.empty_like(x), torch.empty_like(kv)
+        tcore_bwd = _graph_time_us(lambda: ops.attn_bwd(qb, kk, vv, ob2, lse2, dob, dqb, dkvb[:, :Cc], dkvb[:, Cc:],
+                                                        B, H, n, nk, 0.125))
         core_flops = 4.0 * n * nk * 64 * B * H
         core_bytes = 2 * x.numel() * 2 + kv.numel() * 2
         block_flops = 2 * (2.0 * B * n * Cc * Cc) + core_flops
@@ -233,7 +253,22 @@ def _extra_rooflines(ops, peaks):
             "fused_block_us": round(tblock, 1), "fused_block_gflop": round(block_flops / 1e9, 2),
             "fused_block_tflops": round(block_flops / tblock / 1e6, 1),
             "fused_block_frac_of_peak": round(block_flops / tblock / 1e6 / peaks["burst"], 3),
-            "north_star_target_frac": 0.6, "launches_per_block": 4}
+            "north_star_target_frac": 0.6, "launches_per_block": 3 if fused else 4,
+            "q_proj_plus_core_us": round(tqcore, 1) if tqcore else None,
+            "q_proj_plus_core_tflops": round((2.0 * B * n * Cc * Cc + core_flops) / tqcore / 1e6, 1) if tqcore else None,
+            "core_bwd_us": round(tcore_bwd, 1)}
+        # GEGLU up-projection (ff1), M=4096, 2F=10240, K=1280: gate in the GEMM epilogue vs GEMM + gate kernel
+        Mg, Fg, Kg = 4096, 5120, 1280
+        xg = torch.randn(Mg, Kg, device="cuda").to(bf)
+        W1 = (torch.randn(2 * Fg, Kg, device="cuda") * 0.03).to(bf)
+        b1 = torch.zeros(2 * Fg, device="cuda", dtype=bf)
+        ug = torch.empty(Mg, 2 * Fg, device="cuda", dtype=bf)
+        gg = {"gemm_gflop": round(2.0 * Mg * 2 * Fg * Kg / 1e9, 1)}
+        if ops.linear_geglu_ok(Mg, Fg, Kg):
+            gg["fused_us"] = round(_graph_time_us(lambda: ops.linear_geglu_fwd(xg, W1, b1, Fg)), 1)
+        gg["gemm_us"] = round(_graph_time_us(lambda: ops.linear_fwd(xg, W1, bias=b1, out=ug)), 1)
+        gg["gate_kernel_us"] = round(_graph_time_us(lambda: ops.geglu_fwd(ug, Fg)), 1)
+        out["geglu_ff1"] = gg
         # implicit-GEMM 3x3 conv 640 -> 640 @ 64^2, B=4
         B, Hh, Ww, Ci, Co = 4, 64, 64, 640, 640
         M = B * Hh * Ww

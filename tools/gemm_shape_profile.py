@@ -1,5 +1,7 @@
 """Join the B2_GEMM_LOG shape log with an ncu launch list: time per GEMM / conv shape class.
-usage: python tools/gemm_shape_profile.py launches.csv shapes.log"""
+usage: python tools/gemm_shape_profile.py launches.csv shapes.log [aggregate.json]
+(the optional third argument receives {launches, ms, tflops} over ALL gemm2 launches of the profiled step — bench.py
+reports it next to the best-shape roofline fraction)"""
 import collections
 import csv
 import re
@@ -23,5 +25,10 @@ for r, s in zip(rows, shapes):
     fl[key] += 2.0 * M * N * K
 T = sum(tot.values())
 print(f"gemm2 total {T / 1e6:.2f} ms over {len(rows)} launches, {sum(fl.values()) / T / 1e3:.0f} TF/s average")
+if len(sys.argv) > 3:
+    import json
+    json.dump({"launches": len(rows), "ms": round(T / 1e6, 3), "tflops": round(sum(fl.values()) / T / 1e3, 1),
+               "source": "ncu gpu__time_duration per launch (serialised, one training step bs=4 1024^2) joined with B2_GEMM_LOG"},
+              open(sys.argv[3], "w"))
 for k, t in tot.most_common(45):
     print(f"{t / 1e6:7.2f} ms {100 * t / T:5.1f}% {cnt[k]:4d} x {t / cnt[k] / 1e3:7.1f} us {fl[k] / t / 1e3:6.0f} TF/s  {k}")
