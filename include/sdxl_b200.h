@@ -199,6 +199,7 @@ int b2_attn_set_debug(void* counters);
  * K / V: [B * n_k, ld] row-major views (head h = columns h*64..), sample stride k_bs / v_bs elements.
  * b2_xattn_q_core_ok(): C a multiple of 320, n_q a multiple of 256, n_k <= 80; other shapes: b2_gemm + b2_attn_fwd. */
 int b2_xattn_q_core_ok(int B, int n_q, int n_k, int C);
+int b2_gemm2_set_debug(void* buf);  /* clock64 trace buffer (>= 192 uint64) for tools/geglu_trace.py; NULL disables */
 int b2_xattn_set_debug(void* stamps); /* profiling hook: >= 32 uint64 clock64 stamps of CTA 0's first tile; NULL = off */
 int b2_xattn_q_core(const void* xn, const void* Wq, const void* K, const void* V, void* Q, void* O, float* LSE, int B, int n_q,
                     int n_k, int C, int64_t ldx, int64_t ldw, int64_t ldq, int64_t ldo, int64_t ldk, int64_t ldv, int64_t k_bs,

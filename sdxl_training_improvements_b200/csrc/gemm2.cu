@@ -78,7 +78,15 @@ struct Gemm2P {
   // writes bf16(h * gelu(g)) to Z — the separate GEGLU kernel's 2F-wide re-read of u disappears.
   int geglu, gg_F;
   int res_prefetch;  // 1: residual tiles travel one chunk ahead (default); B2_GEMM_NO_RES_PREFETCH=1 restores the per-chunk load
+  unsigned long long* dbg;  // optional clock64 trace of cluster 0 / CTA 0 (b2_gemm2_set_debug, tools/geglu_trace.py); NULL in production
 };
+
+static unsigned long long* g_g2_dbg = nullptr;
+__device__ __forceinline__ unsigned long long g2_clk() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
 
 // 2-D TMA load / store / reduce, cluster address mapping and the epilogue named barrier: tc.cuh (shared with xattn.cu)
 
@@ -92,6 +100,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ __align__(8) uint64_t bar_res[2];
+  __shared__ __align__(16) bf16 bias_s[2][G2_WIDE_BN];  // this tile's bias columns (double-buffered by tile parity)
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -276,8 +285,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int kb0 = split * p.kb_per, kb1 = min(num_kb_total, kb0 + p.kb_per);
         const int buf = tile_i & 1;
         const uint32_t use = (uint32_t)tile_i >> 1;
+        const bool tr = p.dbg && cluster_id == 0 && el && tile_i < 8;
+        if (tr) p.dbg[128 + tile_i * 4] = g2_clk();
         mbar_wait<true>(smem_u32(&bar_acc_empty[buf]), (use & 1) ^ 1u);
         tc_fence_after();
+        if (tr) p.dbg[128 + tile_i * 4 + 1] = g2_clk();
         const uint32_t tacc = tmem_base + buf * 256;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait<true>(smem_u32(&bar_full[stage]), phase);
@@ -301,6 +313,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         if (el) umma_commit_2sm(smem_u32(&bar_acc_full[buf]), 3);
+        if (tr) p.dbg[128 + tile_i * 4 + 2] = g2_clk();
       }
     }
   } else {
@@ -310,6 +323,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int et = row;                        // epilogue thread id 0..127
     const uint32_t lane_off = uint32_t(qd * 32) << 16;
     const uint32_t acc_empty_leader = mapa_u32(smem_u32(&bar_acc_empty[0]), 0);
+    // Hands accumulator buffer `b` back to the MMA issuer (leader CTA) as soon as its last columns are in registers — the
+    // math and the stores of the last chunk no longer hold it.  Relaxed: the tcgen05 fence orders this thread's TMEM reads
+    // before the arrive and nothing else is published through this barrier; the `.release.cluster` arrive that used to sit
+    // at the end of the tile stalled the issuing thread ~3,000 cycles behind its outstanding stores (tools/geglu_trace.py).
+    auto release_acc = [&](int b) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty_leader + b * 8) : "memory");
+    };
     int tile_i = 0;
     uint32_t chunk_i = 0;
     uint32_t res_uses[2] = {0, 0};
@@ -326,6 +349,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool row_ok = gm < p.M;
       const bf16* bias_row =
           p.bias ? p.bias + (long long)((row_ok ? gm : 0) / p.bias_rows_per_group) * p.bias_group_stride : nullptr;
+      // The bias columns of the tile go through shared memory: read straight from global inside the chunk loop, each of the
+      // 8 (GEGLU: 16) 16-byte loads per chunk exposed its full L1-miss latency to the ONE epilogue warp of its scheduler
+      // (clock64 trace, tools/geglu_trace.py: 7,500 cycles per 64-column GEGLU chunk for 1,800 instructions).  Loaded here,
+      // before the wait for the accumulator; the chunk loop's first named barrier orders the writes before the reads.
+      // Only when the CTA's 128 rows share one bias row (always, except per-sample conv bias with H*W < 128).
+      const int tb = tile_i & 1;
+      bool bias_smem = false;
+      if (p.bias) {
+        const int g_lo = m_base / p.bias_rows_per_group, g_hi = min(m_base + 127, p.M - 1) / p.bias_rows_per_group;
+        bias_smem = g_lo == g_hi;
+        if (bias_smem) {
+          const bf16* brow = p.bias + (long long)g_lo * p.bias_group_stride;
+          const int c = et * 8;
+          if (p.geglu) {
+            if (c < 256) *reinterpret_cast<uint4*>(&bias_s[tb][c]) = ld8(brow + (c < 128 ? nb * 128 + c : p.gg_F + nb * 128 + c - 128)).u;
+          } else if (c < ncols) {
+            *reinterpret_cast<uint4*>(&bias_s[tb][c]) = ld8(brow + n_tile + c).u;
+          }
+        }
+      }
       // Residual / accumulate operand: its 16 KB tile per 64-column chunk comes in by TMA.  Issued at the chunk's own start, the
       // load's latency (L2 hit ~0.4 us, HBM ~0.8 us) was exposed once per chunk — five times per 256 x 320 tile, on every
       // "+= gradient" GEMM and every Linear with a fused residual.  Now the first chunk's load leaves BEFORE the wait for the
@@ -337,52 +380,64 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_expect_tx(smem_u32(&bar_res[sb]), G2_EPI_BYTES);
         tma_load_2d(smem_epi + sb * G2_EPI_BYTES, &tmR, smem_u32(&bar_res[sb]), n_tile, m_base);
       }
+      const bool tr = p.dbg && cluster_id == 0 && leader && et == 0 && tile_i < 8;
+      if (tr) p.dbg[tile_i * 8] = g2_clk();
       mbar_wait<true>(smem_u32(&bar_acc_full[buf]), use & 1);
       tc_fence_after();
+      if (tr) p.dbg[tile_i * 8 + 1] = g2_clk();
       const uint32_t tacc = tmem_base + buf * 256 + lane_off;
       if (p.geglu) {
         // accumulator columns [0,128) = h features nb*128 .., [128,256) = the matching g features.  Three staging tiles
         // (h, g, z) per 64-column chunk: GEGLU mode runs the mainloop on 5 stages, which frees a third 16 KB buffer.
         const int nh = nb * 128;
         for (int c0 = 0; c0 < 128; c0 += 64) {
-          uint32_t vh0[32], vh1[32], vg0[32], vg1[32];
-          tmem_ld32_nowait(tacc + c0, vh0);
-          tmem_ld32_nowait(tacc + c0 + 32, vh1);
-          tmem_ld32_nowait(tacc + 128 + c0, vg0);
-          tmem_ld32_nowait(tacc + 128 + c0 + 32, vg1);
           if (et == 0) tma_store_wait_read<0>();  // the previous chunk's three TMA stores have read their staging tiles
           epi_bar_sync();
-          tmem_ld_wait();
+          if (tr) p.dbg[tile_i * 8 + 2 + 3 * (c0 >> 6)] = g2_clk();
           const uint32_t srow = smem_epi + row * 128;
+          // 32 columns of h and of g at a time: with the whole 64 + 64-column chunk in registers (128 + temporaries) ptxas
+          // had no registers left to interleave the eight independent GELU chains, and the lone epilogue warp of each
+          // scheduler ran them at ~3 cycles per instruction (tools/geglu_trace.py); TMEM loads are cheap (~50 cycles).
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t* a = g < 4 ? vh0 + g * 8 : vh1 + (g - 4) * 8;
-            const uint32_t* b = g < 4 ? vg0 + g * 8 : vg1 + (g - 4) * 8;
-            float fh[8], fg[8], tb[8];
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t vh[32], vg[32];
+            tmem_ld32_nowait(tacc + c0 + hf * 32, vh);
+            tmem_ld32_nowait(tacc + 128 + c0 + hf * 32, vg);
+            tmem_ld_wait();
+            if (c0 == 64 && hf == 1) release_acc(buf);  // the whole accumulator has been read
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { fh[j] = __uint_as_float(a[j]); fg[j] = __uint_as_float(b[j]); }
-            if (p.bias) {
-              unpack8(ld8(p.bias + nh + c0 + g * 8), tb);
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const int g = hf * 4 + g4;
+              float fh[8], fg[8], tbv[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) fh[j] += tb[j];
-              unpack8(ld8(p.bias + p.gg_F + nh + c0 + g * 8), tb);
+              for (int j = 0; j < 8; ++j) { fh[j] = __uint_as_float(vh[g4 * 8 + j]); fg[j] = __uint_as_float(vg[g4 * 8 + j]); }
+              if (p.bias) {  // GEGLU mode has one bias row for all rows: always staged
+                bf16x8 bv;
+                bv.u = *reinterpret_cast<const uint4*>(&bias_s[tb][c0 + g * 8]);
+                unpack8(bv, tbv);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) fg[j] += tb[j];
+                for (int j = 0; j < 8; ++j) fh[j] += tbv[j];
+                bv.u = *reinterpret_cast<const uint4*>(&bias_s[tb][128 + c0 + g * 8]);
+                unpack8(bv, tbv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) fg[j] += tbv[j];
+              }
+              const bf16x8 ph = pack8(fh), pg = pack8(fg);
+              unpack8(ph, fh);   // the GEGLU product is formed from the bf16 values u holds (as geglu_fwd_kernel does)
+              unpack8(pg, fg);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) fh[j] *= gelu_erf(fg[j]);
+              const bf16x8 pz = pack8(fh);
+              const uint32_t saddr = srow + ((g ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(ph.u.x), "r"(ph.u.y), "r"(ph.u.z),
+                           "r"(ph.u.w) : "memory");
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr + G2_EPI_BYTES), "r"(pg.u.x), "r"(pg.u.y),
+                           "r"(pg.u.z), "r"(pg.u.w) : "memory");
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr + 2 * G2_EPI_BYTES), "r"(pz.u.x), "r"(pz.u.y),
+                           "r"(pz.u.z), "r"(pz.u.w) : "memory");
             }
-            const bf16x8 ph = pack8(fh), pg = pack8(fg);
-            unpack8(ph, fh);   // the GEGLU product is formed from the bf16 values u holds (as geglu_fwd_kernel does)
-            unpack8(pg, fg);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) fh[j] *= gelu_erf(fg[j]);
-            const bf16x8 pz = pack8(fh);
-            const uint32_t saddr = srow + ((g ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(ph.u.x), "r"(ph.u.y), "r"(ph.u.z),
-                         "r"(ph.u.w) : "memory");
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr + G2_EPI_BYTES), "r"(pg.u.x), "r"(pg.u.y),
-                         "r"(pg.u.z), "r"(pg.u.w) : "memory");
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr + 2 * G2_EPI_BYTES), "r"(pz.u.x), "r"(pz.u.y),
-                         "r"(pz.u.z), "r"(pz.u.w) : "memory");
           }
+          if (tr) p.dbg[tile_i * 8 + 3 + 3 * (c0 >> 6)] = g2_clk();
           fence_proxy_async_smem();
           epi_bar_sync();
           if (et == 0) {
@@ -391,6 +446,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_store_2d(&tmZ, smem_epi + 2 * G2_EPI_BYTES, nh + c0, m_base);
             tma_store_commit();
           }
+          if (tr) p.dbg[tile_i * 8 + 4 + 3 * (c0 >> 6)] = g2_clk();
         }
       } else
       for (int c0 = 0; c0 < ncols; c0 += 64) {
@@ -426,6 +482,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             res_uses[sbuf]++;
           }
           tmem_ld_wait();
+          if (c0 + 64 >= ncols) release_acc(buf);
           const uint32_t srow = stage + row * 128;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -435,10 +492,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
             const bool col_ok = g * 8 < cw;
             if (bias_row && col_ok) {
-              float tb[8];
-              unpack8(ld8(bias_row + n0 + g * 8), tb);
+              float tbv[8];
+              bf16x8 bv;
+              if (bias_smem) bv.u = *reinterpret_cast<const uint4*>(&bias_s[tb][c0 + g * 8]);
+              else bv = ld8(bias_row + n0 + g * 8);
+              unpack8(bv, tbv);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += tb[j];
+              for (int j = 0; j < 8; ++j) f[j] += tbv[j];
             }
             const uint32_t saddr = srow + ((g ^ (row & 7)) << 4);
             if (p.has_res) {
@@ -469,6 +529,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         } else {
           // tile-bounded partial chunk (BN not a multiple of 64): direct 16-byte stores of the valid columns
           tmem_ld_wait();
+          if (c0 + 64 >= ncols) release_acc(buf);
           if (row_ok) {
             bf16* drow = p.D + (long long)gm * p.ldd + n0;
             const bf16* rrow = p.R ? p.R + (long long)gm * p.ldr + n0 : nullptr;
@@ -481,7 +542,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
                 if (bias_row) {
                   float tb[8];
-                  unpack8(ld8(bias_row + n0 + g * 8), tb);
+                  unpack8(ld8(bias_row + n0 + g * 8), tb);  // partial-chunk path: no named barrier here, read from global
 #pragma unroll
                   for (int j = 0; j < 8; ++j) f[j] += tb[j];
                 }
@@ -496,13 +557,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
         }
-      }
-      // accumulator buffer drained: hand it back to the MMA issuer (leader CTA)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty_leader + buf * 8)
-                     : "memory");
       }
     }
     if (et == 0) tma_store_wait_all();
@@ -632,6 +686,7 @@ static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   p.stages = p.wide ? G2_WIDE_STAGES : p.geglu ? G2_STAGES - 1 : G2_STAGES;  // GEGLU: 5 stages + a third staging tile
   p.stage_bytes = p.wide ? G2_WIDE_STAGE_BYTES : G2_STAGE_BYTES;
   if (p.splits > 1) p.has_res = 0;  // the reduce-add epilogue is the accumulation
+  p.dbg = g_g2_dbg;
   static const bool log_calls = getenv("B2_GEMM_LOG") != nullptr;
   if (log_calls)
     fprintf(stderr, "B2GEMM %s M=%d N=%d K=%d a_mn=%d b_mn=%d conv=%d BN=%d splits=%d bias=%d res=%d\n", what, p.M, p.N, p.K,
@@ -748,6 +803,12 @@ static bool conv_geom_ok(int B, int H, int W, int pix) {
 }  // namespace b2
 
 using namespace b2;
+
+/* profiling hook (tools/geglu_trace.py): >= 192 uint64 clock64 stamps of cluster 0 (epilogue thread 0 + MMA thread), NULL disables */
+extern "C" int b2_gemm2_set_debug(void* buf) {
+  b2::g_g2_dbg = reinterpret_cast<unsigned long long*>(buf);
+  return B2_OK;
+}
 
 extern "C" int b2_linear_geglu_ok(int M, int F, int K) {
   if (getenv("B2_GEGLU_UNFUSED")) return 0;

@@ -1,0 +1,59 @@
+"""clock64 trace of the GEGLU-mode GEMM (cluster 0): epilogue thread 0 and the MMA thread, first 8 tiles."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sdxl_training_improvements_b200 import _lib, ops
+
+bf = torch.bfloat16
+M, F, K = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (4096, 5120, 1280)
+x = torch.randn(M, K, device="cuda").to(bf)
+W1 = (torch.randn(2 * F, K, device="cuda") * 0.03).to(bf)
+b1 = torch.zeros(2 * F, device="cuda", dtype=bf)
+for _ in range(3):
+    ops.linear_geglu_fwd(x, W1, b1, F)
+torch.cuda.synchronize()
+buf = torch.zeros(256, device="cuda", dtype=torch.int64)
+_lib.load().b2_gemm2_set_debug(buf.data_ptr())
+ops.linear_geglu_fwd(x, W1, b1, F)
+torch.cuda.synchronize()
+_lib.load().b2_gemm2_set_debug(None)
+t = buf.tolist()
+t0 = min(v for v in t if v > 0)
+print(f"M={M} F={F} K={K}  (cycles relative to the first stamp; mainloop of one 256x256 tile = {K // 64 * 512} tensor cycles)")
+print("epilogue thread 0: tile | wait acc start, acc ready | c0: smem free + tmem ld, math done, stores issued | c1: ... ")
+for i in range(8):
+    r = t[i * 8:i * 8 + 8]
+    if r[0] == 0:
+        continue
+    print(f"  tile {i}: " + " ".join(f"{v - t0:7d}" for v in r) + f"   | acc wait {r[1] - r[0]:6d}  c0: wait {r[2] - r[1]:5d} math {r[3] - r[2]:5d} store {r[4] - r[3]:5d}"
+          f"  c1: wait {r[5] - r[4]:5d} math {r[6] - r[5]:5d} store {r[7] - r[6]:5d}  total {r[7] - r[1]:6d}")
+print("MMA thread: tile | before acc_empty wait, after, last commit issued")
+for i in range(8):
+    r = t[128 + i * 4:128 + i * 4 + 3]
+    if r[0] == 0:
+        continue
+    print(f"  tile {i}: " + " ".join(f"{v - t0:7d}" for v in r) + f"   | wait {r[1] - r[0]:6d} issue {r[2] - r[1]:6d}")
+
+# plain mode (no gate): is the epilogue (time between "acc ready" of tile i and "wait acc start" of tile i+1) shorter than the mainloop?
+for (M2, N2, K2, res) in ((4096, 10240, 1280, False), (4096, 5120, 1280, False), (4096, 1280, 5120, True), (16384, 640, 5120, False)):
+    x2 = torch.randn(M2, K2, device="cuda").to(bf)
+    W2 = (torch.randn(N2, K2, device="cuda") * 0.03).to(bf)
+    bb = torch.zeros(N2, device="cuda", dtype=bf)
+    r2 = torch.randn(M2, N2, device="cuda").to(bf) if res else None
+    o2 = torch.empty(M2, N2, device="cuda", dtype=bf)
+    for _ in range(3):
+        ops.linear_fwd(x2, W2, bias=bb, residual=r2, out=o2)
+    torch.cuda.synchronize()
+    buf.zero_()
+    _lib.load().b2_gemm2_set_debug(buf.data_ptr())
+    ops.linear_fwd(x2, W2, bias=bb, residual=r2, out=o2)
+    torch.cuda.synchronize()
+    _lib.load().b2_gemm2_set_debug(None)
+    t = buf.tolist()
+    print(f"plain M={M2} N={N2} K={K2} residual={res}: mainloop {K2 // 64 * 512} tensor cycles per 256x256 tile")
+    for i in range(7):
+        e, e1, m = t[i * 8:i * 8 + 2], t[(i + 1) * 8:(i + 1) * 8 + 2], t[128 + i * 4:128 + i * 4 + 3]
+        if e[0] == 0 or e1[0] == 0:
+            continue
+        print(f"  tile {i}: epilogue busy {e1[0] - e[1]:6d} (then waits {e1[1] - e1[0]:6d} for the next accumulator) | MMA thread: waits {m[1] - m[0]:6d} for a free accumulator, issues for {m[2] - m[1]:6d}")
