@@ -88,6 +88,49 @@ __device__ __forceinline__ unsigned long long g2_clk() {
   return t;
 }
 
+// One full 64-column chunk of the plain epilogue: accumulator columns (fp32, in registers) * alpha (+ bias columns staged in
+// shared memory) (+ residual tile already in the staging buffer) -> bf16 -> staging buffer (128-byte swizzled rows).
+// Specialised on what is present: written with run-time flags inside the column-group loop the same work was 41 branches
+// and 16 reconvergence pairs per chunk, and the lone epilogue warp of each scheduler needed 1,400 cycles for ~520
+// instructions (clock64 trace, tools/geglu_trace.py).  All shared-memory reads are issued before the first st.shared.
+template <bool RES, bool BIAS>
+__device__ __forceinline__ void epi_chunk_fast(const uint32_t* v0, const uint32_t* v1, float alpha, uint32_t srow, int row,
+                                               const bf16* bias_cols) {
+  bf16x8 rv[8], bv[8];
+  if (RES) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(rv[g].u.x), "=r"(rv[g].u.y), "=r"(rv[g].u.z), "=r"(rv[g].u.w)
+                   : "r"(srow + ((g ^ (row & 7)) << 4)));
+  }
+  if (BIAS) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) bv[g].u = *reinterpret_cast<const uint4*>(bias_cols + g * 8);
+  }
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t* v = g < 4 ? v0 + g * 8 : v1 + (g - 4) * 8;
+    float f[8], t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) * alpha;
+    if (BIAS) {
+      unpack8(bv[g], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += t[j];
+    }
+    if (RES) {
+      unpack8(rv[g], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += t[j];
+    }
+    const bf16x8 o = pack8(f);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((g ^ (row & 7)) << 4)), "r"(o.u.x), "r"(o.u.y),
+                 "r"(o.u.z), "r"(o.u.w)
+                 : "memory");
+  }
+}
+
 // 2-D TMA load / store / reduce, cluster address mapping and the epilogue named barrier: tc.cuh (shared with xattn.cu)
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
@@ -483,39 +526,50 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           tmem_ld_wait();
           if (c0 + 64 >= ncols) release_acc(buf);
+          if (tr && c0 < 128) p.dbg[tile_i * 8 + 2 + 3 * (c0 >> 6)] = g2_clk();
           const uint32_t srow = stage + row * 128;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t* v = g < 4 ? v0 + g * 8 : v1 + (g - 4) * 8;
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-            const bool col_ok = g * 8 < cw;
-            if (bias_row && col_ok) {
-              float tbv[8];
-              bf16x8 bv;
-              if (bias_smem) bv.u = *reinterpret_cast<const uint4*>(&bias_s[tb][c0 + g * 8]);
-              else bv = ld8(bias_row + n0 + g * 8);
-              unpack8(bv, tbv);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += tbv[j];
-            }
-            const uint32_t saddr = srow + ((g ^ (row & 7)) << 4);
+          if (cw == 64 && (!bias_row || bias_smem)) {
+            const bf16* bias_cols = &bias_s[tb][c0];
             if (p.has_res) {
-              bf16x8 rv;
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(rv.u.x), "=r"(rv.u.y), "=r"(rv.u.z), "=r"(rv.u.w)
-                           : "r"(saddr));
-              float tr[8];
-              unpack8(rv, tr);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += tr[j];
+              if (bias_row) epi_chunk_fast<true, true>(v0, v1, p.alpha, srow, row, bias_cols);
+              else epi_chunk_fast<true, false>(v0, v1, p.alpha, srow, row, bias_cols);
+            } else {
+              if (bias_row) epi_chunk_fast<false, true>(v0, v1, p.alpha, srow, row, bias_cols);
+              else epi_chunk_fast<false, false>(v0, v1, p.alpha, srow, row, bias_cols);
             }
-            const bf16x8 o = pack8(f);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(o.u.x), "r"(o.u.y), "r"(o.u.z),
-                         "r"(o.u.w)
-                         : "memory");
+          } else {
+            // narrow last chunk of the matrix, or a per-sample bias whose rows change inside this CTA's slab
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint32_t* v = g < 4 ? v0 + g * 8 : v1 + (g - 4) * 8;
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+              const bool col_ok = g * 8 < cw;
+              if (bias_row && col_ok) {
+                float tbv[8];
+                unpack8(bias_smem ? ld8(&bias_s[tb][c0 + g * 8]) : ld8(bias_row + n0 + g * 8), tbv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += tbv[j];
+              }
+              const uint32_t saddr = srow + ((g ^ (row & 7)) << 4);
+              if (p.has_res) {
+                bf16x8 rv;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(rv.u.x), "=r"(rv.u.y), "=r"(rv.u.z), "=r"(rv.u.w)
+                             : "r"(saddr));
+                float tr8[8];
+                unpack8(rv, tr8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += tr8[j];
+              }
+              const bf16x8 o = pack8(f);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(o.u.x), "r"(o.u.y), "r"(o.u.z),
+                           "r"(o.u.w)
+                           : "memory");
+            }
           }
+          if (tr && c0 < 128) p.dbg[tile_i * 8 + 3 + 3 * (c0 >> 6)] = g2_clk();
           fence_proxy_async_smem();
           epi_bar_sync();
           if (et == 0) {
@@ -525,6 +579,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               tma_store_2d(&tmD, stage, n0, m_base);
             tma_store_commit();
           }
+          if (tr && c0 < 128) p.dbg[tile_i * 8 + 4 + 3 * (c0 >> 6)] = g2_clk();
           ++chunk_i;
         } else {
           // tile-bounded partial chunk (BN not a multiple of 64): direct 16-byte stores of the valid columns

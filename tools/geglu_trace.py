@@ -36,7 +36,8 @@ for i in range(8):
     print(f"  tile {i}: " + " ".join(f"{v - t0:7d}" for v in r) + f"   | wait {r[1] - r[0]:6d} issue {r[2] - r[1]:6d}")
 
 # plain mode (no gate): is the epilogue (time between "acc ready" of tile i and "wait acc start" of tile i+1) shorter than the mainloop?
-for (M2, N2, K2, res) in ((4096, 10240, 1280, False), (4096, 5120, 1280, False), (4096, 1280, 5120, True), (16384, 640, 5120, False)):
+import bench
+for (M2, N2, K2, res) in ((4096, 10240, 1280, False), (4096, 3840, 1280, False), (16384, 5120, 640, False), (16384, 1920, 640, False), (16384, 640, 640, True), (16384, 640, 2560, True)):
     x2 = torch.randn(M2, K2, device="cuda").to(bf)
     W2 = (torch.randn(N2, K2, device="cuda") * 0.03).to(bf)
     bb = torch.zeros(N2, device="cuda", dtype=bf)
@@ -51,9 +52,12 @@ for (M2, N2, K2, res) in ((4096, 10240, 1280, False), (4096, 5120, 1280, False),
     torch.cuda.synchronize()
     _lib.load().b2_gemm2_set_debug(None)
     t = buf.tolist()
-    print(f"plain M={M2} N={N2} K={K2} residual={res}: mainloop {K2 // 64 * 512} tensor cycles per 256x256 tile")
-    for i in range(7):
+    us = bench._graph_time_us(lambda: ops.linear_fwd(x2, W2, bias=bb, residual=r2, out=o2))
+    print(f"plain M={M2} N={N2} K={K2} residual={res}: {us:.1f} us = {2.0 * M2 * N2 * K2 / us / 1e6:.0f} TFLOP/s; mainloop {K2 // 64 * 512} tensor cycles per 256x256 tile")
+    for i in range(2, 5):
         e, e1, m = t[i * 8:i * 8 + 2], t[(i + 1) * 8:(i + 1) * 8 + 2], t[128 + i * 4:128 + i * 4 + 3]
         if e[0] == 0 or e1[0] == 0:
             continue
+        r = t[i * 8:i * 8 + 8]
+        print(f"  tile {i}: chunk 0: sync+ld {r[2] - r[1]:5d} math {r[3] - r[2]:5d} fence+bar+store {r[4] - r[3]:5d} | chunk 1: sync+ld {r[5] - r[4]:5d} math {r[6] - r[5]:5d} fence+bar+store {r[7] - r[6]:5d}")
         print(f"  tile {i}: epilogue busy {e1[0] - e[1]:6d} (then waits {e1[1] - e1[0]:6d} for the next accumulator) | MMA thread: waits {m[1] - m[0]:6d} for a free accumulator, issues for {m[2] - m[1]:6d}")
