@@ -158,6 +158,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int halfn = p.BN >> 1;
   const uint32_t stage_tx = G2_A_BYTES + halfn * 128;  // bytes this CTA's two operand tiles occupy
 
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[187] = g2_clk();  // kernel entry
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -181,7 +182,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(tmem_slot);
-  pdl_wait();               // everything above overlapped the previous kernel's tail; from here on we touch its outputs
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[191] = g2_clk();  // set-up done (barriers, TMEM, cluster sync)
+  pdl_wait();
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[190] = g2_clk();  // predecessor kernel complete               // everything above overlapped the previous kernel's tail; from here on we touch its outputs
   pdl_launch_dependents();  // let the next kernel begin ITS set-up as our CTAs retire
 
   if (warp == 0) {
@@ -614,7 +617,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
+    if (p.dbg && cluster_id == 0 && leader && et == 0) p.dbg[189] = g2_clk();  // last store issued
     if (et == 0) tma_store_wait_all();
+    if (p.dbg && cluster_id == 0 && leader && et == 0) p.dbg[188] = g2_clk();  // all stores complete
   }
 
   tc_fence_before();

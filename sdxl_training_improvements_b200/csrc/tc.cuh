@@ -122,6 +122,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   // on unless B2_PDL=0.  Same-box A/B inside the graphed step (round 2, gpurun_out/r2C_bench_pdl*.log): 118.26 / 117.75 ms off,
   // 118.20 / 117.25 ms on — a few tenths of a millisecond: the step runs under the power cap, so hidden set-up time mostly
   // comes back as a lower SM clock (1 860 -> 1 800 MHz in the same runs).
+  // Extending the attribute to the ~45 normalisation / element-wise / loss / optimizer kernels (each starting with
+  // griddepcontrol.wait) was tried and reverted: ABAB on one box 117.42 / 117.52 / 117.31 ms with it, 116.54 / 116.94 / 117.15
+  // without, and one tiny-UNet parity test failed — those kernels have no set-up to hide, and their early-resident CTAs take
+  // slots from the side-stream kernels.
   static const bool off = getenv("B2_PDL") != nullptr && atoi(getenv("B2_PDL")) == 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;

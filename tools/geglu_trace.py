@@ -61,3 +61,31 @@ for (M2, N2, K2, res) in ((4096, 10240, 1280, False), (4096, 3840, 1280, False),
         r = t[i * 8:i * 8 + 8]
         print(f"  tile {i}: chunk 0: sync+ld {r[2] - r[1]:5d} math {r[3] - r[2]:5d} fence+bar+store {r[4] - r[3]:5d} | chunk 1: sync+ld {r[5] - r[4]:5d} math {r[6] - r[5]:5d} fence+bar+store {r[7] - r[6]:5d}")
         print(f"  tile {i}: epilogue busy {e1[0] - e[1]:6d} (then waits {e1[1] - e1[0]:6d} for the next accumulator) | MMA thread: waits {m[1] - m[0]:6d} for a free accumulator, issues for {m[2] - m[1]:6d}")
+
+
+# single-round GEMMs (one tile per CTA pair): where does the launch's time go?  Graph-replay time per launch next to the
+# cycle stamps of cluster 0: entry -> set-up done -> first MMA issue possible -> last MMA issued -> accumulator ready ->
+# last store issued -> stores complete.
+for (M2, N2, K2, res, bmn) in ((4096, 1280, 1280, True, False), (4096, 1280, 1280, False, True), (4096, 1280, 5120, True, False)):
+    x2 = torch.randn(M2, K2, device="cuda").to(bf)
+    W2 = (torch.randn(N2, K2, device="cuda") * 0.03).to(bf)
+    bb = torch.zeros(N2, device="cuda", dtype=bf)
+    r2 = torch.randn(M2, N2, device="cuda").to(bf) if res else None
+    o2 = torch.empty(M2, N2, device="cuda", dtype=bf)
+    dy = torch.randn(M2, N2, device="cuda").to(bf)
+    dx = torch.empty(M2, K2, device="cuda", dtype=bf)
+    fn = (lambda: ops.linear_dgrad(dy, W2, dx)) if bmn else (lambda: ops.linear_fwd(x2, W2, bias=bb, residual=r2, out=o2))
+    us = bench._graph_time_us(fn)
+    buf.zero_()
+    _lib.load().b2_gemm2_set_debug(buf.data_ptr())
+    fn()
+    torch.cuda.synchronize()
+    _lib.load().b2_gemm2_set_debug(None)
+    t = buf.tolist()
+    e0 = t[187]
+    m = t[128:131]
+    ep = t[0:8]
+    print(f"{'dgrad' if bmn else 'fwd'} M={M2} N={N2} K={K2} residual={res}: {us:.1f} us per launch in graph replay ({us * 1.85e3:.0f} cycles at 1.85 GHz); "
+          f"mainloop {K2 // 64 * (640 if N2 % 320 == 0 and not bmn else 512)} tensor cycles")
+    print(f"   cycles from kernel entry (cluster 0): set-up done {t[191] - e0}, dependency wait done {t[190] - e0}, MMA thread has accumulator {m[1] - e0}, "
+          f"last MMA issued {m[2] - e0}, epilogue sees accumulator {ep[1] - e0}, last store issued {t[189] - e0}, stores complete {t[188] - e0}")
