@@ -23,7 +23,7 @@
 
 namespace b2 {
 
-constexpr int G2_THREADS = 192;
+constexpr int G2_THREADS = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 and 6-9: two epilogue groups
 constexpr int G2_STAGES = 6;
 constexpr int G2_BK = 64;
 constexpr int G2_A_BYTES = 128 * G2_BK * 2;        // 16 KiB: this CTA's 128 rows of A
@@ -78,6 +78,7 @@ struct Gemm2P {
   // writes bf16(h * gelu(g)) to Z — the separate GEGLU kernel's 2F-wide re-read of u disappears.
   int geglu, gg_F;
   int res_prefetch;  // 1: residual tiles travel one chunk ahead (default); B2_GEMM_NO_RES_PREFETCH=1 restores the per-chunk load
+  int epi_groups;    // 2 (default): both epilogue warp groups work; 1: warps 6-9 idle (B2_GEMM_EPI_GROUPS=1, for A/B runs)
   unsigned long long* dbg;  // optional clock64 trace of cluster 0 / CTA 0 (b2_gemm2_set_debug, tools/geglu_trace.py); NULL in production
 };
 
@@ -172,7 +173,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_acc_full[b]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[b]), 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(smem_u32(&bar_acc_empty[b]), 8 * p.epi_groups);  // 4 epilogue warps per group x 2 CTAs
       mbar_init(smem_u32(&bar_res[b]), 1);
     }
     fence_barrier_init();
@@ -362,8 +363,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (tr) p.dbg[128 + tile_i * 4 + 2] = g2_clk();
       }
     }
-  } else {
+  } else if (((warp - 2) >> 2) < p.epi_groups) {
     // ===================== epilogue (both CTAs): TMEM -> regs -> smem -> TMA store =====================
+    // Two groups of four warps (one warp of each group per scheduler).  Plain mode: the groups take ALTERNATE 64-column
+    // chunks of the tile, each with its own staging buffer, named barrier and store-issuing thread, so two chunks are in
+    // flight and the lone-warp latencies of one group hide behind the other (a single group needed ~1,250 cycles per chunk,
+    // more than half of it barriers / fences / TMEM-load waits: tools/geglu_trace.py).  GEGLU mode: both groups work on
+    // the same chunk, 32 of its 64 columns each.
+    const int grp = (warp - 2) >> 2;
+    const bool two = p.epi_groups == 2;
     const int qd = warp & 3;
     const int row = qd * 32 + lane;            // TMEM lane == row of this CTA's 128-row slab
     const int et = row;                        // epilogue thread id 0..127
@@ -379,8 +387,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (lane == 0)
         asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty_leader + b * 8) : "memory");
     };
+    auto gbar = [&]() {  // this group's 128 threads
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
+    auto allbar = [&]() {  // every epilogue thread of the CTA
+      if (two) asm volatile("bar.sync 3, 256;" ::: "memory");
+      else asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    const int c_first = two ? grp * 64 : 0, c_step = two ? 128 : 64;  // plain mode: this group's chunks of a tile
     int tile_i = 0;
-    uint32_t chunk_i = 0;
+    uint32_t chunk_i = 0;  // chunks this group has staged so far (single group: parity selects the staging buffer)
     uint32_t res_uses[2] = {0, 0};
     const bool reduce_out = p.splits > 1;
     for (int u = cluster_id; u < num_units; u += num_clusters, ++tile_i) {
@@ -405,7 +422,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (p.bias) {
         const int g_lo = m_base / p.bias_rows_per_group, g_hi = min(m_base + 127, p.M - 1) / p.bias_rows_per_group;
         bias_smem = g_lo == g_hi;
-        if (bias_smem) {
+        if (bias_smem && grp == 0) {
           const bf16* brow = p.bias + (long long)g_lo * p.bias_group_stride;
           const int c = et * 8;
           if (p.geglu) {
@@ -414,43 +431,46 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             *reinterpret_cast<uint4*>(&bias_s[tb][c]) = ld8(brow + n_tile + c).u;
           }
         }
+        if (two) allbar();  // group 1 reads what group 0 staged (and has left the previous tile's bias buffer)
       }
       // Residual / accumulate operand: its 16 KB tile per 64-column chunk comes in by TMA.  Issued at the chunk's own start, the
       // load's latency (L2 hit ~0.4 us, HBM ~0.8 us) was exposed once per chunk — five times per 256 x 320 tile, on every
       // "+= gradient" GEMM and every Linear with a fused residual.  Now the first chunk's load leaves BEFORE the wait for the
       // accumulator and each chunk prefetches the next one's tile into the other staging buffer.
       auto chunk_full = [&](int c0) { return (min(64, ncols - c0) == 64) || (n_tile + p.BN >= p.N); };
-      if (p.has_res && p.res_prefetch && !p.geglu && et == 0 && chunk_full(0)) {
-        const uint32_t sb = chunk_i & 1;
-        tma_store_wait_read<1>();  // the store that last read this staging buffer (two chunks ago) has drained
+      const bool first_res_early = p.has_res && p.res_prefetch && !p.geglu && c_first < ncols && chunk_full(c_first);
+      if (first_res_early && et == 0) {
+        const uint32_t sb = two ? (uint32_t)grp : (chunk_i & 1);
+        if (two) tma_store_wait_read<0>();  // this group's previous store has read the buffer
+        else tma_store_wait_read<1>();      // the store that last read this staging buffer (two chunks ago) has drained
         mbar_expect_tx(smem_u32(&bar_res[sb]), G2_EPI_BYTES);
-        tma_load_2d(smem_epi + sb * G2_EPI_BYTES, &tmR, smem_u32(&bar_res[sb]), n_tile, m_base);
+        tma_load_2d(smem_epi + sb * G2_EPI_BYTES, &tmR, smem_u32(&bar_res[sb]), n_tile + c_first, m_base);
       }
-      const bool tr = p.dbg && cluster_id == 0 && leader && et == 0 && tile_i < 8;
+      const bool tr = p.dbg && cluster_id == 0 && leader && et == 0 && grp == 0 && tile_i < 8;
       if (tr) p.dbg[tile_i * 8] = g2_clk();
       mbar_wait<true>(smem_u32(&bar_acc_full[buf]), use & 1);
       tc_fence_after();
       if (tr) p.dbg[tile_i * 8 + 1] = g2_clk();
       const uint32_t tacc = tmem_base + buf * 256 + lane_off;
+      if (!p.geglu && c_first >= ncols) release_acc(buf);  // narrow tile: this group has no chunk in it
       if (p.geglu) {
         // accumulator columns [0,128) = h features nb*128 .., [128,256) = the matching g features.  Three staging tiles
         // (h, g, z) per 64-column chunk: GEGLU mode runs the mainloop on 5 stages, which frees a third 16 KB buffer.
         const int nh = nb * 128;
         for (int c0 = 0; c0 < 128; c0 += 64) {
-          if (et == 0) tma_store_wait_read<0>();  // the previous chunk's three TMA stores have read their staging tiles
-          epi_bar_sync();
+          if (et == 0 && grp == 0) tma_store_wait_read<0>();  // the previous chunk's three TMA stores have read their tiles
+          allbar();
           if (tr) p.dbg[tile_i * 8 + 2 + 3 * (c0 >> 6)] = g2_clk();
           const uint32_t srow = smem_epi + row * 128;
           // 32 columns of h and of g at a time: with the whole 64 + 64-column chunk in registers (128 + temporaries) ptxas
           // had no registers left to interleave the eight independent GELU chains, and the lone epilogue warp of each
           // scheduler ran them at ~3 cycles per instruction (tools/geglu_trace.py); TMEM loads are cheap (~50 cycles).
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
+          for (int hf = two ? grp : 0; hf < (two ? grp + 1 : 2); ++hf) {  // two groups: one 32-column half each
             uint32_t vh[32], vg[32];
             tmem_ld32_nowait(tacc + c0 + hf * 32, vh);
             tmem_ld32_nowait(tacc + 128 + c0 + hf * 32, vg);
             tmem_ld_wait();
-            if (c0 == 64 && hf == 1) release_acc(buf);  // the whole accumulator has been read
+            if (c0 == 64 && (two || hf == 1)) release_acc(buf);  // this warp has read all it needs of the accumulator
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
               const int g = hf * 4 + g4;
@@ -485,8 +505,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           if (tr) p.dbg[tile_i * 8 + 3 + 3 * (c0 >> 6)] = g2_clk();
           fence_proxy_async_smem();
-          epi_bar_sync();
-          if (et == 0) {
+          allbar();
+          if (et == 0 && grp == 0) {
             tma_store_2d(&tmD, smem_epi, nh + c0, m_base);
             tma_store_2d(&tmD, smem_epi + G2_EPI_BYTES, p.gg_F + nh + c0, m_base);
             tma_store_2d(&tmZ, smem_epi + 2 * G2_EPI_BYTES, nh + c0, m_base);
@@ -495,7 +515,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (tr) p.dbg[tile_i * 8 + 4 + 3 * (c0 >> 6)] = g2_clk();
         }
       } else
-      for (int c0 = 0; c0 < ncols; c0 += 64) {
+      for (int c0 = c_first; c0 < ncols; c0 += c_step) {
         const int cw = min(64, ncols - c0);
         const int n0 = n_tile + c0;
         uint32_t v0[32], v1[32];
@@ -503,13 +523,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (cw > 32) tmem_ld32_nowait(tacc + c0 + 32, v1);
         const bool full_chunk = (cw == 64) || (n_tile + p.BN >= p.N);  // TMA may write the whole 64-wide box
         if (full_chunk) {
-          const uint32_t sbuf = chunk_i & 1;
+          const uint32_t sbuf = two ? (uint32_t)grp : (chunk_i & 1);
           const uint32_t stage = smem_epi + sbuf * G2_EPI_BYTES;
           if (et == 0) {
-            if (p.has_res && !p.res_prefetch) {
-              tma_store_wait_read<1>();
-              mbar_expect_tx(smem_u32(&bar_res[sbuf]), G2_EPI_BYTES);
-              tma_load_2d(stage, &tmR, smem_u32(&bar_res[sbuf]), n0, m_base);
+            if (p.has_res && (two || !p.res_prefetch)) {
+              // one staging buffer per group: the residual tile of this chunk can only be fetched now (the group's first
+              // chunk of the tile was fetched before the accumulator wait); the other group's chunk runs meanwhile
+              if (!(first_res_early && c0 == c_first)) {
+                if (two) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+                mbar_expect_tx(smem_u32(&bar_res[sbuf]), G2_EPI_BYTES);
+                tma_load_2d(stage, &tmR, smem_u32(&bar_res[sbuf]), n0, m_base);
+              }
             } else if (p.has_res) {
               // this chunk's residual tile is already in flight (tile start / previous chunk); send the next chunk's after
               // the store that last read the OTHER staging buffer (the previous chunk's) has drained
@@ -519,16 +543,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 tma_load_2d(smem_epi + (sbuf ^ 1) * G2_EPI_BYTES, &tmR, smem_u32(&bar_res[sbuf ^ 1]), n0 + 64, m_base);
               }
             } else {
-              tma_store_wait_read<1>();  // the previous TMA store that read this staging buffer must have drained
+              // the previous TMA store that read this staging buffer must have drained
+              if (two) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
             }
           }
-          epi_bar_sync();
+          gbar();
           if (p.has_res) {
             mbar_wait(smem_u32(&bar_res[sbuf]), res_uses[sbuf] & 1);
             res_uses[sbuf]++;
           }
           tmem_ld_wait();
-          if (c0 + 64 >= ncols) release_acc(buf);
+          if (c0 + c_step >= ncols) release_acc(buf);
           if (tr && c0 < 128) p.dbg[tile_i * 8 + 2 + 3 * (c0 >> 6)] = g2_clk();
           const uint32_t srow = stage + row * 128;
           if (cw == 64 && (!bias_row || bias_smem)) {
@@ -574,7 +599,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           if (tr && c0 < 128) p.dbg[tile_i * 8 + 3 + 3 * (c0 >> 6)] = g2_clk();
           fence_proxy_async_smem();
-          epi_bar_sync();
+          gbar();
           if (et == 0) {
             if (reduce_out)
               tma_reduce_add_2d(&tmD, stage, n0, m_base);
@@ -587,7 +612,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         } else {
           // tile-bounded partial chunk (BN not a multiple of 64): direct 16-byte stores of the valid columns
           tmem_ld_wait();
-          if (c0 + 64 >= ncols) release_acc(buf);
+          if (c0 + c_step >= ncols) release_acc(buf);
           if (row_ok) {
             bf16* drow = p.D + (long long)gm * p.ldd + n0;
             const bf16* rrow = p.R ? p.R + (long long)gm * p.ldr + n0 : nullptr;
@@ -617,9 +642,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-    if (p.dbg && cluster_id == 0 && leader && et == 0) p.dbg[189] = g2_clk();  // last store issued
+    if (p.dbg && cluster_id == 0 && leader && et == 0 && grp == 0) p.dbg[189] = g2_clk();  // last store issued
     if (et == 0) tma_store_wait_all();
-    if (p.dbg && cluster_id == 0 && leader && et == 0) p.dbg[188] = g2_clk();  // all stores complete
+    if (p.dbg && cluster_id == 0 && leader && et == 0 && grp == 0) p.dbg[188] = g2_clk();  // all stores complete
   }
 
   tc_fence_before();
@@ -747,6 +772,8 @@ static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   p.stage_bytes = p.wide ? G2_WIDE_STAGE_BYTES : G2_STAGE_BYTES;
   if (p.splits > 1) p.has_res = 0;  // the reduce-add epilogue is the accumulation
   p.dbg = g_g2_dbg;
+  static const int epi_groups = (getenv("B2_GEMM_EPI_GROUPS") && atoi(getenv("B2_GEMM_EPI_GROUPS")) == 1) ? 1 : 2;
+  p.epi_groups = epi_groups;
   static const bool log_calls = getenv("B2_GEMM_LOG") != nullptr;
   if (log_calls)
     fprintf(stderr, "B2GEMM %s M=%d N=%d K=%d a_mn=%d b_mn=%d conv=%d BN=%d splits=%d bias=%d res=%d\n", what, p.M, p.N, p.K,
