@@ -217,6 +217,8 @@ int b2_linear_geglu_ok(int M, int F, int K);
 int b2_linear_geglu(const void* x, const void* W1, const void* b1, void* u, void* z, int M, int F, int K, int64_t ldx,
                     int64_t ldw, int64_t ldu, int64_t ldz, void* stream);
 int b2_geglu_bwd(const void* u, const void* dz, void* du, int64_t M, int F, void* stream);
+/* same + the ff1 bias gradient: db32[c] += sum_m du[m, c] (fp32, 2F entries; replaces b2_colsum_f32 over du) */
+int b2_geglu_bwd_bias(const void* u, const void* dz, void* du, float* db32, int64_t M, int F, void* stream);
 
 /* Elementwise / plumbing */
 int b2_silu_fwd(const void* x, void* y, int64_t n, void* stream);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "b2_linear_geglu_ok": [i32, i32, i32],
     "b2_linear_geglu": [c_p, c_p, c_p, c_p, c_p, i32, i32, i32, i64, i64, i64, i64, c_p],
     "b2_geglu_bwd": [c_p, c_p, c_p, i64, i32, c_p],
+    "b2_geglu_bwd_bias": [c_p, c_p, c_p, c_p, i64, i32, c_p],
     "b2_silu_fwd": [c_p, c_p, i64, c_p],
     "b2_silu_bwd": [c_p, c_p, c_p, i64, i32, c_p],
     "b2_add": [c_p, c_p, c_p, i64, c_p],

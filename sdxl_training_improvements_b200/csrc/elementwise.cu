@@ -92,6 +92,70 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ u, const bf16* __restr
   }
 }
 
+// GEGLU backward that also produces the ff1 bias gradient: db[c] += sum_m du[m, c] over the bf16 values it stores.  The
+// separate column-sum kernel re-read all of du (84 MB per transformer block at 1024 px) right after this kernel wrote it.
+// CTA = 32 vector-columns x 8 row lanes; a warp covers 32 consecutive 16-byte vectors of one row (512 B each of h, g, dz);
+// per-thread column sums in registers, reduced over the 8 row lanes in shared memory, one atomicAdd per column per CTA.
+__global__ void __launch_bounds__(256) geglu_bwd_bias_kernel(const bf16* __restrict__ u, const bf16* __restrict__ dz,
+                                                              bf16* __restrict__ du, float* __restrict__ db, long long M, int F,
+                                                              long long rows_per_cta) {
+  __shared__ float red[8][32 * 16 + 1];
+  const int cvl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cvl) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float sh[8], sg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[j] = sg[j] = 0.f;
+  if (c < F) {
+    for (long long m = r0 + rl; m < r1; m += 16) {
+      // two rows per trip: six independent 16-byte loads in flight
+      const bool two = m + 8 < r1;
+      const long long m2 = two ? m + 8 : m;
+      const bf16x8 vh0 = ld8(u + m * 2 * F + c), vg0 = ld8(u + m * 2 * F + F + c), vd0 = ld8(dz + m * F + c);
+      const bf16x8 vh1 = ld8(u + m2 * 2 * F + c), vg1 = ld8(u + m2 * 2 * F + F + c), vd1 = ld8(dz + m2 * F + c);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t == 1 && !two) break;
+        float h[8], g[8], d[8], dh[8], dg[8];
+        unpack8(t ? vh1 : vh0, h);
+        unpack8(t ? vg1 : vg0, g);
+        unpack8(t ? vd1 : vd0, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float cdf, pdf;
+          gelu_parts(g[j], cdf, pdf);
+          dh[j] = d[j] * g[j] * cdf;
+          dg[j] = d[j] * h[j] * fmaf(g[j], pdf, cdf);
+        }
+        const bf16x8 oh = pack8(dh), og = pack8(dg);
+        const long long mm = t ? m2 : m;
+        st8(du + mm * 2 * F + c, oh);
+        st8(du + mm * 2 * F + F + c, og);
+        unpack8(oh, dh);  // the sums are over what du holds (as colsum of du would see it)
+        unpack8(og, dg);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sh[j] += dh[j]; sg[j] += dg[j]; }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[rl][cvl * 16 + j] = sh[j];
+    red[rl][cvl * 16 + 8 + j] = sg[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+    const int v = i >> 4, j = i & 15;
+    const int cc = (blockIdx.x * 32 + v) * 8 + (j & 7);
+    if (cc < F) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += red[r][i];
+      atomicAdd(db + (j < 8 ? cc : F + cc), t);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- silu / add / copy
 __global__ void silu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -302,6 +366,17 @@ extern "C" int b2_geglu_bwd(const void* u, const void* dz, void* du, int64_t M, 
     geglu_bwd_kernel<long long><<<ew_blocks(nvec, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)u, (const bf16*)dz,
                                                                                         (bf16*)du, M, F);
   return check_launch("geglu_bwd");
+}
+extern "C" int b2_geglu_bwd_bias(const void* u, const void* dz, void* du, float* db32, int64_t M, int F, void* stream) {
+  B2_REQUIRE(u && dz && du && db32 && M > 0 && F > 0 && F % 8 == 0, "b2_geglu_bwd_bias: bad args");
+  const int colblocks = (F / 8 + 31) / 32;
+  long long rchunks = (8LL * num_sms() + colblocks - 1) / colblocks;  // ~8 CTAs per SM in flight
+  long long rows_per_cta = (M + rchunks - 1) / rchunks;
+  rows_per_cta = (rows_per_cta + 15) / 16 * 16;
+  rchunks = (M + rows_per_cta - 1) / rows_per_cta;
+  geglu_bwd_bias_kernel<<<dim3(colblocks, (unsigned)rchunks), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)u, (const bf16*)dz, (bf16*)du, db32, M, F, rows_per_cta);
+  return check_launch("geglu_bwd_bias");
 }
 extern "C" int b2_silu_fwd(const void* x, void* y, int64_t n, void* stream) {
   B2_REQUIRE(x && y && n > 0, "b2_silu_fwd: bad args");

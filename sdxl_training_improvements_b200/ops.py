@@ -283,10 +283,15 @@ def linear_geglu_fwd(x, W1, b1, F):
     return u, z
 
 
-def geglu_bwd(u, dz, F):
+def geglu_bwd(u, dz, F, dbias32=None):
+    """du[M, 2F] from u = [h | g] and dz; with `dbias32` (fp32 [2F] staging slice) the column sums of du — the bias gradient
+    of the up-projection — are accumulated into it in the same pass."""
     M = u.shape[0]
     du = torch.empty_like(u)
-    _lib.check(_lib.load().b2_geglu_bwd(_p(u), _p(dz), _p(du), M, F, _stream()), "geglu_bwd")
+    if dbias32 is not None:
+        _lib.check(_lib.load().b2_geglu_bwd_bias(_p(u), _p(dz), _p(du), _p(dbias32), M, F, _stream()), "geglu_bwd_bias")
+    else:
+        _lib.check(_lib.load().b2_geglu_bwd(_p(u), _p(dz), _p(du), M, F, _stream()), "geglu_bwd")
     return du
 
 

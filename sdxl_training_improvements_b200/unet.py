@@ -34,11 +34,12 @@ PRED_PAD = 64  # conv_out's 4 output channels padded to 64: N = 64 puts its forw
 
 class Act:
     """An activation and its (lazily allocated) gradient."""
-    __slots__ = ("d", "g")
+    __slots__ = ("d", "g", "bias_grad_done")
 
     def __init__(self, d: torch.Tensor):
         self.d = d
         self.g: Optional[torch.Tensor] = None
+        self.bias_grad_done = False  # set by a backward closure that already produced the producing Linear's bias gradient
 
 
 def _gslot(t: Act):
@@ -155,7 +156,7 @@ class UNetEngine:
             gb = st.gs(bname) if bname else None
             with self._side_branch():  # weight + bias gradients beside the input gradient
                 ops.linear_wgrad(dy, x.d, gW, accumulate=True)
-                if bname:
+                if bname and not out.bias_grad_done:
                     ops.colsum_f32(dy, gb)
             if need_dx:
                 buf, acc = _gslot(x)
@@ -180,7 +181,8 @@ class UNetEngine:
             gW, gb = st.g(wname, 2 * F, K), st.gs(bname)
             with self._side_branch():
                 ops.linear_wgrad(dy, x.d, gW, accumulate=True)
-                ops.colsum_f32(dy, gb)
+                if not u.bias_grad_done:
+                    ops.colsum_f32(dy, gb)
             buf, acc = _gslot(x)
             ops.linear_dgrad(dy, Wt, buf, acc)
             self._join()
@@ -414,7 +416,9 @@ class UNetEngine:
             z = Act(ops.geglu_fwd(u.d, 4 * Cc))
 
         def geglu_bwd():
-            u.g = ops.geglu_bwd(u.d, z.g, 4 * Cc)
+            # the up-projection's bias gradient (column sums of du) falls out of the same pass; its Linear closure skips it
+            u.g = ops.geglu_bwd(u.d, z.g, 4 * Cc, dbias32=self.store.gs(f"{pfx}.ff.net.0.proj.bias"))
+            u.bias_grad_done = True
 
         self.tape.append(geglu_bwd)
         return self.linear(z, f"{pfx}.ff.net.2.weight", Cc, 4 * Cc, f"{pfx}.ff.net.2.bias", residual=h2)

@@ -364,6 +364,20 @@ def test_softmax(ops, rows, n):
     _close(dS[:, :n], refd, atol=1e-3, what="softmax bwd")
 
 
+@pytest.mark.parametrize("M,F", [(4096, 5120), (300, 128), (1003, 2560), (64, 40)])
+def test_geglu_bwd_with_bias_column_sums(ops, M, F):
+    """b2_geglu_bwd_bias: du identical to b2_geglu_bwd, and db32 += column sums of the bf16 du (what b2_colsum_f32 over du gives)."""
+    u = _rand(M, 2 * F, seed=21)
+    dz = _rand(M, F, seed=22)
+    du0 = ops.geglu_bwd(u, dz, F)
+    db = torch.full((2 * F,), 0.25, device="cuda", dtype=torch.float32)
+    du1 = ops.geglu_bwd(u, dz, F, dbias32=db)
+    assert torch.equal(du0, du1)
+    ref = 0.25 + du0.float().sum(0)
+    assert float((db - ref).abs().max()) <= 1e-3 * max(1.0, float(ref.abs().max())), float((db - ref).abs().max())
+    torch.cuda.synchronize()
+
+
 def test_geglu_silu_add_colsum(ops):
     M, Fd = 96, 640
     u = _rand(M, 2 * Fd, seed=21)
