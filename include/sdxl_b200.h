@@ -342,6 +342,11 @@ int b2_dpx_create(int rank, int world, int mode, void* const* grad_ptrs, void* c
 int b2_dpx_exchange(void* handle, int chunk, uint32_t seq, int n_ranges, const int64_t* range_off,
                     const int64_t* range_len, int64_t staging_base, void* main_stream);
 int b2_dpx_finish(void* handle, uint32_t seq, void* main_stream);
+/* b2_dpx_finish + the global gradient norm for free: *gnorm_sq_out = sum over the whole exchanged buffer of (reduced bf16
+ * gradient)^2 — what b2_sumsq over the buffer would return (replaces the 5 GB read of clip_grad_norm_'s norm pass,
+ * flow_matching_trainer.py:181-186).  Copy-engine transports only (b2_dpx_norm_supported). */
+int b2_dpx_finish_norm(void* handle, uint32_t seq, void* main_stream, double* gnorm_sq_out);
+int b2_dpx_norm_supported(void* handle);
 int b2_dpx_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
 int b2_dpx_destroy(void* handle);
 

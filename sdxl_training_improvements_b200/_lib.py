@@ -112,6 +112,8 @@ SIGNATURES = {
     "b2_dpx_exchange": [c_p, i32, C.c_uint32, i32, C.POINTER(i64), C.POINTER(i64), i64, c_p],
     "b2_dpx_memcpy_async": [c_p, c_p, i64, c_p],
     "b2_dpx_finish": [c_p, C.c_uint32, c_p],
+    "b2_dpx_finish_norm": [c_p, C.c_uint32, c_p, c_p],
+    "b2_dpx_norm_supported": [c_p],
     "b2_dpx_destroy": [c_p],
     "b2_adamw": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, c_p, f32, f32, c_p, c_p],
 }

@@ -39,7 +39,11 @@ namespace b2 {
 
 constexpr int DPX_MAX_WORLD = 16;
 constexpr int DPX_MAX_CHUNKS = 64;
-constexpr int DPX_FLAG_WORDS = 2 * DPX_MAX_CHUNKS * DPX_MAX_WORLD;
+constexpr int DPX_FLAG_WORDS = 3 * DPX_MAX_CHUNKS * DPX_MAX_WORLD;  // kinds: 0 ready / pushed, 1 delivered, 2 norm published
+constexpr int DPX_SQ_ACCS = 64;                                      // partial-sum accumulators of the reduce kernel
+// behind the flag words of every rank's flag page: [2 parities][world] doubles = each rank's sum of squares of its shards
+constexpr size_t DPX_NORM_OFF = DPX_FLAG_WORDS * sizeof(uint32_t);
+constexpr size_t DPX_PAGE_BYTES = DPX_NORM_OFF + 2 * DPX_MAX_WORLD * sizeof(double);
 
 typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
@@ -80,8 +84,11 @@ __device__ __forceinline__ void st8_stream(bf16* p, const bf16x8& v) { __stcs(re
 // grad[i] = bf16( fp32(grad[i]) + sum_s fp32(staging[s * slot_stride + i]) ), 8 elements per 16-byte access, four
 // vectors per thread.  No shared memory and few registers, so its CTAs co-reside with the persistent GEMM / attention
 // CTAs instead of waiting for an SM; many short CTAs rather than a persistent grid for the same reason.
+// sq_acc (optional): DPX_SQ_ACCS doubles; every warp adds the sum of squares of the bf16 values it stores — the
+// global gradient norm of the REDUCED gradients falls out of the exchange (each element is summed by exactly one rank).
 __global__ void __launch_bounds__(128) dpx_reduce_kernel(bf16* __restrict__ grad, const bf16* __restrict__ staging,
-                                                         long long slot_stride, int nslots, long long nvec) {
+                                                         long long slot_stride, int nslots, long long nvec,
+                                                         double* __restrict__ sq_acc) {
   const long long base = ((long long)blockIdx.x * blockDim.x) * 4 + threadIdx.x;
   float acc[4][8];
   bool live[4];
@@ -109,11 +116,43 @@ __global__ void __launch_bounds__(128) dpx_reduce_kernel(bf16* __restrict__ grad
       }
     }
   }
+  float sq = 0.f;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const long long v = base + (long long)u * blockDim.x;
-    if (live[u]) st8_stream(grad + v * 8, pack8(acc[u]));
+    if (live[u]) {
+      const bf16x8 o = pack8(acc[u]);
+      st8_stream(grad + v * 8, o);
+      float f[8];
+      unpack8(o, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sq = fmaf(f[e], f[e], sq);
+    }
   }
+  if (sq_acc) {
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sq_acc + ((blockIdx.x * 4 + (threadIdx.x >> 5)) & (DPX_SQ_ACCS - 1)), (double)sq);
+  }
+}
+
+struct PeerNorm {
+  double* p[DPX_MAX_WORLD];
+};
+// one thread: this rank's sum of squares -> slot [parity][self] of every rank's flag page (own included); accumulators cleared
+__global__ void dpx_norm_publish_kernel(double* sq_acc, PeerNorm slots, int world, int self, int parity) {
+  double t = 0.0;
+  for (int i = 0; i < DPX_SQ_ACCS; ++i) {
+    t += sq_acc[i];
+    sq_acc[i] = 0.0;
+  }
+  for (int p = 0; p < world; ++p) slots.p[p][parity * DPX_MAX_WORLD + self] = t;
+  __threadfence_system();
+}
+// one thread: total over ranks in rank order (identical on every rank) -> out
+__global__ void dpx_norm_total_kernel(const double* my_slots, int world, int parity, double* out) {
+  double t = 0.0;
+  for (int p = 0; p < world; ++p) t += my_slots[parity * DPX_MAX_WORLD + p];
+  *out = t;
 }
 
 struct PeerBufs {
@@ -202,6 +241,7 @@ struct Dpx {
   cudaEvent_t ev_in = nullptr, ev_red = nullptr, ev_done = nullptr;
   std::vector<cudaEvent_t> ev_cs;
   WaitValue32Fn wait32 = nullptr;
+  double* sq_acc = nullptr;  // DPX_SQ_ACCS partial sums of squares (reduce kernel)
   std::vector<int> pending;  // chunks exchanged since the last finish()
   uint32_t pending_seq = 0;
 };
@@ -267,8 +307,8 @@ extern "C" int b2_dpx_ipc_import(const unsigned char* handle /*64 bytes*/, int64
 extern "C" int b2_dpx_alloc_flags(void** flags_out) {
   B2_REQUIRE(flags_out, "b2_dpx_alloc_flags: bad args");
   void* p = nullptr;
-  DPX_CUDA(cudaMalloc(&p, DPX_FLAG_WORDS * sizeof(uint32_t)));
-  DPX_CUDA(cudaMemset(p, 0, DPX_FLAG_WORDS * sizeof(uint32_t)));
+  DPX_CUDA(cudaMalloc(&p, DPX_PAGE_BYTES));
+  DPX_CUDA(cudaMemset(p, 0, DPX_PAGE_BYTES));
   DPX_CUDA(cudaDeviceSynchronize());
   *flags_out = p;
   return B2_OK;
@@ -317,6 +357,8 @@ extern "C" int b2_dpx_create(int rank, int world, int mode, void* const* grad_pt
   DPX_CUDA(cudaEventCreateWithFlags(&d->ev_in, cudaEventDisableTiming));
   DPX_CUDA(cudaEventCreateWithFlags(&d->ev_red, cudaEventDisableTiming));
   DPX_CUDA(cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
+  DPX_CUDA(cudaMalloc(&d->sq_acc, DPX_SQ_ACCS * sizeof(double)));
+  DPX_CUDA(cudaMemset(d->sq_acc, 0, DPX_SQ_ACCS * sizeof(double)));
   *handle_out = d;
   return B2_OK;
 }
@@ -334,6 +376,7 @@ extern "C" int b2_dpx_destroy(void* handle) {
   cudaEventDestroy(d->ev_in);
   cudaEventDestroy(d->ev_red);
   cudaEventDestroy(d->ev_done);
+  cudaFree(d->sq_acc);
   delete d;
   return B2_OK;
 }
@@ -470,7 +513,7 @@ extern "C" int b2_dpx_exchange(void* handle, int chunk, uint32_t seq, int n_rang
         const long long nvec = sl / 8;
         const long long blocks = (nvec + 128 * 4 - 1) / (128 * 4);
         dpx_reduce_kernel<<<(unsigned)blocks, 128, 0, d->xs>>>(d->grad[R] + so, d->staging + so_stage, d->slot_stride, W - 1,
-                                                               nvec);
+                                                               nvec, d->sq_acc);
         if ((rc = check_launch("dpx_reduce"))) return rc;
       }
       so_stage += shard_size(range_len[i], W);
@@ -497,16 +540,46 @@ extern "C" int b2_dpx_exchange(void* handle, int chunk, uint32_t seq, int n_rang
 
 // Make `main_stream` wait until every chunk exchanged with `seq` has been delivered into the local gradient buffer by
 // every peer (and this rank's own pulls / pushes are complete, so the buffer may be overwritten afterwards).
+// gnorm_sq_out (optional, copy-engine transports only): receives sum over ALL ranks' shards of (reduced bf16 gradient)^2, i.e.
+// what b2_sumsq over the exchanged buffer would return, without reading the buffer again: partial sums come out of the reduce
+// kernel, every rank publishes its own into every peer's flag page, and all ranks add them in rank order (bit-identical).
+extern "C" int b2_dpx_finish_norm(void* handle, uint32_t seq, void* main_stream, double* gnorm_sq_out);
 extern "C" int b2_dpx_finish(void* handle, uint32_t seq, void* main_stream) {
+  return b2_dpx_finish_norm(handle, seq, main_stream, nullptr);
+}
+extern "C" int b2_dpx_norm_supported(void* handle) {
+  Dpx* d = (Dpx*)handle;
+  return d && d->mode != 2 ? 1 : 0;
+}
+extern "C" int b2_dpx_finish_norm(void* handle, uint32_t seq, void* main_stream, double* gnorm_sq_out) {
   Dpx* d = (Dpx*)handle;
   B2_REQUIRE(d, "b2_dpx_finish: bad args");
-  if (d->pending.empty()) return B2_OK;
+  B2_REQUIRE(!gnorm_sq_out || d->mode != 2, "b2_dpx_finish_norm: the sm transport does not produce the gradient norm");
+  if (d->pending.empty()) {
+    B2_REQUIRE(!gnorm_sq_out, "b2_dpx_finish_norm: nothing was exchanged, there is no norm to return");
+    return B2_OK;
+  }
   B2_REQUIRE(d->pending_seq == seq, "b2_dpx_finish: sequence %u does not match the pending exchange %u", seq, d->pending_seq);
   int rc;
   for (int chunk : d->pending)
     for (int p = 0; p < d->world; ++p)
       if (p != d->rank && (rc = dpx_wait_flag(d, d->xs, 1, chunk, p, seq))) return rc;
   d->pending.clear();
+  if (gnorm_sq_out) {
+    const int parity = (int)(seq & 1u);
+    PeerNorm pn;
+    for (int p = 0; p < DPX_MAX_WORLD; ++p)
+      pn.p[p] = p < d->world ? reinterpret_cast<double*>(reinterpret_cast<char*>(d->flags[p]) + DPX_NORM_OFF) : nullptr;
+    dpx_norm_publish_kernel<<<1, 1, 0, d->xs>>>(d->sq_acc, pn, d->world, d->rank, parity);
+    if ((rc = check_launch("dpx_norm_publish"))) return rc;
+    if ((rc = dpx_signal(d, 2, 0, seq))) return rc;
+    for (int p = 0; p < d->world; ++p)
+      if (p != d->rank && (rc = dpx_wait_flag(d, d->xs, 2, 0, p, seq))) return rc;
+    dpx_norm_total_kernel<<<1, 1, 0, d->xs>>>(pn.p[d->rank], d->world, parity, gnorm_sq_out);
+    if ((rc = check_launch("dpx_norm_total"))) return rc;
+  } else if (d->mode != 2) {
+    DPX_CUDA(cudaMemsetAsync(d->sq_acc, 0, DPX_SQ_ACCS * sizeof(double), d->xs));  // self-test / autotune / callers without clip
+  }
   DPX_CUDA(cudaEventRecord(d->ev_done, d->xs));
   DPX_CUDA(cudaStreamWaitEvent((cudaStream_t)main_stream, d->ev_done, 0));
   return B2_OK;

@@ -297,10 +297,22 @@ class PeerGradExchange:
         announce the last accumulation micro-step."""
         self.exchange_chunk(self.WHOLE)
 
-    def finish(self):
-        """The current stream waits for every chunk of this step to be complete in the local buffer."""
+    @property
+    def provides_norm(self) -> bool:
+        """True when finish(gnorm_sq_out=...) can return the squared norm of the reduced gradients (copy-engine transports)."""
+        return bool(self.lib.b2_dpx_norm_supported(self.handle)) and os.environ.get("B2_DP_NORM_FOLD", "1") != "0"
+
+    def finish(self, gnorm_sq_out: Optional[torch.Tensor] = None):
+        """The current stream waits for every chunk of this step to be complete in the local buffer.  With `gnorm_sq_out`
+        (a float64 device scalar) it also receives sum((reduced gradient)^2) over the whole buffer, accumulated by the
+        exchange's reduce kernels and added over ranks in rank order — the optimizer's clip needs no pass of its own."""
         from . import _lib
-        _lib.check(self.lib.b2_dpx_finish(self.handle, C.c_uint32(self.seq & 0xFFFFFFFF), self._stream()), "dpx_finish")
+        if gnorm_sq_out is not None:
+            assert gnorm_sq_out.dtype == torch.float64 and gnorm_sq_out.is_cuda
+            _lib.check(self.lib.b2_dpx_finish_norm(self.handle, C.c_uint32(self.seq & 0xFFFFFFFF), self._stream(),
+                                                   C.c_void_p(gnorm_sq_out.data_ptr())), "dpx_finish_norm")
+        else:
+            _lib.check(self.lib.b2_dpx_finish(self.handle, C.c_uint32(self.seq & 0xFFFFFFFF), self._stream()), "dpx_finish")
         self.seq += 1
         self.issued = False
 

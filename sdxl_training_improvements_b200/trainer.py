@@ -345,9 +345,10 @@ class GraphedOptimizerStep:
     coefficient are device-side, so replays stay correct).  Host-side bookkeeping that cannot be captured (the
     reference's per-tensor deferred weight decay) runs after the replay via `optimizer.after_graph_step()`."""
 
-    def __init__(self, optimizer, max_norm: float, grad_scale: float):
+    def __init__(self, optimizer, max_norm: float, grad_scale: float, gnorm_ready: bool = False):
         self.optimizer = optimizer
         self.max_norm, self.gscale = max_norm, grad_scale
+        self.gnorm_ready = gnorm_ready  # data parallel: the exchange delivers sum(grad^2); no norm pass in this graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_replay = 0
         self._hyper = None
@@ -369,9 +370,10 @@ class GraphedOptimizerStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             if isinstance(opt, B200AdamWBF16):  # zero_grad() folded into the optimizer kernel (no separate 5 GB fill)
-                opt.fused_step(max_norm=self.max_norm, grad_scale=self.gscale, _in_graph=True, zero_grad=True)
+                opt.fused_step(max_norm=self.max_norm, grad_scale=self.gscale, _in_graph=True, zero_grad=True,
+                               gnorm_ready=self.gnorm_ready)
             else:
-                opt.fused_step(max_norm=self.max_norm, grad_scale=self.gscale, _in_graph=True)
+                opt.fused_step(max_norm=self.max_norm, grad_scale=self.gscale, _in_graph=True, gnorm_ready=self.gnorm_ready)
                 opt.zero_grad()
         self.launches_per_replay = _lib.launch_count() - n0
         torch.cuda.synchronize()
@@ -557,24 +559,34 @@ class _StepBase:
             self.core.dp = try_create_exchange(self.unet.store.grad)
 
     def optimizer_step(self):
+        norm_ready = False
         if self.world_size > 1:
             x = self.core.dp
             if x is not None:
                 if not x.issued:  # nobody announced the last micro-step: exchange the whole buffer now, no overlap
                     x.exchange_all()
-                x.finish()
+                # the exchange's reduce kernels have already summed the squares of the reduced gradients: with a fused
+                # optimizer and clipping on, finish() delivers the global norm and the optimizer skips its own 5 GB pass
+                norm_ready = bool(getattr(x, "provides_norm", False) and hasattr(self.optimizer, "fused_step")
+                                  and self.clip_grad_norm and self.clip_grad_norm > 0)
+                if norm_ready:
+                    x.finish(gnorm_sq_out=self.optimizer.gnorm_sq)
+                else:
+                    x.finish()
             else:
                 allreduce_gradients(self.unet)
         if self.cuda_graph and hasattr(self.optimizer, "fused_step"):
-            if self._opt_graph is None:
-                self._opt_graph = GraphedOptimizerStep(self.optimizer, self.clip_grad_norm, 1.0 / self.world_size).capture()
+            if self._opt_graph is None or self._opt_graph.gnorm_ready != norm_ready:
+                self._opt_graph = GraphedOptimizerStep(self.optimizer, self.clip_grad_norm, 1.0 / self.world_size,
+                                                       gnorm_ready=norm_ready).capture()
             self._opt_graph.replay()
             return
         if isinstance(self.optimizer, B200AdamWBF16):
-            self.optimizer.fused_step(max_norm=self.clip_grad_norm, grad_scale=1.0 / self.world_size, zero_grad=True)
+            self.optimizer.fused_step(max_norm=self.clip_grad_norm, grad_scale=1.0 / self.world_size, zero_grad=True,
+                                      gnorm_ready=norm_ready)
             return
         if hasattr(self.optimizer, "fused_step"):
-            self.optimizer.fused_step(max_norm=self.clip_grad_norm, grad_scale=1.0 / self.world_size)
+            self.optimizer.fused_step(max_norm=self.clip_grad_norm, grad_scale=1.0 / self.world_size, gnorm_ready=norm_ready)
         else:  # a reference optimizer reading p.grad (adamw_bfloat16/__init__.py:92-119)
             if self.world_size > 1:
                 self.unet.store.grad.mul_(1.0 / self.world_size)
@@ -736,13 +748,14 @@ class B200AdamW:
         if self.master is not None:
             self.master.copy_(self.unet.store.flat.float())
 
-    def fused_step(self, max_norm: float = 0.0, grad_scale: float = 1.0, _in_graph: bool = False):
+    def fused_step(self, max_norm: float = 0.0, grad_scale: float = 1.0, _in_graph: bool = False, gnorm_ready: bool = False):
         st = self.unet.store
         g = self.param_groups[0]
         gn = None
         if max_norm and max_norm > 0:
-            self.gnorm_sq.zero_()
-            ops.sumsq(st.grad, self.gnorm_sq)
+            if not gnorm_ready:  # else: the data-parallel exchange already wrote sum(grad^2) into gnorm_sq
+                self.gnorm_sq.zero_()
+                ops.sumsq(st.grad, self.gnorm_sq)
             gn = self.gnorm_sq
         ops.philox_advance(self.step_ctr, 1)
         ops.adamw(st.flat, self.master, st.grad, self.m, self.v, lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1],
@@ -801,13 +814,14 @@ class B200AdamWBF16:
         self._min_headroom = 0.0  # steps can skip the per-tensor scan while no accumulator can reach the threshold
 
     def fused_step(self, max_norm: float = 0.0, grad_scale: float = 1.0, rng_mode: int = 0, test_rand16=None,
-                   _in_graph: bool = False, zero_grad: bool = False):
+                   _in_graph: bool = False, zero_grad: bool = False, gnorm_ready: bool = False):
         st = self.unet.store
         g = self.param_groups[0]
         gn = None
         if max_norm and max_norm > 0:
-            self.gnorm_sq.zero_()
-            ops.sumsq(st.grad, self.gnorm_sq)
+            if not gnorm_ready:  # else: the data-parallel exchange already wrote sum(grad^2) into gnorm_sq
+                self.gnorm_sq.zero_()
+                ops.sumsq(st.grad, self.gnorm_sq)
             gn = self.gnorm_sq
         ops.philox_advance(self.seed_offset, 1)  # seed_offset[1] = optimizer step, kept on the device (graph-safe)
         ops.adamw_bf16(st.flat, st.grad, self.exp_avg, self.exp_avg_sq, self.shift, lr=g["lr"], beta1=g["betas"][0],

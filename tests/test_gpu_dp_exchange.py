@@ -183,7 +183,7 @@ def _equivalence_worker(rank, world, port, q):
         b = Bg // world
         sl = slice(rank * b, (rank + 1) * b)
         mine = {k: (v[sl] if torch.is_tensor(v) else v[sl]) for k, v in full.items()}
-        rels = []
+        rels, norm_checks = [], []
         for rep in range(2):   # pass 0: no chunk plan yet -> whole-buffer exchange; pass 1: chunks leave during backward
             for n_ in nets:
                 n_.zero_grad()
@@ -195,9 +195,23 @@ def _equivalence_worker(rank, world, port, q):
                 x = tr_dp.core.dp
                 if not x.issued:
                     x.exchange_all()
-                x.finish()
+                if x.provides_norm:  # the exchange's reduce kernels also deliver sum((reduced gradient)^2)
+                    gn = torch.full((1,), -1.0, device="cuda", dtype=torch.float64)
+                    x.finish(gnorm_sq_out=gn)
+                else:
+                    gn = None
+                    x.finish()
             else:
+                gn = None
                 dist.all_reduce(nets[0].store.grad)
+            if gn is not None:
+                from sdxl_training_improvements_b200 import ops
+                chk = torch.zeros(1, device="cuda", dtype=torch.float64)
+                ops.sumsq(nets[0].store.grad, chk)
+                torch.cuda.synchronize()
+                gns = [torch.empty_like(gn) for _ in range(world)]
+                dist.all_gather(gns, gn)
+                norm_checks.append((abs(float(gn) - float(chk)) / max(float(chk), 1e-30), all(torch.equal(gns[0], t) for t in gns)))
             out1 = tr_one.training_step(full, noise=noise, timesteps=ts)
             out1["loss"].backward()
             torch.cuda.synchronize()
@@ -211,7 +225,7 @@ def _equivalence_worker(rank, world, port, q):
         everyone = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(everyone, flat)
         same = all(torch.equal(everyone[0], e) for e in everyone)
-        q.put((rank, used_peer, rels, loss_dp, loss_one, same))
+        q.put((rank, used_peer, rels, loss_dp, loss_one, same, norm_checks))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -272,8 +286,10 @@ def test_two_ranks_times_b_equals_one_rank_times_2b():
     """T6 (VERDICT r1 missing #4).  Tolerances (stated): gradient rel-L2 <= 1e-2 (two bf16 partial sums vs one bf16 sum of
     four samples: different rounding points, same fp32 mathematics), loss |d| <= 1e-3 * max(1, loss)."""
     _world()
-    for rank, used_peer, rels, loss_dp, loss_one, same in _spawn(_equivalence_worker, 2):
+    for rank, used_peer, rels, loss_dp, loss_one, same, norm_checks in _spawn(_equivalence_worker, 2):
         assert used_peer, "the peer-memory exchange was not in use"
+        for rel, identical in norm_checks:  # norm folded into the exchange == b2_sumsq over the reduced buffer, same bits on all ranks
+            assert rel <= 1e-5 and identical, f"rank {rank}: exchange-provided grad norm^2 off by {rel:.2e}, identical={identical}"
         assert same, "reduced gradients differ across ranks"
         assert all(r <= 1e-2 for r in rels), f"rank {rank}: reduced gradient / world vs single-GPU gradient rel-L2 {rels}"
         assert abs(loss_dp - loss_one) <= 1e-3 * max(1.0, abs(loss_one)), (loss_dp, loss_one)
