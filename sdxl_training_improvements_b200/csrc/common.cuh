@@ -79,9 +79,10 @@ __device__ __forceinline__ bf16x8 ld8(const bf16* p) {
 }
 __device__ __forceinline__ void st8(bf16* p, const bf16x8& v) { *reinterpret_cast<uint4*>(p) = v.u; }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// fast division (MUFU.RCP + multiply, 2 ulp): the IEEE divide is ~10 instructions in kernels that sit next to their HBM bound
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 __device__ __forceinline__ float dsilu_f(float x) {
-  float s = 1.f / (1.f + __expf(-x));
+  float s = __fdividef(1.f, 1.f + __expf(-x));
   return s * (1.f + x * (1.f - s));
 }
 
