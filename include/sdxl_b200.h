@@ -199,6 +199,12 @@ int b2_attn_set_debug(void* counters);
  * K / V: [B * n_k, ld] row-major views (head h = columns h*64..), sample stride k_bs / v_bs elements.
  * b2_xattn_q_core_ok(): C a multiple of 320, n_q a multiple of 256, n_k <= 80; other shapes: b2_gemm + b2_attn_fwd. */
 int b2_xattn_q_core_ok(int B, int n_q, int n_k, int C);
+/* Down-projection input gradient with the GEGLU backward in its epilogue: du[M, 2F] from dy[M, C], W2[C, F] (row-major Linear
+ * weight [out = C, in = F]) and u[M, 2F] = [h | g]; dz is never stored.  Bit-identical to b2_gemm(dgrad) + b2_geglu_bwd.
+ * replaces: autograd of diffusers FeedForward.net[2] (Linear) + GEGLU.forward's `hidden_states * self.gelu(gate)`. */
+int b2_linear_dgrad_geglu_ok(int M, int F, int C);
+int b2_linear_dgrad_geglu(const void* dy, const void* W2, const void* u, void* du, int M, int F, int C, int64_t ldy,
+                          int64_t ldw, int64_t ldu, int64_t lddu, void* stream);
 int b2_gemm2_set_debug(void* buf);  /* clock64 trace buffer (>= 192 uint64) for tools/geglu_trace.py; NULL disables */
 int b2_xattn_set_debug(void* stamps); /* profiling hook: >= 32 uint64 clock64 stamps of CTA 0's first tile; NULL = off */
 int b2_xattn_q_core(const void* xn, const void* Wq, const void* K, const void* V, void* Q, void* O, float* LSE, int B, int n_q,

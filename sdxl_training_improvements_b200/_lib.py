@@ -60,6 +60,8 @@ SIGNATURES = {
     "b2_xattn_bwd_ok": [i32, i32, i32, i32],
     "b2_xattn_bwd": [C.POINTER(AttnArgs), c_p],
     "b2_xattn_q_core_ok": [i32, i32, i32, i32],
+    "b2_linear_dgrad_geglu_ok": [i32, i32, i32],
+    "b2_linear_dgrad_geglu": [c_p, c_p, c_p, c_p, i32, i32, i32, i64, i64, i64, i64, c_p],
     "b2_gemm2_set_debug": [c_p],
     "b2_xattn_set_debug": [c_p],
     "b2_xattn_q_core": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, f32, c_p],

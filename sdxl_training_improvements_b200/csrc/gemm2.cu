@@ -34,7 +34,7 @@ constexpr int G2_WIDE_BN = 320;
 constexpr int G2_WIDE_STAGES = 5;
 constexpr int G2_WIDE_STAGE_BYTES = G2_A_BYTES + (G2_WIDE_BN / 2) * G2_BK * 2;  // 16 KiB A + 20 KiB B half
 static_assert(G2_WIDE_STAGES * G2_WIDE_STAGE_BYTES + 2 * G2_EPI_BYTES + 1024 <= G2_SMEM, "wide mode must fit the same smem budget");
-static_assert((G2_STAGES - 1) * G2_STAGE_BYTES + 3 * G2_EPI_BYTES + 1024 <= G2_SMEM, "GEGLU mode: 5 stages + 3 staging tiles");
+static_assert((G2_STAGES - 1) * G2_STAGE_BYTES + 4 * G2_EPI_BYTES + 1024 <= G2_SMEM, "GEGLU modes: 5 stages + 3 (forward) / 4 (backward) staging tiles");
 constexpr int G2_TMEM_COLS = 512;
 
 struct Gemm2P {
@@ -77,6 +77,16 @@ struct Gemm2P {
   // rounds both to bf16 exactly as the un-fused path stores them, writes them to u (the backward pass needs both) and
   // writes bf16(h * gelu(g)) to Z — the separate GEGLU kernel's 2F-wide re-read of u disappears.
   int geglu, gg_F;
+  // GEGLU-backward mode (b2_linear_dgrad_geglu): the GEMM is the down-projection's input gradient dz[M, F] = dy W2; the
+  // epilogue never stores dz — per 64-column chunk it fetches the matching h and g tiles of u = [h | g] by TMA (tmR maps u),
+  // forms dh = dz g Phi(g), dg = dz h (Phi(g) + g phi(g)) in place and stores both into du (tmD maps du[M, 2F]): the separate
+  // GEGLU-backward kernel's pass over dz, u and du (210 MB per transformer block at 1024 px) shrinks to the u read + du write.
+  // Two staging tiles per epilogue group (four in all, mainloop on 5 stages); needs both epilogue groups.  Traced
+  // (tools/geglu_trace.py): per chunk ~1.5k cycles store drain + 2.5-3.4k until the u tiles arrive + 4.7k math (issue-bound:
+  // two epilogue warps per scheduler) and the mainloop slows to ~18k cycles per tile under the extra shared-memory / TMA
+  // traffic; an L2 prefetch of the u boxes did not shorten the arrival (it is TMA-queue / smem-write bound, not HBM latency)
+  // and was removed.  75 us against 41 (dgrad) + 53 (gate-backward kernel) at M=4096, F=5120, C=1280.
+  int gbwd;
   int res_prefetch;  // 1: residual tiles travel one chunk ahead (default); B2_GEMM_NO_RES_PREFETCH=1 restores the per-chunk load
   int epi_groups;    // 2 (default): both epilogue warp groups work; 1: warps 6-9 idle (B2_GEMM_EPI_GROUPS=1, for A/B runs)
   unsigned long long* dbg;  // optional clock64 trace of cluster 0 / CTA 0 (b2_gemm2_set_debug, tools/geglu_trace.py); NULL in production
@@ -164,7 +174,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
-    if (p.has_res) tma_prefetch_desc(&tmR);
+    if (p.has_res || p.gbwd) tma_prefetch_desc(&tmR);
 #pragma unroll
     for (int s = 0; s < G2_STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
@@ -491,8 +501,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const bf16x8 ph = pack8(fh), pg = pack8(fg);
               unpack8(ph, fh);   // the GEGLU product is formed from the bf16 values u holds (as geglu_fwd_kernel does)
               unpack8(pg, fg);
+              float cdf[8], pdf[8];
+              gelu_parts8(fg, cdf, pdf);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) fh[j] *= gelu_erf(fg[j]);
+              for (int j = 0; j < 8; ++j) fh[j] *= fg[j] * cdf[j];  // h * gelu(g), gelu(g) = g * Phi(g) as gelu_erf forms it
               const bf16x8 pz = pack8(fh);
               const uint32_t saddr = srow + ((g ^ (row & 7)) << 4);
               asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(ph.u.x), "r"(ph.u.y), "r"(ph.u.z),
@@ -513,6 +525,70 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_store_commit();
           }
           if (tr) p.dbg[tile_i * 8 + 4 + 3 * (c0 >> 6)] = g2_clk();
+        }
+      } else if (p.gbwd) {
+        for (int c0 = c_first; c0 < ncols; c0 += c_step) {  // ncols is a multiple of 64 (F % 128 == 0): full chunks only
+          const int n0 = n_tile + c0;
+          uint32_t v0[32], v1[32];
+          tmem_ld32_nowait(tacc + c0, v0);
+          tmem_ld32_nowait(tacc + c0 + 32, v1);
+          const uint32_t stage_h = smem_epi + (uint32_t)(grp * 2) * G2_EPI_BYTES, stage_g = stage_h + G2_EPI_BYTES;
+          if (et == 0) {
+            tma_store_wait_read<0>();  // this group's previous two stores have read the tiles
+            mbar_expect_tx(smem_u32(&bar_res[grp]), 2 * G2_EPI_BYTES);
+            tma_load_2d(stage_h, &tmR, smem_u32(&bar_res[grp]), n0, m_base);
+            tma_load_2d(stage_g, &tmR, smem_u32(&bar_res[grp]), p.gg_F + n0, m_base);
+          }
+          if (tr && c0 < 256) p.dbg[tile_i * 8 + 2 + 3 * (c0 >> 7)] = g2_clk();
+          mbar_wait(smem_u32(&bar_res[grp]), res_uses[grp] & 1);
+          res_uses[grp]++;
+          tmem_ld_wait();
+          if (c0 + c_step >= ncols) release_acc(buf);
+          if (tr && c0 < 256) p.dbg[tile_i * 8 + 3 + 3 * (c0 >> 7)] = g2_clk();
+          const uint32_t srow = row * 128;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {  // four column groups at a time: their eight shared-memory reads up front
+            bf16x8 hv[4], gv[4];
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const uint32_t so = srow + (((hf * 4 + g4) ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(hv[g4].u.x), "=r"(hv[g4].u.y), "=r"(hv[g4].u.z), "=r"(hv[g4].u.w) : "r"(stage_h + so));
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(gv[g4].u.x), "=r"(gv[g4].u.y), "=r"(gv[g4].u.z), "=r"(gv[g4].u.w) : "r"(stage_g + so));
+            }
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const uint32_t* v = (hf ? v1 : v0) + g4 * 8;
+              float d[8], fh[8], fg[8], dh[8], dg[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d[j] = __uint_as_float(v[j]);
+              unpack8(pack8(d), d);  // dz as the un-fused path stores it (bf16): same bits downstream
+              unpack8(hv[g4], fh);
+              unpack8(gv[g4], fg);
+              float cdf[8], pdf[8];
+              gelu_parts8(fg, cdf, pdf);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                dh[j] = d[j] * fg[j] * cdf[j];
+                dg[j] = d[j] * fh[j] * fmaf(fg[j], pdf[j], cdf[j]);
+              }
+              const bf16x8 oh = pack8(dh), og = pack8(dg);
+              const uint32_t so = srow + (((hf * 4 + g4) ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage_h + so), "r"(oh.u.x), "r"(oh.u.y), "r"(oh.u.z),
+                           "r"(oh.u.w) : "memory");
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage_g + so), "r"(og.u.x), "r"(og.u.y), "r"(og.u.z),
+                           "r"(og.u.w) : "memory");
+            }
+          }
+          if (tr && c0 < 256) p.dbg[tile_i * 8 + 4 + 3 * (c0 >> 7)] = g2_clk();
+          fence_proxy_async_smem();
+          gbar();
+          if (et == 0) {
+            tma_store_2d(&tmD, stage_h, n0, m_base);
+            tma_store_2d(&tmD, stage_g, p.gg_F + n0, m_base);
+            tma_store_commit();
+          }
         }
       } else
       for (int c0 = c_first; c0 < ncols; c0 += c_step) {
@@ -768,7 +844,7 @@ static int gemm2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   static const bool no_res_prefetch = getenv("B2_GEMM_NO_RES_PREFETCH") != nullptr;
   p.res_prefetch = no_res_prefetch ? 0 : 1;
   p.wide = p.BN == G2_WIDE_BN ? 1 : 0;
-  p.stages = p.wide ? G2_WIDE_STAGES : p.geglu ? G2_STAGES - 1 : G2_STAGES;  // GEGLU: 5 stages + a third staging tile
+  p.stages = p.wide ? G2_WIDE_STAGES : (p.geglu || p.gbwd) ? G2_STAGES - 1 : G2_STAGES;  // GEGLU modes: 5 stages + extra staging tiles
   p.stage_bytes = p.wide ? G2_WIDE_STAGE_BYTES : G2_STAGE_BYTES;
   if (p.splits > 1) p.has_res = 0;  // the reduce-add epilogue is the accumulation
   p.dbg = g_g2_dbg;
@@ -923,6 +999,36 @@ extern "C" int b2_linear_geglu(const void* x, const void* W1, const void* b1, vo
   p.D = reinterpret_cast<bf16*>(u); p.ldd = ldu;
   p.geglu = 1; p.gg_F = F;
   return gemm2_launch(ta, tb, td, td, p, st, "b2_linear_geglu", &tz);
+}
+
+extern "C" int b2_linear_dgrad_geglu_ok(int M, int F, int C) {
+  if (getenv("B2_GEGLU_BWD_UNFUSED")) return 0;
+  if (getenv("B2_GEMM_EPI_GROUPS") && atoi(getenv("B2_GEMM_EPI_GROUPS")) == 1) return 0;  // needs both epilogue groups
+  return M >= 256 && F >= 256 && (F % 128) == 0 && C >= 64 && (C % 8) == 0;
+}
+
+// du[M, 2F] = GEGLU-backward( dz = dy[M, C] @ W2[C, F], u[M, 2F] ): the down-projection's dgrad GEMM with the gate's backward
+// in its epilogue (replaces b2_gemm(dgrad) + b2_geglu_bwd; diffusers GEGLU.forward: hidden_states * gelu(gate)).
+extern "C" int b2_linear_dgrad_geglu(const void* dy, const void* W2, const void* u, void* du, int M, int F, int C, int64_t ldy,
+                                     int64_t ldw, int64_t ldu, int64_t lddu, void* stream) {
+  B2_REQUIRE(dy && W2 && u && du, "b2_linear_dgrad_geglu: null pointer");
+  B2_REQUIRE(b2_linear_dgrad_geglu_ok(M, F, C), "b2_linear_dgrad_geglu: unsupported shape M=%d F=%d C=%d (use b2_gemm + b2_geglu_bwd)",
+             M, F, C);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap ta, tb, td, tr;
+  int rc;
+  if ((rc = make_map_2d(&ta, dy, C, M, ldy, 64, 128, "dgrad_geglu dy"))) return rc;
+  if ((rc = make_map_2d(&tb, W2, F, C, ldw, 64, 64, "dgrad_geglu W2(mn)"))) return rc;
+  if ((rc = make_map_2d(&td, du, 2ull * F, M, lddu, 64, 128, "dgrad_geglu du"))) return rc;
+  if ((rc = make_map_2d(&tr, u, 2ull * F, M, ldu, 64, 128, "dgrad_geglu u"))) return rc;
+  Gemm2P p{};
+  p.M = M; p.N = F; p.K = C; p.BN = 256;
+  p.a_mn = 0; p.b_mn = 1;
+  p.alpha = 1.f;
+  p.bias_rows_per_group = 0x7fffffff;
+  p.D = reinterpret_cast<bf16*>(du); p.ldd = lddu;
+  p.gbwd = 1; p.gg_F = F;
+  return gemm2_launch(ta, tb, td, tr, p, st, "b2_linear_dgrad_geglu");
 }
 
 extern "C" int b2_conv3x3_implicit_ok(int B, int H, int W, int Cin, int Cout) {

@@ -268,6 +268,22 @@ def xattn_q_core(xn, Wq, k, v, B, n_q, n_k, scale):
     return q, o, lse
 
 
+def linear_dgrad_geglu_ok(M, F, C) -> bool:
+    return bool(_lib.load().b2_linear_dgrad_geglu_ok(int(M), int(F), int(C)))
+
+
+def linear_dgrad_geglu(dy, W2, u, F):
+    """du[M, 2F]: the down-projection's input gradient dz = dy @ W2 pushed through the GEGLU backward in the GEMM epilogue
+    (dz itself is never stored).  dy [M, C], W2 [C, F] (Linear weight, row-major), u [M, 2F] = [h | g]."""
+    _need_cuda(dy, W2, u)
+    M, Cc = dy.shape
+    du = torch.empty_like(u)
+    _lib.check(_lib.load().b2_linear_dgrad_geglu(_p(dy), _p(W2), _p(u), _p(du), int(M), int(F), int(Cc), int(dy.stride(0)),
+                                                 int(W2.stride(0)), int(u.stride(0)), int(du.stride(0)), _stream()),
+               "linear_dgrad_geglu")
+    return du
+
+
 def linear_geglu_ok(M, F, K) -> bool:
     return bool(_lib.load().b2_linear_geglu_ok(int(M), int(F), int(K)))
 

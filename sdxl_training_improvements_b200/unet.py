@@ -416,12 +416,38 @@ class UNetEngine:
             z = Act(ops.geglu_fwd(u.d, 4 * Cc))
 
         def geglu_bwd():
+            if u.g is not None:  # the down-projection's dgrad GEMM already pushed dz through the gate (see _linear_ff2)
+                return
             # the up-projection's bias gradient (column sums of du) falls out of the same pass; its Linear closure skips it
             u.g = ops.geglu_bwd(u.d, z.g, 4 * Cc, dbias32=self.store.gs(f"{pfx}.ff.net.0.proj.bias"))
             u.bias_grad_done = True
 
         self.tape.append(geglu_bwd)
+        if ops.linear_dgrad_geglu_ok(z.d.shape[0], 4 * Cc, Cc):
+            return self._linear_ff2(z, u, f"{pfx}.ff.net.2.weight", f"{pfx}.ff.net.2.bias", Cc, 4 * Cc, h2)
         return self.linear(z, f"{pfx}.ff.net.2.weight", Cc, 4 * Cc, f"{pfx}.ff.net.2.bias", residual=h2)
+
+    def _linear_ff2(self, z: Act, u: Act, wname: str, bname: str, N: int, F: int, residual: Act) -> Act:
+        """FeedForward down-projection whose backward fuses the GEGLU backward into the input-gradient GEMM: du = f(dy W2, u)
+        comes out of the dgrad epilogue (csrc/gemm2.cu, GEGLU-backward mode); dz is never written and the gate's own
+        backward closure finds u.g already filled."""
+        st = self.store
+        Wt = st.w(wname, N, F)
+        y = ops.linear_fwd(z.d, Wt, bias=st.v(bname), residual=residual.d)
+        out = Act(y)
+
+        def bwd():
+            dy = out.g
+            gW, gb = st.g(wname, N, F), st.gs(bname)
+            with self._side_branch():  # weight + bias gradients beside the input gradient
+                ops.linear_wgrad(dy, z.d, gW, accumulate=True)
+                ops.colsum_f32(dy, gb)
+            u.g = ops.linear_dgrad_geglu(dy, Wt, u.d, F)
+            self._join()
+            self._add_grad(residual, dy)
+
+        self.tape.append(bwd)
+        return out
 
     def transformer(self, x: Act, B, H, W, Cc, depth, pfx, ctx, n_ctx) -> Act:
         a = self.groupnorm(x, B, H * W, Cc, f"{pfx}.norm.weight", f"{pfx}.norm.bias", 1e-6, False)

@@ -364,6 +364,27 @@ def test_softmax(ops, rows, n):
     _close(dS[:, :n], refd, atol=1e-3, what="softmax bwd")
 
 
+@pytest.mark.parametrize("M,F,Cc", [(4096, 5120, 1280), (16384, 2560, 640), (1000, 384, 128), (256, 256, 64)])
+def test_dgrad_with_geglu_backward_epilogue_is_bit_identical(ops, M, F, Cc):
+    """b2_linear_dgrad_geglu == b2_gemm(dgrad of the down-projection) + b2_geglu_bwd, bit for bit (dz is rounded to bf16 in the
+    epilogue exactly where the un-fused path stores it); and against fp32 torch for the whole expression."""
+    assert ops.linear_dgrad_geglu_ok(M, F, Cc)
+    dy = _rand(M, Cc, seed=31)
+    W2 = _rand(Cc, F, scale=1 / math.sqrt(F), seed=32)
+    u = _rand(M, 2 * F, seed=33)
+    dz = ops.linear_dgrad(dy, W2)                 # [M, F]
+    ref = ops.geglu_bwd(u, dz, F)
+    got = ops.linear_dgrad_geglu(dy, W2, u, F)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref), f"{int((got != ref).sum())} of {ref.numel()} elements differ"
+    h, g = u[:, :F].float(), u[:, F:].float()
+    dzf = (dy.float() @ W2.float())
+    cdf = 0.5 * (1 + torch.erf(g / math.sqrt(2)))
+    pdf = torch.exp(-0.5 * g * g) / math.sqrt(2 * math.pi)
+    _close(got[:, :F], dzf * g * cdf, atol=3e-2, what="dh")
+    _close(got[:, F:], dzf * h * (cdf + g * pdf), atol=3e-2, what="dg")
+
+
 @pytest.mark.parametrize("M,F", [(4096, 5120), (300, 128), (1003, 2560), (64, 40)])
 def test_geglu_bwd_with_bias_column_sums(ops, M, F):
     """b2_geglu_bwd_bias: du identical to b2_geglu_bwd, and db32 += column sums of the bf16 du (what b2_colsum_f32 over du gives)."""

@@ -89,3 +89,24 @@ for (M2, N2, K2, res, bmn) in ((4096, 1280, 1280, True, False), (4096, 1280, 128
           f"mainloop {K2 // 64 * (640 if N2 % 320 == 0 and not bmn else 512)} tensor cycles")
     print(f"   cycles from kernel entry (cluster 0): set-up done {t[191] - e0}, dependency wait done {t[190] - e0}, MMA thread has accumulator {m[1] - e0}, "
           f"last MMA issued {m[2] - e0}, epilogue sees accumulator {ep[1] - e0}, last store issued {t[189] - e0}, stores complete {t[188] - e0}")
+
+
+# GEGLU-backward mode (dgrad of the down-projection + gate backward in the epilogue): group 0's two chunks of each tile
+M3, F3, C3 = 4096, 5120, 1280
+dy3 = torch.randn(M3, C3, device="cuda").to(bf)
+W3 = (torch.randn(C3, F3, device="cuda") * 0.02).to(bf)
+u3 = torch.randn(M3, 2 * F3, device="cuda").to(bf)
+for _ in range(3):
+    ops.linear_dgrad_geglu(dy3, W3, u3, F3)
+torch.cuda.synchronize()
+buf.zero_()
+_lib.load().b2_gemm2_set_debug(buf.data_ptr())
+ops.linear_dgrad_geglu(dy3, W3, u3, F3)
+torch.cuda.synchronize()
+_lib.load().b2_gemm2_set_debug(None)
+t = buf.tolist()
+print("dgrad + GEGLU backward epilogue, group 0 (chunks 0 and 2 of each 256-column tile):")
+for i in range(1, 5):
+    r, r1, m = t[i * 8:i * 8 + 8], t[(i + 1) * 8:(i + 1) * 8 + 2], t[128 + i * 4:128 + i * 4 + 3]
+    print(f"  tile {i}: acc wait {r[1] - r[0]:6d} | chunk 0: drain + issue loads {r[2] - r[1]:5d}, u tiles arrive {r[3] - r[2]:5d}, math {r[4] - r[3]:5d} | "
+          f"chunk 2: fence+bar+store+drain+issue {r[5] - r[4]:5d}, arrive {r[6] - r[5]:5d}, math {r[7] - r[6]:5d} | to next tile {r1[0] - r[7]:5d} | MMA waits {m[1] - m[0]:6d} issues {m[2] - m[1]:6d}")
