@@ -63,8 +63,10 @@ class RecordingExchange:
         self.calls.append(("all",))
         self.issued = True
 
-    def finish(self):
-        self.calls.append(("finish",))
+    provides_norm = False  # set True by the test of the norm hand-off
+
+    def finish(self, gnorm_sq_out=None):
+        self.calls.append(("finish",) if gnorm_sq_out is None else ("finish+norm", gnorm_sq_out))
         self.issued = False
 
 
@@ -79,7 +81,8 @@ def rig(monkeypatch):
     opt = trainer_mod.B200AdamW(net, lr=1e-3)
     scales = []
     real_fused = opt.fused_step
-    opt.fused_step = lambda **kw: (scales.append(kw.get("grad_scale")), x.calls.append(("update",)))[0]
+    opt.fused_step = lambda **kw: (scales.append(kw.get("grad_scale")),
+                                   x.calls.append(("update",) if not kw.get("gnorm_ready") else ("update", "norm from exchange")))[0]
     conf = SimpleNamespace(model=SimpleNamespace(num_timesteps=1000, sigma_min=0.002, sigma_max=20000.0, use_ztsnr=True,
                                                  min_snr_gamma=None),
                            training=SimpleNamespace(method="ddpm", prediction_type="v_prediction",
@@ -136,3 +139,23 @@ def test_unannounced_step_still_exchanges_once(rig):
     assert x.calls == [], "without the announcement nothing may be exchanged during backward"
     tr.optimizer_step()
     assert x.calls == [("all",), ("finish",), ("update",)]
+
+
+def test_exchange_hands_the_gradient_norm_to_the_fused_optimizer(rig):
+    """Copy-engine transports sum (reduced gradient)^2 inside their reduce kernels: finish() must then be given the optimizer's
+    gnorm_sq buffer and the fused step must be told to skip its own pass — and neither when clipping is off or the transport
+    cannot provide it (clip_grad_norm_, flow_matching_trainer.py:181-186, needs the norm of the REDUCED gradients)."""
+    tr, x, batch = rig.tr, rig.x, rig.batch
+    x.provides_norm = True
+    tr._execute_training_step(batch)
+    assert x.calls[-2][0] == "finish+norm" and x.calls[-2][1] is tr.optimizer.gnorm_sq
+    assert x.calls[-1] == ("update", "norm from exchange")
+    x.calls.clear()
+    tr.clip_grad_norm = 0.0           # no clipping: nobody needs a norm
+    tr._execute_training_step(batch)
+    assert x.calls[-2:] == [("finish",), ("update",)]
+    x.calls.clear()
+    tr.clip_grad_norm = 1.0
+    x.provides_norm = False           # e.g. the "sm" transport
+    tr._execute_training_step(batch)
+    assert x.calls[-2:] == [("finish",), ("update",)]
