@@ -165,3 +165,54 @@ def test_adamw_bf16_optimizer_class_on_tiny_unet(ops):
             assert bad <= max(8, got.numel() // 2000), f"step {step} {name}: {bad} elements differ"
             assert float((gotf - want).abs().max()) <= 2 ** -6 * float(want.abs().max())
     assert opt.state_dict()["state"]["conv_in.weight"]["exp_avg"].numel() == 64 * 4 * 9
+
+
+def test_adamw_random_bits_match_the_numpy_restatement(ops):
+    """Pins the kernel's counter hash to tests/test_adamw_hash_cpu.py bit for bit: with g = 0 and exp_avg = 0 the parameter and
+    the shift are rounded with the two halves of the SECOND random word, and with a plain gradient exp_avg is rounded with the
+    low half of the FIRST — all three predicted exactly from the numpy hash (stochastic/__init__.py:46-71: add 16 random bits
+    below the bf16 mantissa, truncate)."""
+    import numpy as np
+    from test_adamw_hash_cpu import keys, rand64
+    n = 1 << 16
+    seed, step = 1234567891234, 9
+    g = torch.Generator(device="cuda").manual_seed(11)
+    p0 = (torch.randn(n, device="cuda", generator=g) * 0.05).to(bf16)
+    s0 = (torch.randn(n, device="cuda", generator=g) * 3e-4).to(bf16)
+    v0 = (torch.rand(n, device="cuda", generator=g) * 1e-4).to(bf16)
+    z = torch.zeros(n, device="cuda", dtype=bf16)
+    so = torch.tensor([seed, 0], device="cuda", dtype=torch.int64)
+    ka, kb = keys(seed, step)
+    r01, r23 = rand64(np.arange(n, dtype=np.uint64), ka, kb)
+    r01, r23 = r01.astype(np.uint32), r23.astype(np.uint32)
+
+    def bits(t):
+        return t.float().cpu().numpy().view(np.uint32)
+
+    def sr(x32, r16):   # x32: float32 array
+        return ((x32.view(np.uint32).astype(np.uint64) + r16.astype(np.uint64)) & np.uint64(0xFFFF0000)).astype(np.uint32)
+
+    def rn_bf16(x32):
+        b = x32.view(np.uint32).astype(np.uint64)
+        return (((b + np.uint64(0x7FFF) + ((b >> np.uint64(16)) & np.uint64(1))) >> np.uint64(16)) << np.uint64(16)).astype(np.uint32)
+
+    # ---- second word: p <- SR(p + shift, r23 low), shift <- SR(bf16(p_old - p_new) + shift, r23 high)
+    p, m, v, sh = p0.clone(), z.clone(), v0.clone(), s0.clone()
+    ops.adamw_bf16(p, z, m, v, sh, lr=1e-3, step=step, seed_offset=so)
+    pf, sf = p0.float().cpu().numpy(), s0.float().cpu().numpy()
+    p_pred = sr((sf + pf).astype(np.float32), r23 & np.uint32(0xFFFF))
+    assert np.array_equal(bits(p), p_pred), f"{int((bits(p) != p_pred).sum())} parameters differ from the numpy prediction"
+    d = rn_bf16((pf - p_pred.view(np.float32)).astype(np.float32)).view(np.float32)
+    s_pred = sr((d + sf).astype(np.float32), r23 >> np.uint32(16))
+    assert np.array_equal(bits(sh), s_pred), f"{int((bits(sh) != s_pred).sum())} shift values differ from the numpy prediction"
+    # ---- first word, low half: exp_avg <- SR(g + (1 - b1) * bf16(b1 * exp_avg), r01 low)   (operand order as written)
+    gr = (torch.randn(n, device="cuda", generator=g) * 1e-2).to(bf16)
+    m0 = (torch.randn(n, device="cuda", generator=g) * 1e-2).to(bf16)
+    p, m, v, sh = p0.clone(), m0.clone(), v0.clone(), s0.clone()
+    ops.adamw_bf16(p, gr.clone(), m, v, sh, lr=1e-3, step=step, seed_offset=so)
+    b1, omb1 = np.float32(0.9), np.float32(1.0 - 0.9)
+    m1 = rn_bf16((m0.float().cpu().numpy().astype(np.float64) * np.float64(b1)).astype(np.float32)).view(np.float32)
+    # fma = one rounding of the exact a*b + c: the 32-bit product plus an 8-bit addend is exact in 64-bit extended precision
+    mr = (np.longdouble(omb1) * m1.astype(np.longdouble) + gr.float().cpu().numpy().astype(np.longdouble)).astype(np.float32)
+    m_pred = sr(mr, r01 & np.uint32(0xFFFF))
+    assert np.array_equal(bits(m), m_pred), f"{int((bits(m) != m_pred).sum())} exp_avg values differ from the numpy prediction"
